@@ -1,0 +1,230 @@
+"""ADVI -- the drop-in shell around the fused CUDA ELBO engine.
+
+Mirrors bijax's class surface:
+  * v1 (README.md:113, the surface north_star names):  ADVI(prior, bijector, log_likelihood_fn, vi_type="mean_field")
+  * v2 (bijax/advi.py:26-34):  ADVI(prior, likelihood_fn, prior_constraints, vi_type, rank, ordered_posterior_bijectors)
+  * .init(seed[, initializer])                    advi.py:77-78  (+ utils.py:39-55)
+  * .loss_fn(params, outputs, inputs, full_data_size, seed, n_samples=1)     advi.py:80-95
+  * .apply(params) == .get_params_posterior(params)                          advi.py:97-100
+
+What runs underneath is NOT the reference's op-by-op graph: ``loss_fn`` enqueues one fused step (bjx_elbo_step) that
+returns the loss and every gradient; the returned scalar carries a custom autograd node (the jax.custom_vjp analogue)
+whose backward just scales the saved gradients.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, Optional, Tuple
+
+import torch
+
+from . import _native as nv
+from . import bijectors as tfb
+from . import likelihoods as lk
+from . import random as brandom
+from .engine import ElboEngine
+from .spec import compile_latents, fill_in_bijector
+from .tree import tree_flatten, tree_unflatten
+
+_POSTERIOR_KEYS = ("posterior", "approx_posterior")
+
+
+def _scale_key(vi_type: str) -> str:
+    return "scale_diag" if vi_type == "mean_field" else "scale_tril"
+
+
+class _ElboFunction(torch.autograd.Function):
+    """custom_vjp: forward computes loss AND all gradients in one launch sequence; backward = cotangent x residuals."""
+
+    @staticmethod
+    def forward(ctx, loc, raw, kw, run):
+        out = run(loc.detach(), raw.detach(), kw.detach() if kw is not None else None)
+        ctx.save_for_backward(out)
+        ctx.shapes = (loc.shape, raw.shape, None if kw is None else kw.shape)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        ls, rs, ks = ctx.shapes
+        D, P = math.prod(ls), math.prod(rs)
+        d_loc = (g * out[1 : 1 + D]).reshape(ls)
+        d_raw = (g * out[1 + D : 1 + D + P]).reshape(rs)
+        d_kw = (g * out[1 + D + P :]).reshape(ks) if ks is not None else None
+        return d_loc, d_raw, d_kw, None
+
+
+class ADVI:
+    def __init__(self, prior: Dict[str, Any], *args, vi_type: str = "mean_field", rank: Optional[int] = None,
+                 ordered_posterior_bijectors=None, bijector=None, log_likelihood_fn=None, likelihood_fn=None,
+                 prior_constraints=None, device=None, precision: str = "auto"):
+        # positional forms: v1 (prior, bijector, log_likelihood_fn[, vi_type]); v2 (prior, likelihood_fn[, prior_constraints[, vi_type]])
+        args = list(args)
+        if args:
+            if isinstance(args[0], dict):
+                bijector = args.pop(0)
+                if args:
+                    log_likelihood_fn = args.pop(0)
+            else:
+                likelihood_fn = args.pop(0)
+                if args and (isinstance(args[0], dict) or args[0] is None):
+                    prior_constraints = args.pop(0)
+            if args and isinstance(args[0], str):
+                vi_type = args.pop(0)
+            if args:
+                raise TypeError("too many positional arguments")
+        constraints = bijector if bijector is not None else prior_constraints
+        if constraints is None:
+            constraints = {}
+        likelihood = log_likelihood_fn if log_likelihood_fn is not None else likelihood_fn
+        if likelihood is None:
+            raise TypeError("a likelihood is required (log_likelihood_fn= / likelihood_fn=)")
+
+        self.prior = prior
+        self.prior_constraints = fill_in_bijector(constraints, self.prior)  # core.py:107-111
+        self.bijector = self.prior_constraints
+        assert self.prior_constraints.keys() == self.prior.keys(), (
+            "The keys in `prior` and `prior_constraints` must be the same."
+        )
+        assert (vi_type == "low_rank") == (rank is not None), "`rank` must be specified only if `vi_type` is `low_rank`."
+        if vi_type == "low_rank":
+            raise NotImplementedError("low_rank is outside the fused hot path (SURVEY.md section 2, row 2); use mean_field or full_rank")
+        if vi_type not in ("mean_field", "full_rank"):
+            raise ValueError(f"unknown vi_type {vi_type!r}")
+        if not isinstance(likelihood, lk.Likelihood):
+            raise NotImplementedError(
+                "arbitrary python log_likelihood_fn callables are not on the fused CUDA path; pass one of "
+                "bijax_b200.likelihoods.{BernoulliLogits, GaussianLinear, BernoulliProbs}"
+            )
+        self.likelihood_fn = self.log_likelihood_fn = likelihood
+        self.vi_type = vi_type
+        self.rank = rank
+        # default parameter bijectors: [Identity, Exp] mean field (core.py:180-181), [Identity, Identity] full rank (core.py:205-206)
+        if ordered_posterior_bijectors is None:
+            ordered_posterior_bijectors = [tfb.Identity(), tfb.Exp() if vi_type == "mean_field" else tfb.Identity()]
+        if type(ordered_posterior_bijectors[0]).__name__ != "Identity":
+            raise NotImplementedError("only Identity is supported on the location parameter")
+        self.posterior_params_bijector = ordered_posterior_bijectors
+        self.latents = compile_latents(self.prior, self.prior_constraints)
+        self.size = self.latents.size
+        self.unravel_fn = self.latents.unravel
+        self.device = device
+        self.precision = precision
+        self._engines: Dict[Tuple, ElboEngine] = {}
+        self._group = None  # torch.distributed process group for row-sharded data (see parallel.py)
+        self._global_len: Optional[int] = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def init(self, seed, initializer: Optional[Callable] = None):
+        """advi.py:77-78: raw params = initializer(seed, (P,)), default normal(stddev=1), unraveled in (loc, scale) order."""
+        D = self.size
+        P = D if self.vi_type == "mean_field" else D * D
+        flat = brandom.normal(seed, (D + P,)) if initializer is None else initializer(seed, (D + P,))
+        scale = flat[D:].reshape((D,) if self.vi_type == "mean_field" else (D, D))
+        return {"posterior": {"loc": flat[:D].clone(), _scale_key(self.vi_type): scale.clone()}}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _split_params(self, params):
+        key = next((k for k in _POSTERIOR_KEYS if k in params), None)
+        if key is None:
+            raise KeyError(f"params needs one of {_POSTERIOR_KEYS}")
+        post = params[key]
+        if isinstance(post, dict):
+            loc = post["loc"]
+            raw = post.get("scale_diag", post.get("scale_tril", post.get("scale")))
+        else:  # an object with attributes (e.g. a tfd distribution holding raw leaves, as the reference's init returns)
+            loc = post.loc
+            raw = getattr(post, "scale_diag", None)
+            if raw is None:
+                raw = getattr(post, "scale_tril")
+        kwargs = {k: v for k, v in params.items() if k != key}
+        return loc, raw, kwargs
+
+    def _engine_for(self, kwargs) -> Tuple[ElboEngine, list]:
+        names = sorted(kwargs)
+        leaves = []
+        layout = []
+        for n in names:
+            ls, _ = tree_flatten(kwargs[n])
+            numel = sum(int(l.numel()) for l in ls)
+            layout.append((n, numel))
+            leaves.extend(ls)
+        sig = tuple(layout)
+        if sig not in self._engines:
+            self._engines[sig] = ElboEngine(self.latents, self.likelihood_fn, self.vi_type, self.posterior_params_bijector[1],
+                                            layout, device=self.device, precision=self.precision)
+        return self._engines[sig], leaves
+
+    def distributed(self, group=None, global_len: Optional[int] = None):
+        """Row-sharded data parallelism: ``outputs`` / ``inputs`` passed to loss_fn are this rank's shard; one all-reduce
+        of the packed [loss | grads] buffer per step."""
+        import torch.distributed as dist
+
+        self._group = group if group is not None else dist.group.WORLD
+        self._global_len = global_len
+        return self
+
+    def _run(self, engine, seed, outputs, inputs, full_data_size, n_samples):
+        X = None
+        if engine.lik_id != nv.LIK_BERNOULLI_PROBS:
+            X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
+        n_local = len(outputs)
+        prior_weight = 1.0
+        n_global = n_local
+        if self._group is not None:
+            import torch.distributed as dist
+
+            if self._global_len is None:
+                t = torch.tensor([n_local], dtype=torch.int64, device=engine.device)
+                dist.all_reduce(t, group=self._group)
+                self._global_len = int(t.item())
+            n_global = self._global_len
+            prior_weight = 1.0 if dist.get_rank(self._group) == 0 else 0.0
+        ll_scale = float(full_data_size) / float(n_global)  # advi.py:92
+
+        def run(loc, raw, kw):
+            out = engine.step(seed, loc, raw, kw, X, outputs, ll_scale, n_samples, prior_weight)
+            if self._group is not None:
+                import torch.distributed as dist
+
+                dist.all_reduce(out, group=self._group)
+            return out
+
+        return run
+
+    def loss_fn(self, params, outputs, inputs, full_data_size, seed, n_samples=1):
+        """Negative Monte-Carlo ELBO (advi.py:80-95); differentiable w.r.t. every tensor leaf of ``params``."""
+        loc, raw, kwargs = self._split_params(params)
+        engine, kw_leaves = self._engine_for(kwargs)
+        kw = torch.cat([l.reshape(-1).to(torch.float32) for l in kw_leaves]) if kw_leaves else None
+        run = self._run(engine, seed, outputs, inputs, full_data_size, n_samples)
+        return _ElboFunction.apply(loc, raw, kw, run)
+
+    def value_and_grad(self, params, outputs, inputs, full_data_size, seed, n_samples=1):
+        """jax.value_and_grad(loss_fn)(params, ...) in one fused step: (loss, grads with the structure of params)."""
+        loc, raw, kwargs = self._split_params(params)
+        engine, kw_leaves = self._engine_for(kwargs)
+        kw = torch.cat([l.detach().reshape(-1).to(torch.float32) for l in kw_leaves]) if kw_leaves else None
+        out = self._run(engine, seed, outputs, inputs, full_data_size, n_samples)(loc.detach(), raw.detach(), kw)
+        D, P = engine.D, engine.P
+        key = next(k for k in _POSTERIOR_KEYS if k in params)
+        grads: Dict[str, Any] = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), _scale_key(self.vi_type): out[1 + D : 1 + D + P].reshape(raw.shape)}}
+        o = 1 + D + P
+        for n in sorted(kwargs):
+            ls, td = tree_flatten(kwargs[n])
+            gl = []
+            for l in ls:
+                gl.append(out[o : o + l.numel()].reshape(l.shape))
+                o += l.numel()
+            grads[n] = tree_unflatten(td, gl)
+        return out[0], grads
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def get_params_posterior(self, params):
+        from .core import Posterior
+
+        loc, raw, kwargs = self._split_params(params)
+        engine, _ = self._engine_for(kwargs)
+        return Posterior(self, engine, loc.detach(), raw.detach())
+
+    apply = get_params_posterior

@@ -1,0 +1,172 @@
+// Shared host/device helpers for libbjx (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bjx.h"
+
+namespace bjx {
+
+// ---- host-side error plumbing (thread-local message, see bjx_api.cu) --------------------------------------------
+int fail(int code, const char* fmt, ...);
+
+#define BJX_CUDA_TRY(expr)                                                                             \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) return ::bjx::fail(BJX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define BJX_LAUNCH_CHECK(what)                                                                          \
+  do {                                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess) return ::bjx::fail(BJX_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define BJX_REQUIRE(cond, ...)                                             \
+  do {                                                                     \
+    if (!(cond)) return ::bjx::fail(BJX_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+int sm_count();
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- Threefry-2x32-20 (Salmon et al. SC'11; the generator under jax.random) ---------------------------------------
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
+  x0 += k0;
+  x1 += k1;
+#define BJX_TF_ROUND(r) \
+  x0 += x1;             \
+  x1 = rotl32(x1, r);   \
+  x1 ^= x0;
+  BJX_TF_ROUND(13) BJX_TF_ROUND(15) BJX_TF_ROUND(26) BJX_TF_ROUND(6)
+  x0 += k1;
+  x1 += ks2 + 1u;
+  BJX_TF_ROUND(17) BJX_TF_ROUND(29) BJX_TF_ROUND(16) BJX_TF_ROUND(24)
+  x0 += ks2;
+  x1 += k0 + 2u;
+  BJX_TF_ROUND(13) BJX_TF_ROUND(15) BJX_TF_ROUND(26) BJX_TF_ROUND(6)
+  x0 += k0;
+  x1 += k1 + 3u;
+  BJX_TF_ROUND(17) BJX_TF_ROUND(29) BJX_TF_ROUND(16) BJX_TF_ROUND(24)
+  x0 += k1;
+  x1 += ks2 + 4u;
+  BJX_TF_ROUND(13) BJX_TF_ROUND(15) BJX_TF_ROUND(26) BJX_TF_ROUND(6)
+  x0 += ks2;
+  x1 += k0 + 5u;
+#undef BJX_TF_ROUND
+}
+
+// 32 random bits for flat index i of a stream of `total` draws (jax._src.prng counter layouts).
+__device__ __forceinline__ uint32_t random_bits_at(uint32_t k0, uint32_t k1, uint64_t i, uint64_t total, int layout) {
+  uint32_t a, b;
+  if (layout == BJX_LAYOUT_PARTITIONABLE) {
+    a = (uint32_t)(i >> 32);
+    b = (uint32_t)i;
+    threefry2x32(k0, k1, a, b);
+    return a ^ b;
+  }
+  // legacy: iota(total) (+ one zero pad if odd) split in halves; pair j = (j, j + h)
+  const uint64_t h = (total + 1) >> 1;
+  const bool second = i >= h;
+  const uint64_t j = second ? i - h : i;
+  const uint64_t c1 = j + h;
+  a = (uint32_t)j;
+  b = (c1 < total) ? (uint32_t)c1 : 0u;  // the pad element
+  threefry2x32(k0, k1, a, b);
+  return second ? b : a;
+}
+
+// jax.random.uniform bit trick followed by the affine map; all roundings explicit (no FMA contraction).
+__device__ __forceinline__ float bits_to_unit(uint32_t bits) {
+  return __fsub_rn(__uint_as_float((bits >> 9) | 0x3F800000u), 1.0f);
+}
+
+__device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float hi) {
+  const float scale = __fsub_rn(hi, lo);
+  const float u = __fadd_rn(__fmul_rn(bits_to_unit(bits), scale), lo);
+  return fmaxf(lo, u);
+}
+
+// XLA ErfInv (f32, Giles' polynomial) under the pinned spec of oracle/threefry.py:
+// binary32 RN, no FMA, w = float(-log1p(-(double)(u*u))).
+__device__ __forceinline__ float erfinv_spec(float u) {
+  const float t = __fmul_rn(u, u);
+  float w = (float)(-log1p(-(double)t));
+  float p;
+  if (w < 5.0f) {
+    w = __fsub_rn(w, 2.5f);
+    p = 2.81022636e-08f;
+    p = __fadd_rn(3.43273939e-07f, __fmul_rn(p, w));
+    p = __fadd_rn(-3.5233877e-06f, __fmul_rn(p, w));
+    p = __fadd_rn(-4.39150654e-06f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00021858087f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00125372503f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00417768164f, __fmul_rn(p, w));
+    p = __fadd_rn(0.246640727f, __fmul_rn(p, w));
+    p = __fadd_rn(1.50140941f, __fmul_rn(p, w));
+  } else {
+    w = __fsub_rn(__fsqrt_rn(w), 3.0f);
+    p = -0.000200214257f;
+    p = __fadd_rn(0.000100950558f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00134934322f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00367342844f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00573950773f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.0076224613f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00943887047f, __fmul_rn(p, w));
+    p = __fadd_rn(1.00167406f, __fmul_rn(p, w));
+    p = __fadd_rn(2.83297682f, __fmul_rn(p, w));
+  }
+  const float r = __fmul_rn(p, u);
+  return (fabsf(u) == 1.0f) ? __fmul_rn(__int_as_float(0x7f800000), u) : r;
+}
+
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+  const float lo = __int_as_float(0xBF7FFFFF);  // nextafter(-1, 0)
+  const float u = bits_to_uniform(bits, lo, 1.0f);
+  return __fmul_rn(1.41421354f, erfinv_spec(u));  // float32(sqrt(2))
+}
+
+// ---- numerically careful elementwise pieces --------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) {
+  // log(1 + e^x) = max(x, 0) + log1p(e^{-|x|})
+  return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) {
+  // 1 / (1 + e^{-x}) without overflow on either side
+  const float e = expf(-fabsf(x));
+  const float s = 1.0f / (1.0f + e);
+  return x >= 0.0f ? s : e * s;
+}
+
+// ---- reductions -----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over a block of up to 1024 threads; result valid in thread 0. `red` must hold >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? red[lane] : 0.0f;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// ---- launchers implemented across the .cu files ---------------------------------------------------------------------
+struct Workspace;  // laid out in bjx_elbo.cu
+
+}  // namespace bjx

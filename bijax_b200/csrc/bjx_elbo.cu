@@ -1,0 +1,692 @@
+// The ELBO + gradient step (advi.py:80-95 under utils.py:7): plan, prologue, tail and the C entry points.
+//
+// Launch sequence of one step (all on the caller's stream, no host sync, graph-capturable):
+//   [full rank only: k_eps, k_fullrank_z]
+//   k_prologue        eps = normal(key); z; theta = b(z); per-(s,d) prior/entropy terms and their z-derivatives
+//   <likelihood>      one of: k_lik_tc (tcgen05), k_lik_smalld, k_lik_tiled_A+B, k_lik_coin  -> partial sums
+//   k_reduce_partials deterministic reduction of the per-CTA partials
+//   k_tail            chain rule through the bijector and the reparameterisation: d loc, d raw_scale (+ gz for full rank)
+//   [full rank only: k_fullrank_dM]
+//   k_scalars         loss and d kwargs
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bjx_elbo.cuh"
+#include "bjx_sgemm.cuh"
+#include "bjx_variational.cuh"
+
+namespace bjx {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---- optional event pairs around the streaming-likelihood launch (bench.py's roofline measurement) -------------------
+struct Profile {
+  std::vector<cudaEvent_t> ev;  // 2 * capacity
+  int capacity = 0, used = 0;
+};
+static thread_local Profile g_prof;
+
+static void prof_mark(cudaStream_t st, int which) {
+  if (g_prof.capacity == 0 || g_prof.used >= g_prof.capacity) return;
+  cudaEventRecord(g_prof.ev[2 * g_prof.used + which], st);
+  if (which == 1) ++g_prof.used;
+}
+
+// ---- plan ---------------------------------------------------------------------------------------------------------------
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int make_plan(const BjxElboArgs& a, Plan& p) {
+  memset(&p, 0, sizeof(p));
+  BJX_REQUIRE(a.S >= 1 && a.S <= (1 << 20), "S (n_samples) must be in [1, 2^20] (got %lld)", (long long)a.S);
+  BJX_REQUIRE(a.D >= 1, "D must be >= 1");
+  BJX_REQUIRE(a.N >= 0, "N must be >= 0");
+  BJX_REQUIRE(a.K >= 0, "K must be >= 0");
+  BJX_REQUIRE(a.vi_type == BJX_VI_MEAN_FIELD || a.vi_type == BJX_VI_FULL_RANK, "unknown vi_type %d", a.vi_type);
+  BJX_REQUIRE(a.scale_bijector >= BJX_SCALE_EXP && a.scale_bijector <= BJX_SCALE_IDENTITY, "unknown scale bijector %d",
+              a.scale_bijector);
+  BJX_REQUIRE(a.threefry_layout == BJX_LAYOUT_LEGACY || a.threefry_layout == BJX_LAYOUT_PARTITIONABLE,
+              "unknown threefry layout %d", a.threefry_layout);
+  BJX_REQUIRE(a.S * a.D <= 0xFFFFFFFFll, "S*D must fit the 32-bit legacy counter");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
+
+  if (a.likelihood == BJX_LIK_BERNOULLI_PROBS) {
+    BJX_REQUIRE(a.w_offset >= 0 && a.w_offset < a.D, "w_offset out of range");
+    p.kernel = KERNEL_COIN;
+  } else if (a.likelihood == BJX_LIK_BERNOULLI_LOGITS || a.likelihood == BJX_LIK_GAUSSIAN) {
+    BJX_REQUIRE(a.Dw >= 1 && a.w_offset >= 0 && a.w_offset + a.Dw <= a.D, "weights [w_offset, w_offset+Dw) must lie in [0, D)");
+    BJX_REQUIRE(a.ldx >= a.Dw, "ldx must be >= Dw");
+    if (a.likelihood == BJX_LIK_GAUSSIAN) {
+      BJX_REQUIRE(a.noise_src >= BJX_NOISE_CONST && a.noise_src <= BJX_NOISE_LATENT, "unknown noise_src %d", a.noise_src);
+      if (a.noise_src == BJX_NOISE_KWARG) BJX_REQUIRE(a.noise_index >= 0 && a.noise_index < a.K, "noise kwarg index out of range");
+      if (a.noise_src == BJX_NOISE_LATENT)
+        BJX_REQUIRE(a.noise_index >= 0 && a.noise_index < a.D && !(a.noise_index >= a.w_offset && a.noise_index < a.w_offset + a.Dw),
+                    "latent noise coordinate out of range or inside the weights");
+    }
+    const bool want_tc = a.precision == BJX_PREC_BF16X2 || a.precision == BJX_PREC_BF16X3 || a.precision == BJX_PREC_AUTO;
+    if (a.precision != BJX_PREC_FP32 && a.precision != BJX_PREC_AUTO && !tc_eligible(a))
+      return fail(BJX_ERR_UNSUPPORTED, "tensor-core precision requested but the shape is outside the tcgen05 kernel's envelope");
+    if (want_tc && tc_eligible(a))
+      p.kernel = KERNEL_TC_BF16;
+    else if (a.Dw <= 15)
+      p.kernel = KERNEL_FP32_SMALLD;
+    else
+      p.kernel = KERNEL_FP32_TILED;
+  } else {
+    return fail(BJX_ERR_INVALID_ARGUMENT, "unknown likelihood family %d", a.likelihood);
+  }
+
+  p.Pn = a.vi_type == BJX_VI_MEAN_FIELD ? a.D : a.D * a.D;
+  p.n_qp_blocks = (int)((a.S * a.D + 255) / 256);
+  const int64_t Dw = a.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : a.Dw;
+
+  switch (p.kernel) {
+    case KERNEL_COIN:
+      p.PG = p.PS = 1;
+      break;
+    case KERNEL_FP32_SMALLD: {
+      p.sd_rec4 = (int)((a.Dw + 1 + 3) / 4);
+      p.sd_SB = next_pow2((int)(a.S < 256 ? a.S : 256));
+      p.sd_grid_y = (int)((a.S + p.sd_SB - 1) / p.sd_SB);
+      int64_t gx = (a.N + SD_CHUNK_ROWS - 1) / SD_CHUNK_ROWS;
+      const int64_t cap = (int64_t)sms * 4 / p.sd_grid_y;  // a whole number of resident waves (4 CTAs of 256 threads per SM)
+      if (gx > cap) gx = cap;
+      if (gx < 1) gx = 1;
+      p.sd_grid_x = (int)gx;
+      p.PG = p.PS = p.sd_grid_x;
+      break;
+    }
+    case KERNEL_FP32_TILED: {
+      p.tA_grid_y = (int)((a.S + 31) / 32);
+      int64_t mt = (a.N + 127) / 128;
+      int64_t gx = (int64_t)sms * 2 / p.tA_grid_y;
+      if (gx < 1) gx = 1;
+      if (gx > mt) gx = mt;
+      if (gx < 1) gx = 1;
+      p.tA_grid_x = (int)gx;
+      p.PS = p.tA_grid_x;
+      p.tB_tiles = (int)(((a.S + 31) / 32) * ((a.Dw + 127) / 128));
+      int64_t ks = ((int64_t)sms * 2 + p.tB_tiles - 1) / p.tB_tiles;
+      int64_t kmax = (a.N + 255) / 256;  // at least 256 rows per slot
+      if (ks > kmax) ks = kmax;
+      if (ks < 1) ks = 1;
+      p.tB_kslots = (int)ks;
+      p.tB_rows_per_slot = (a.N + ks - 1) / ks;
+      p.tB_rows_per_slot = (p.tB_rows_per_slot + SG_BK - 1) / SG_BK * SG_BK;
+      p.PG = p.tB_kslots;
+      break;
+    }
+    case KERNEL_TC_BF16: {
+      int rc = tc_plan(a, p);
+      if (rc) return rc;
+      p.PG = p.PS = p.tc_ctas;
+      break;
+    }
+  }
+
+  // workspace carve-up (256-byte aligned regions)
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t SD = (size_t)a.S * a.D * sizeof(float);
+  p.o_eps = take(SD);
+  p.o_z = take(a.vi_type == BJX_VI_FULL_RANK ? SD : 0);
+  p.o_theta = take(SD);
+  p.o_bprime = take(SD);
+  p.o_gprior = take(SD);
+  p.o_gz = take(a.vi_type == BJX_VI_FULL_RANK ? SD : 0);
+  p.o_qp = take((size_t)p.n_qp_blocks * sizeof(float));
+  p.o_G = take((size_t)a.S * Dw * sizeof(float));
+  p.o_stat = take((size_t)a.S * sizeof(float));
+  p.o_Gpart = take((size_t)p.PG * a.S * Dw * sizeof(float));
+  p.o_statpart = take((size_t)p.PS * a.S * sizeof(float));
+  p.o_gbuf = take(p.kernel == KERNEL_FP32_TILED ? (size_t)a.N * a.S * sizeof(float) : 0);
+  p.o_tc_theta = take(p.kernel == KERNEL_TC_BF16 ? tc_theta_bytes(a, p) : 0);
+  p.o_stage_key = take(16);
+  p.o_stage_params = take((size_t)(a.D + p.Pn + a.K) * sizeof(float));
+  p.o_stage_out = take((size_t)(1 + a.D + p.Pn + a.K) * sizeof(float));
+  p.total = off;
+  return BJX_OK;
+}
+
+// ---- prologue -----------------------------------------------------------------------------------------------------------
+// One thread per (s, d).  Mean field: draws eps, forms z = loc + sigma * eps.  Full rank: eps and z were produced by
+// k_eps / k_fullrank_z.  Then theta = b(z), and the per-coordinate pieces of q.log_prob - log p~ with d/dz.
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ key, const float* __restrict__ loc,
+                                                  const float* __restrict__ raw, const BjxCoord* __restrict__ coords,
+                                                  int64_t S, int64_t D, int scale_bij, int layout,
+                                                  float* __restrict__ eps_buf, const float* __restrict__ z_buf,
+                                                  float* __restrict__ theta, float* __restrict__ bprime,
+                                                  float* __restrict__ gprior, float* __restrict__ qp_part,
+                                                  float* __restrict__ eps_out) {
+  __shared__ float red[32];
+  const int64_t total = S * D;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  float term = 0.0f;
+  if (i < total) {
+    const int64_t d = i % D;
+    float eps, z, logsig;
+    if (FULL) {
+      eps = eps_buf[i];
+      z = z_buf[i];
+      const ScaleEval sc = eval_scale(raw[d * D + d], scale_bij);
+      logsig = logf(fabsf(sc.sigma));
+    } else {
+      const uint32_t bits = random_bits_at(key[0], key[1], (uint64_t)i, (uint64_t)total, layout);
+      eps = bits_to_normal(bits);
+      eps_buf[i] = eps;
+      const float rho = raw[d];
+      const ScaleEval sc = eval_scale(rho, scale_bij);
+      z = loc[d] + sc.sigma * eps;
+      logsig = scale_bij == BJX_SCALE_EXP ? rho : logf(sc.sigma);
+    }
+    if (eps_out) eps_out[i] = eps;
+    const CoordEval ce = eval_coord(z, coords[d]);
+    theta[i] = ce.theta;
+    bprime[i] = ce.dtheta;
+    gprior[i] = -ce.dlogp;
+    // q.log_prob per coordinate (z - loc)/sigma == eps, minus the unconstrained prior's log density
+    term = (-0.5f * eps * eps - logsig - BJX_HALF_LOG_2PI) - ce.logp;
+  }
+  const float t = block_sum(term, red);
+  if (threadIdx.x == 0) qp_part[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(256) k_eps(const uint32_t* __restrict__ key, int64_t total, int layout,
+                                             float* __restrict__ eps) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < total) eps[i] = bits_to_normal(random_bits_at(key[0], key[1], (uint64_t)i, (uint64_t)total, layout));
+}
+
+// ---- full-rank contractions (fp32 FFMA; S x D x D) -----------------------------------------------------------------
+struct LoadEps {  // A(m = s, k = j) = eps[s, j]
+  static constexpr bool k_fast = true;
+  const float* eps;
+  int64_t S, D;
+  __device__ __forceinline__ float operator()(int64_t s, int64_t j) const { return (s < S && j < D) ? eps[s * D + j] : 0.0f; }
+};
+struct LoadTril {  // B(n = i, k = j) = scale(M[i, j]) for j <= i, else 0   (MultivariateNormalTriL masks with band_part)
+  static constexpr bool k_fast = true;
+  const float* M;
+  int64_t D;
+  int scale_bij;
+  __device__ __forceinline__ float operator()(int64_t i, int64_t j) const {
+    return (i < D && j <= i) ? eval_scale(M[i * D + j], scale_bij).sigma : 0.0f;
+  }
+};
+struct LoadColMajor {  // A(m, k) = base[k * D + m]
+  static constexpr bool k_fast = false;
+  const float* base;
+  int64_t rows, D, kmax;
+  __device__ __forceinline__ float operator()(int64_t m, int64_t k) const { return (m < rows && k < kmax) ? base[k * D + m] : 0.0f; }
+};
+
+// z[s, i] = loc[i] + sum_{j <= i} L[i, j] eps[s, j]
+__global__ void __launch_bounds__(256) k_fullrank_z(const float* __restrict__ eps, const float* __restrict__ M,
+                                                    const float* __restrict__ loc, int64_t S, int64_t D, int scale_bij,
+                                                    float* __restrict__ z) {
+  constexpr int BM = 64, BN = 64;
+  __shared__ SgemmSmem<BM, BN> sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  float acc[4][4];
+  const int64_t kend = min(D, n0 + BN);  // columns j > i contribute nothing
+  sgemm_tile<BM, BN>(acc, LoadEps{eps, S, D}, LoadTril{M, D, scale_bij}, m0, n0, 0, kend, sm);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t s = m0 + ty + 16 * i;
+    if (s >= S) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = n0 + tx + 16 * j;
+      if (c < D) z[s * D + c] = loc[c] + acc[i][j];
+    }
+  }
+}
+
+// d raw[i, j] = [i >= j] * ( sum_s gz[s, i] eps[s, j] * scale'(raw_ij) ) - [i == j] * prior_weight * dlog|L_ii|/draw_ii
+__global__ void __launch_bounds__(256) k_fullrank_dM(const float* __restrict__ gz, const float* __restrict__ eps,
+                                                     const float* __restrict__ M, int64_t S, int64_t D, int scale_bij,
+                                                     float prior_weight, float* __restrict__ dM) {
+  constexpr int BM = 64, BN = 64;
+  __shared__ SgemmSmem<BM, BN> sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  float acc[4][4];
+  const bool live = n0 <= m0 + BM - 1;  // tile touches the lower triangle
+  if (live) {
+    sgemm_tile<BM, BN>(acc, LoadColMajor{gz, D, D, S}, LoadColMajor{eps, D, D, S}, m0, n0, 0, S, sm);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = m0 + ty + 16 * i;
+    if (r >= D) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = n0 + tx + 16 * j;
+      if (c >= D) continue;
+      float v = 0.0f;
+      if (c <= r) {
+        const ScaleEval sc = eval_scale(M[r * D + c], scale_bij);
+        v = acc[i][j] * sc.dsigma;
+        if (c == r) v -= prior_weight * sc.dlogsigma;
+      }
+      dM[r * D + c] = v;
+    }
+  }
+}
+
+// ---- coin toss (tfd.Bernoulli(probs=p).log_prob(y).sum(), README.md:91-95): one block per sample ---------------------
+__global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
+                                                  int64_t D, int64_t w_off, float* __restrict__ G, float* __restrict__ stat) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const float p = theta[(int64_t)s * D + w_off];
+  const float lp = logf(p), l1p = log1pf(-p);
+  const float ip = 1.0f / p, i1p = 1.0f / (1.0f - p);
+  float f = 0.0f, g = 0.0f;
+  for (int64_t n = threadIdx.x; n < N; n += 256) {
+    const float k = y[n];
+    f += (1.0f - k) * l1p + k * lp;
+    g += k * ip - (1.0f - k) * i1p;
+  }
+  const float fs = block_sum(f, red);
+  const float gs = block_sum(g, red);
+  if (threadIdx.x == 0) {
+    stat[s] = fs;
+    G[s] = gs;
+  }
+}
+
+// ---- tail ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ Gpart, int PG, const float* __restrict__ statpart,
+                                                         int PS, int64_t SDw, int64_t S, float* __restrict__ G,
+                                                         float* __restrict__ stat) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < SDw) {
+    float t = 0.0f;
+    for (int p = 0; p < PG; ++p) t += Gpart[(size_t)p * SDw + i];
+    G[i] = t;
+  } else if (i < SDw + S) {
+    const int64_t s = i - SDw;
+    float t = 0.0f;
+    for (int p = 0; p < PS; ++p) t += statpart[(size_t)p * S + s];
+    stat[s] = t;
+  }
+}
+
+struct TailArgs {
+  int64_t S, D, Dw, w_off, N;
+  int vi_type, scale_bij, likelihood, noise_src, noise_index;
+  float noise_value, ll_scale, prior_weight;
+};
+
+__device__ __forceinline__ float tau_of(const TailArgs& t, const float* kwargs, const float* theta, int64_t s) {
+  if (t.noise_src == BJX_NOISE_KWARG) return expf(kwargs[t.noise_index]);
+  if (t.noise_src == BJX_NOISE_LATENT) return theta[s * t.D + t.noise_index];
+  return t.noise_value;
+}
+
+// One thread per latent coordinate d; loops over the S samples.
+//   gz[s,d] = prior_weight * (-d log p~ / dz) / S  -  (ll_scale / S) * dll_s/dtheta_d * b'(z)
+//   d loc[d] = sum_s gz;   d rho[d] = sigma'(rho) * sum_s gz * eps  -  prior_weight * dlog sigma / d rho     (mean field)
+__global__ void __launch_bounds__(128) k_tail(TailArgs t, const float* __restrict__ raw, const float* __restrict__ kwargs,
+                                              const float* __restrict__ eps, const float* __restrict__ theta,
+                                              const float* __restrict__ bprime, const float* __restrict__ gprior,
+                                              const float* __restrict__ G, const float* __restrict__ stat,
+                                              float* __restrict__ gz_out, float* __restrict__ out) {
+  const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (d >= t.D) return;
+  const float invS = 1.0f / (float)t.S;
+  const float cS = t.ll_scale * invS;
+  const bool is_w = t.likelihood == BJX_LIK_BERNOULLI_PROBS ? (d == t.w_off) : (d >= t.w_off && d < t.w_off + t.Dw);
+  const bool is_noise = t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_LATENT && d == t.noise_index;
+  const int64_t Dw = t.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : t.Dw;
+  float acc_mu = 0.0f, acc_rho = 0.0f;
+  for (int64_t s = 0; s < t.S; ++s) {
+    const int64_t i = s * t.D + d;
+    float dll = 0.0f;  // d ll_s / d theta[s, d]
+    if (is_w) {
+      dll = G[s * Dw + (d - t.w_off)];
+      if (t.likelihood == BJX_LIK_GAUSSIAN) {
+        const float tau = tau_of(t, kwargs, theta, s);
+        dll = dll / (tau * tau);
+      }
+    } else if (is_noise) {
+      const float tau = theta[i];
+      dll = (stat[s] / (tau * tau) - (float)t.N) / tau;  // d/dtau [ -Q/(2 tau^2) - N log tau ]
+    }
+    const float gz = t.prior_weight * gprior[i] * invS - cS * dll * bprime[i];
+    if (gz_out) gz_out[i] = gz;
+    acc_mu += gz;
+    acc_rho = fmaf(gz, eps[i], acc_rho);
+  }
+  out[1 + d] = acc_mu;
+  if (t.vi_type == BJX_VI_MEAN_FIELD) {
+    const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
+    out[1 + t.D + d] = acc_rho * sc.dsigma - t.prior_weight * sc.dlogsigma;
+  }
+}
+
+// loss = prior_weight * mean_s(q_s - p~_s) - ll_scale * mean_s ll_s ;  d kwargs
+__global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t Pn, const float* __restrict__ kwargs,
+                                                 const float* __restrict__ theta, const float* __restrict__ qp_part,
+                                                 int n_qp, const float* __restrict__ stat, float* __restrict__ out) {
+  __shared__ float red[32];
+  float qp = 0.0f;
+  for (int i = threadIdx.x; i < n_qp; i += 256) qp += qp_part[i];
+  qp = block_sum(qp, red);
+  float ll = 0.0f, dk = 0.0f;
+  for (int64_t s = threadIdx.x; s < t.S; s += 256) {
+    if (t.likelihood == BJX_LIK_GAUSSIAN) {
+      const float tau = tau_of(t, kwargs, theta, s);
+      const float q = stat[s] / (tau * tau);
+      ll += -0.5f * q - (float)t.N * (logf(tau) + BJX_HALF_LOG_2PI);
+      dk += q - (float)t.N;  // d ll_s / d log tau
+    } else {
+      ll += stat[s];
+    }
+  }
+  ll = block_sum(ll, red);
+  dk = block_sum(dk, red);
+  if (threadIdx.x == 0) {
+    const float invS = 1.0f / (float)t.S;
+    out[0] = t.prior_weight * qp * invS - t.ll_scale * ll * invS;
+    float* dkw = out + 1 + t.D + Pn;
+    for (int64_t k = 0; k < K; ++k) dkw[k] = 0.0f;
+    if (t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_KWARG) dkw[t.noise_index] = -t.ll_scale * dk * invS;
+  }
+}
+
+// ---- orchestration ------------------------------------------------------------------------------------------------------
+static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+  float* eps = (float*)(ws + p.o_eps);
+  float* z = (float*)(ws + p.o_z);
+  float* theta = (float*)(ws + p.o_theta);
+  float* bprime = (float*)(ws + p.o_bprime);
+  float* gprior = (float*)(ws + p.o_gprior);
+  float* qp = (float*)(ws + p.o_qp);
+  const int64_t total = a.S * a.D;
+  if (a.vi_type == BJX_VI_FULL_RANK) {
+    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, total, a.threefry_layout, eps);
+    BJX_LAUNCH_CHECK("k_eps");
+    dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.S + 63) / 64));
+    k_fullrank_z<<<grid, 256, 0, st>>>(eps, a.raw_scale, a.loc, a.S, a.D, a.scale_bijector, z);
+    BJX_LAUNCH_CHECK("k_fullrank_z");
+    k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
+                                                    a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out);
+  } else {
+    k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
+                                                     a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out);
+  }
+  BJX_LAUNCH_CHECK("k_prologue");
+  return BJX_OK;
+}
+
+static int check_ptrs(const BjxElboArgs& a, const Plan& p) {
+  BJX_REQUIRE(a.key && a.loc && a.raw_scale && a.coords && a.out, "null key/loc/raw_scale/coords/out pointer");
+  BJX_REQUIRE(a.K == 0 || a.kwargs, "K > 0 but kwargs is null");
+  BJX_REQUIRE(a.N == 0 || a.y, "y is null");
+  BJX_REQUIRE(a.likelihood == BJX_LIK_BERNOULLI_PROBS || a.N == 0 || a.X, "X is null");
+  BJX_REQUIRE(a.workspace != nullptr, "workspace is null");
+  if (a.workspace_bytes < p.total)
+    return fail(BJX_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", a.workspace_bytes, p.total);
+  return BJX_OK;
+}
+
+static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
+  char* ws = (char*)a.workspace;
+  int rc = run_prologue(a, p, ws, st);
+  if (rc) return rc;
+
+  float* G = (float*)(ws + p.o_G);
+  float* stat = (float*)(ws + p.o_stat);
+  const int64_t Dw = a.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : a.Dw;
+  if (p.kernel == KERNEL_COIN) {
+    k_lik_coin<<<(unsigned)a.S, 256, 0, st>>>(a.y, a.N, (const float*)(ws + p.o_theta), a.D, a.w_offset, G, stat);
+    BJX_LAUNCH_CHECK("k_lik_coin");
+  } else {
+    if (a.N == 0) {
+      BJX_CUDA_TRY(cudaMemsetAsync(ws + p.o_Gpart, 0, (size_t)p.PG * a.S * Dw * sizeof(float), st));
+      BJX_CUDA_TRY(cudaMemsetAsync(ws + p.o_statpart, 0, (size_t)p.PS * a.S * sizeof(float), st));
+    } else {
+      prof_mark(st, 0);
+      if (p.kernel == KERNEL_FP32_SMALLD) {
+        rc = launch_lik_smalld(a, p, ws, st);
+      } else if (p.kernel == KERNEL_FP32_TILED) {
+        rc = launch_lik_tiled(a, p, ws, st);
+      } else {
+        rc = launch_lik_tc(a, p, ws, st);
+      }
+      prof_mark(st, 1);
+    }
+    if (rc) return rc;
+    const int64_t SDw = a.S * Dw;
+    k_reduce_partials<<<(unsigned)((SDw + a.S + 255) / 256), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
+                                                                          (const float*)(ws + p.o_statpart), p.PS, SDw,
+                                                                          a.S, G, stat);
+    BJX_LAUNCH_CHECK("k_reduce_partials");
+  }
+
+  TailArgs t;
+  t.S = a.S; t.D = a.D; t.Dw = a.Dw; t.w_off = a.w_offset; t.N = a.N;
+  t.vi_type = a.vi_type; t.scale_bij = a.scale_bijector; t.likelihood = a.likelihood;
+  t.noise_src = a.noise_src; t.noise_index = a.noise_index; t.noise_value = a.noise_value;
+  t.ll_scale = a.ll_scale; t.prior_weight = a.prior_weight;
+  float* gz = a.vi_type == BJX_VI_FULL_RANK ? (float*)(ws + p.o_gz) : nullptr;
+  k_tail<<<(unsigned)((a.D + 127) / 128), 128, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
+                                                       (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
+                                                       (const float*)(ws + p.o_gprior), G, stat, gz, a.out);
+  BJX_LAUNCH_CHECK("k_tail");
+  if (a.vi_type == BJX_VI_FULL_RANK) {
+    dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.D + 63) / 64));
+    k_fullrank_dM<<<grid, 256, 0, st>>>(gz, (const float*)(ws + p.o_eps), a.raw_scale, a.S, a.D, a.scale_bijector,
+                                        a.prior_weight, a.out + 1 + a.D);
+    BJX_LAUNCH_CHECK("k_fullrank_dM");
+  }
+  k_scalars<<<1, 256, 0, st>>>(t, a.K, p.Pn, a.kwargs, (const float*)(ws + p.o_theta), (const float*)(ws + p.o_qp),
+                               p.n_qp_blocks, stat, a.out);
+  BJX_LAUNCH_CHECK("k_scalars");
+  return BJX_OK;
+}
+
+// ---- fused optimiser step (optax.adam, eps outside the square root, bias-corrected) ---------------------------------
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                              const float* __restrict__ g, int64_t n, float lr, float b1, float b2,
+                                              float eps, float c1, float c2) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+}  // namespace bjx
+
+// =========================================================================================================================
+extern "C" {
+
+int bjx_abi_version(void) { return BJX_ABI_VERSION; }
+
+const char* bjx_last_error(void) { return bjx::g_last_error.c_str(); }
+
+int bjx_device_sm_count(void) { return bjx::sm_count(); }
+
+size_t bjx_elbo_workspace_bytes(const BjxElboArgs* args) {
+  if (!args) return 0;
+  bjx::Plan p;
+  if (bjx::make_plan(*args, p) != BJX_OK) return 0;
+  return p.total;
+}
+
+int bjx_elbo_kernel_choice(const BjxElboArgs* args) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr, "args is null");
+  Plan p;
+  int rc = make_plan(*args, p);
+  if (rc) return rc;
+  return p.kernel;
+}
+
+int bjx_elbo_step(const BjxElboArgs* args, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr, "args is null");
+  Plan p;
+  int rc = make_plan(*args, p);
+  if (rc) return rc;
+  rc = check_ptrs(*args, p);
+  if (rc) return rc;
+  return run_step(*args, p, (cudaStream_t)stream);
+}
+
+int bjx_elbo_step_host(const BjxElboArgs* args, const uint32_t* key_host, const float* params_host, float* out_host,
+                       void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr && key_host && params_host && out_host, "null pointer");
+  Plan p;
+  int rc = make_plan(*args, p);
+  if (rc) return rc;
+  BjxElboArgs a = *args;
+  char* ws = (char*)a.workspace;
+  BJX_REQUIRE(ws != nullptr, "workspace is null");
+  if (a.workspace_bytes < p.total)
+    return fail(BJX_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", a.workspace_bytes, p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sp = (float*)(ws + p.o_stage_params);
+  a.key = (const uint32_t*)(ws + p.o_stage_key);
+  a.loc = sp;
+  a.raw_scale = sp + a.D;
+  a.kwargs = a.K ? sp + a.D + p.Pn : nullptr;
+  a.out = (float*)(ws + p.o_stage_out);
+  rc = check_ptrs(a, p);
+  if (rc) return rc;
+  const size_t n_params = (size_t)(a.D + p.Pn + a.K);
+  BJX_CUDA_TRY(cudaMemcpyAsync((void*)a.key, key_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  BJX_CUDA_TRY(cudaMemcpyAsync(sp, params_host, n_params * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = run_step(a, p, st);
+  if (rc) return rc;
+  BJX_CUDA_TRY(cudaMemcpyAsync(out_host, a.out, (1 + n_params) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BJX_CUDA_TRY(cudaStreamSynchronize(st));
+  return BJX_OK;
+}
+
+int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr && theta_out != nullptr, "null pointer");
+  BjxElboArgs a = *args;
+  // sampling needs no data: plan as a data-free coin problem so that no likelihood scratch is required
+  a.likelihood = BJX_LIK_BERNOULLI_PROBS;
+  a.w_offset = 0;
+  a.N = 0;
+  Plan p;
+  int rc = make_plan(a, p);
+  if (rc) return rc;
+  BJX_REQUIRE(a.key && a.loc && a.raw_scale && a.coords && a.workspace, "null key/loc/raw_scale/coords/workspace pointer");
+  if (a.workspace_bytes < p.total)
+    return fail(BJX_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", a.workspace_bytes, p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)a.workspace;
+  a.eps_out = nullptr;
+  rc = run_prologue(a, p, ws, st);
+  if (rc) return rc;
+  const size_t SD = (size_t)a.S * a.D * sizeof(float);
+  BJX_CUDA_TRY(cudaMemcpyAsync(theta_out, ws + p.o_theta, SD, cudaMemcpyDeviceToDevice, st));
+  if (z_out) {
+    if (a.vi_type == BJX_VI_FULL_RANK) {
+      BJX_CUDA_TRY(cudaMemcpyAsync(z_out, ws + p.o_z, SD, cudaMemcpyDeviceToDevice, st));
+    } else {
+      return fail(BJX_ERR_UNSUPPORTED, "z_out is only materialised for the full-rank family; invert the bijector instead");
+    }
+  }
+  return BJX_OK;
+}
+
+int bjx_profile_begin(int32_t capacity) {
+  using namespace bjx;
+  BJX_REQUIRE(capacity > 0 && capacity <= (1 << 16), "capacity must be in [1, 65536]");
+  bjx_profile_end();
+  g_prof.ev.resize(2 * (size_t)capacity);
+  for (auto& e : g_prof.ev) BJX_CUDA_TRY(cudaEventCreate(&e));
+  g_prof.capacity = capacity;
+  g_prof.used = 0;
+  return BJX_OK;
+}
+
+int bjx_profile_collect(float* ms_out_host, int32_t max_out, int32_t* n_out_host) {
+  using namespace bjx;
+  BJX_REQUIRE(ms_out_host && n_out_host && max_out >= 0, "null pointer");
+  int n = g_prof.used < max_out ? g_prof.used : max_out;
+  for (int i = 0; i < n; ++i) {
+    BJX_CUDA_TRY(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    BJX_CUDA_TRY(cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+  }
+  *n_out_host = n;
+  g_prof.used = 0;
+  return BJX_OK;
+}
+
+int bjx_profile_end(void) {
+  using namespace bjx;
+  for (auto& e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.capacity = 0;
+  g_prof.used = 0;
+  return BJX_OK;
+}
+
+int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
+                    float b2, float eps, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(params && m && v && grads, "null pointer");
+  BJX_REQUIRE(n >= 0 && step >= 1, "need n >= 0 and step >= 1");
+  if (n == 0) return BJX_OK;
+  const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, n, lr, b1, b2, eps, c1, c2);
+  BJX_LAUNCH_CHECK("k_adam");
+  return BJX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// Kernel 5+6, CUDA-core (fp32 FFMA) variants of the streaming likelihood pass:
+//   eta[n, s] = X[n, :] . theta[s, w]      (user likelihood_fn, advi.py:90; exemplars README.md:99-106)
+//   stat[s]   = sum_n f(y_n, eta[n, s])    (likelihood.log_prob(outputs).sum(), advi.py:91)
+//   G[s, d]   = sum_n g(y_n, eta[n, s]) X[n, d]   (the transposed dot_general of the VJP, utils.py:7)
+// Two kernels: a single-pass register-resident one for a handful of columns (config c2: D = 5), and a generic
+// two-pass tiled fallback for any shape the tensor-core kernel (bjx_lik_tc.cu) does not take.
+#include "bjx_elbo.cuh"
+#include "bjx_sgemm.cuh"
+
+namespace bjx {
+
+// =====================================================================================================================
+// small-D: each thread owns one Monte-Carlo sample s (theta[s, :] and G[s, :] live in registers) and a lane of rows;
+// rows are staged through shared memory as padded records [x_0 .. x_{Dw-1}, y, 0...] so that a warp reads one record
+// with REC4 broadcast LDS.128.  X is read from HBM exactly once, coalesced.
+// =====================================================================================================================
+constexpr int SD_CHUNK = SD_CHUNK_ROWS;
+
+template <int REC4>
+__global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y,
+                                                    int64_t N, int Dw, const float* __restrict__ theta, int64_t D,
+                                                    int64_t w_off, int S, int family, int SB, int64_t rows_per_cta,
+                                                    float* __restrict__ Gpart, float* __restrict__ statpart) {
+  constexpr int REC = REC4 * 4;
+  __shared__ __align__(16) float sm[256 * (REC + 1)];
+  const int tid = threadIdx.x;
+  const int RL = 256 / SB;
+  const int sl = tid % SB, rl = tid / SB;
+  const int s = blockIdx.y * SB + sl;
+  const bool s_ok = s < S;
+
+  float th[REC], G[REC];
+#pragma unroll
+  for (int d = 0; d < REC; ++d) {
+    th[d] = (s_ok && d < Dw) ? theta[(int64_t)s * D + w_off + d] : 0.0f;
+    G[d] = 0.0f;
+  }
+  float stat = 0.0f;
+
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row_end = min(N, row_begin + rows_per_cta);
+  for (int64_t base = row_begin; base < row_end; base += SD_CHUNK) {
+    const int nvalid = (int)min((int64_t)SD_CHUNK, row_end - base);
+    __syncthreads();  // previous chunk fully consumed
+    if (tid < nvalid) {
+      const float* xr = X + (base + tid) * ldx;
+      float* rec = sm + tid * REC;
+#pragma unroll
+      for (int d = 0; d < REC; ++d) rec[d] = d < Dw ? xr[d] : 0.0f;
+      rec[Dw] = y[base + tid];
+    }
+    __syncthreads();
+    for (int r = rl; r < nvalid; r += RL) {
+      float rec[REC];
+      const float4* rp = reinterpret_cast<const float4*>(sm + r * REC);
+#pragma unroll
+      for (int q = 0; q < REC4; ++q) {
+        const float4 v = rp[q];
+        rec[4 * q + 0] = v.x;
+        rec[4 * q + 1] = v.y;
+        rec[4 * q + 2] = v.z;
+        rec[4 * q + 3] = v.w;
+      }
+      float yv = 0.0f;
+#pragma unroll
+      for (int d = 0; d < REC; ++d) yv = (d == Dw) ? rec[d] : yv;
+      float eta = 0.0f;
+#pragma unroll
+      for (int d = 0; d < REC; ++d) eta = fmaf(rec[d], th[d], eta);  // th[d >= Dw] == 0: y and padding drop out
+      float f, g;
+      link_eval(family, yv, eta, f, g);
+      stat += f;
+#pragma unroll
+      for (int d = 0; d < REC; ++d) G[d] = fmaf(g, rec[d], G[d]);
+    }
+  }
+
+  // deterministic reduction over the RL row lanes of this CTA
+  __syncthreads();
+  float* red = sm + (size_t)(rl * SB + sl) * (REC + 1);
+#pragma unroll
+  for (int d = 0; d < REC; ++d) red[d] = G[d];
+  red[REC] = stat;
+  __syncthreads();
+  if (rl == 0 && s_ok) {
+    float acc[REC + 1];
+#pragma unroll
+    for (int d = 0; d <= REC; ++d) acc[d] = 0.0f;
+    for (int l = 0; l < RL; ++l) {
+      const float* rr = sm + (size_t)(l * SB + sl) * (REC + 1);
+#pragma unroll
+      for (int d = 0; d <= REC; ++d) acc[d] += rr[d];
+    }
+    float* gp = Gpart + ((size_t)blockIdx.x * S + s) * Dw;
+#pragma unroll
+    for (int d = 0; d < REC; ++d)
+      if (d < Dw) gp[d] = acc[d];
+    statpart[(size_t)blockIdx.x * S + s] = acc[REC];
+  }
+}
+
+int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+  const float* theta = (const float*)(ws + p.o_theta);
+  float* Gpart = (float*)(ws + p.o_Gpart);
+  float* statpart = (float*)(ws + p.o_statpart);
+  const int64_t rows_per_cta = (a.N + p.sd_grid_x - 1) / p.sd_grid_x;
+  dim3 grid(p.sd_grid_x, p.sd_grid_y);
+#define BJX_SD_LAUNCH(R4)                                                                                          \
+  k_lik_smalld<R4><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,       \
+                                         a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart)
+  switch (p.sd_rec4) {
+    case 1: BJX_SD_LAUNCH(1); break;
+    case 2: BJX_SD_LAUNCH(2); break;
+    case 3: BJX_SD_LAUNCH(3); break;
+    case 4: BJX_SD_LAUNCH(4); break;
+    default: return fail(BJX_ERR_UNSUPPORTED, "small-D kernel supports Dw <= 15 (got %lld)", (long long)a.Dw);
+  }
+#undef BJX_SD_LAUNCH
+  BJX_LAUNCH_CHECK("k_lik_smalld");
+  return BJX_OK;
+}
+
+// =====================================================================================================================
+// generic fp32 fallback, two passes:
+//   A: eta tile = X @ theta^T (BM=128 rows x BN=32 samples), link function in the epilogue, g[n, s] -> scratch
+//   B: G = g^T @ X, split over row ranges into partial slots (reduced deterministically by the tail kernel)
+// =====================================================================================================================
+struct LoadRowMajorK {  // M(row, k) = base[row * ld + k]
+  static constexpr bool k_fast = true;
+  const float* base;
+  int64_t ld, rows, cols;
+  __device__ __forceinline__ float operator()(int64_t r, int64_t k) const {
+    return (r < rows && k < cols) ? base[r * ld + k] : 0.0f;
+  }
+};
+struct LoadTransposed {  // M(row, k) = base[k * ld + row]
+  static constexpr bool k_fast = false;
+  const float* base;
+  int64_t ld, rows, kmax;
+  __device__ __forceinline__ float operator()(int64_t r, int64_t k) const {
+    return (r < rows && k < kmax) ? base[k * ld + r] : 0.0f;
+  }
+};
+
+__global__ void __launch_bounds__(256) k_lik_tiled_A(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y,
+                                                     int64_t N, int64_t Dw, const float* __restrict__ theta, int64_t D,
+                                                     int64_t w_off, int S, int family, float* __restrict__ gbuf,
+                                                     float* __restrict__ statpart) {
+  constexpr int BM = 128, BN = 32;
+  __shared__ SgemmSmem<BM, BN> sm;
+  __shared__ float red[16][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  LoadRowMajorK la{X, ldx, N, Dw};
+  LoadRowMajorK lb{theta + w_off, D, S, Dw};
+  float stat_acc[BN / 16] = {0.0f, 0.0f};
+  const int64_t m_tiles = (N + BM - 1) / BM;
+  for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+    const int64_t m0 = mt * BM;
+    float acc[BM / 16][BN / 16];
+    sgemm_tile<BM, BN>(acc, la, lb, m0, n0, 0, Dw, sm);
+#pragma unroll
+    for (int i = 0; i < BM / 16; ++i) {
+      const int64_t m = m0 + ty + 16 * i;
+      if (m >= N) continue;
+      const float yv = y[m];
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const int64_t s = n0 + tx + 16 * j;
+        if (s >= S) continue;
+        float f, g;
+        link_eval(family, yv, acc[i][j], f, g);
+        gbuf[m * S + s] = g;
+        stat_acc[j] += f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < BN / 16; ++j) red[ty][tx + 16 * j] = stat_acc[j];
+  __syncthreads();
+  if (tid < BN && n0 + tid < S) {
+    float t = 0.0f;
+    for (int r = 0; r < 16; ++r) t += red[r][tid];
+    statpart[(size_t)blockIdx.x * S + n0 + tid] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_lik_tiled_B(const float* __restrict__ X, int64_t ldx, int64_t N, int64_t Dw,
+                                                     const float* __restrict__ gbuf, int S, int64_t rows_per_slot,
+                                                     int n_tiles, float* __restrict__ Gpart) {
+  constexpr int BM = 32, BN = 128;
+  __shared__ SgemmSmem<BM, BN> sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ks = blockIdx.x;
+  const int mt = blockIdx.y / n_tiles, nt = blockIdx.y % n_tiles;
+  const int64_t m0 = (int64_t)mt * BM, n0 = (int64_t)nt * BN;
+  const int64_t k_begin = (int64_t)ks * rows_per_slot;
+  const int64_t k_end = min(N, k_begin + rows_per_slot);
+  LoadTransposed la{gbuf, S, S, N};    // A(m = s, k = row) = g[row, s]
+  LoadTransposed lb{X, ldx, Dw, N};    // B(n = d, k = row) = X[row, d]
+  float acc[BM / 16][BN / 16];
+  sgemm_tile<BM, BN>(acc, la, lb, m0, n0, k_begin, k_end > k_begin ? k_end : k_begin, sm);
+#pragma unroll
+  for (int i = 0; i < BM / 16; ++i) {
+    const int64_t s = m0 + ty + 16 * i;
+    if (s >= S) continue;
+#pragma unroll
+    for (int j = 0; j < BN / 16; ++j) {
+      const int64_t d = n0 + tx + 16 * j;
+      if (d < Dw) Gpart[((size_t)ks * S + s) * Dw + d] = acc[i][j];
+    }
+  }
+}
+
+int launch_lik_tiled(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+  const float* theta = (const float*)(ws + p.o_theta);
+  float* gbuf = (float*)(ws + p.o_gbuf);
+  float* Gpart = (float*)(ws + p.o_Gpart);
+  float* statpart = (float*)(ws + p.o_statpart);
+  k_lik_tiled_A<<<dim3(p.tA_grid_x, p.tA_grid_y), 256, 0, st>>>(a.X, a.ldx, a.y, a.N, a.Dw, theta, a.D, a.w_offset,
+                                                                (int)a.S, a.likelihood, gbuf, statpart);
+  BJX_LAUNCH_CHECK("k_lik_tiled_A");
+  const int n_tiles = (int)((a.Dw + 127) / 128);
+  k_lik_tiled_B<<<dim3(p.tB_kslots, p.tB_tiles), 256, 0, st>>>(a.X, a.ldx, a.N, a.Dw, gbuf, (int)a.S, p.tB_rows_per_slot,
+                                                               n_tiles, Gpart);
+  BJX_LAUNCH_CHECK("k_lik_tiled_B");
+  return BJX_OK;
+}
+
+}  // namespace bjx

@@ -1,0 +1,197 @@
+"""Host-side driver of the fused ELBO+gradient step: owns the coordinate table, the workspace and the argument block, and
+calls ``bjx_elbo_step`` through the C ABI.  One engine per (model, device)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from . import likelihoods as lk
+from . import random as brandom
+from .spec import LatentSpec
+
+_SCALE_IDS = {"Exp": nv.SCALE_EXP, "Softplus": nv.SCALE_SOFTPLUS, "Identity": nv.SCALE_IDENTITY}
+_PRECISIONS = {"auto": nv.PREC_AUTO, "fp32": nv.PREC_FP32, "bf16x3": nv.PREC_BF16X3, "bf16x2": nv.PREC_BF16X2}
+
+
+class ElboEngine:
+    def __init__(
+        self,
+        latents: LatentSpec,
+        likelihood,
+        vi_type: str = "mean_field",
+        scale_bijector=None,
+        kwarg_layout: Sequence[Tuple[str, int]] = (),
+        device=None,
+        precision: str = "auto",
+    ):
+        nv.require_cuda()
+        self.lib = nv.load()
+        self.latents = latents
+        self.likelihood = likelihood
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if vi_type not in ("mean_field", "full_rank"):
+            raise NotImplementedError(
+                f"vi_type={vi_type!r}: only mean_field and full_rank are fused; low_rank stays out of scope (SURVEY.md section 2)"
+            )
+        self.vi_type = nv.VI_MEAN_FIELD if vi_type == "mean_field" else nv.VI_FULL_RANK
+        sb = type(scale_bijector).__name__ if scale_bijector is not None else ("Exp" if vi_type == "mean_field" else "Identity")
+        if sb not in _SCALE_IDS:
+            raise NotImplementedError(f"scale bijector {sb} is not one of Exp / Softplus / Identity")
+        self.scale_bijector = _SCALE_IDS[sb]
+        self.D = latents.size
+        self.P = self.D if self.vi_type == nv.VI_MEAN_FIELD else self.D * self.D
+        self.kwarg_layout = list(kwarg_layout)  # [(name, numel)] in sorted-key order
+        self.K = sum(n for _, n in self.kwarg_layout)
+        self.precision = _PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        self.coords = torch.from_numpy(latents.coords.view(np.uint8).copy()).to(self.device)
+        self._ws: Optional[torch.Tensor] = None
+        self._resolve_likelihood()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _resolve_likelihood(self):
+        L = self.likelihood
+        self.noise_src, self.noise_index, self.noise_value = nv.NOISE_CONST, 0, 1.0
+        self.x_name = getattr(L, "X", None)
+        if isinstance(L, lk.BernoulliProbs):
+            off, n = self.latents.offset_of(L.probs)
+            if n != 1:
+                raise ValueError("BernoulliProbs needs a scalar latent")
+            self.lik_id, self.w_offset, self.Dw = nv.LIK_BERNOULLI_PROBS, off, 0
+        elif isinstance(L, (lk.BernoulliLogits, lk.GaussianLinear)):
+            off, n = self.latents.offset_of(L.weights)
+            self.w_offset, self.Dw = off, n
+            self.lik_id = nv.LIK_BERNOULLI_LOGITS if isinstance(L, lk.BernoulliLogits) else nv.LIK_GAUSSIAN
+            if isinstance(L, lk.GaussianLinear):
+                if L.noise_scale is not None:
+                    self.noise_src, self.noise_value = nv.NOISE_CONST, float(L.noise_scale)
+                elif L.noise_latent is not None:
+                    o, n2 = self.latents.offset_of(L.noise_latent)
+                    if n2 != 1:
+                        raise ValueError("noise_latent must be a scalar latent")
+                    self.noise_src, self.noise_index = nv.NOISE_LATENT, o
+                else:
+                    pos, found = 0, False
+                    for name, numel in self.kwarg_layout:
+                        if name == L.log_noise_scale:
+                            if numel != 1:
+                                raise ValueError("log_noise_scale must be a scalar parameter")
+                            self.noise_src, self.noise_index, found = nv.NOISE_KWARG, pos, True
+                        pos += numel
+                    if not found:
+                        raise KeyError(f"params has no trainable entry {L.log_noise_scale!r} for the Gaussian noise scale")
+        else:
+            raise NotImplementedError(
+                "only the recognised likelihood families (bijax_b200.likelihoods) run on the fused CUDA path"
+            )
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _args(self, S, N, ldx, ll_scale, prior_weight, layout) -> nv.BjxElboArgs:
+        a = nv.BjxElboArgs()
+        a.S, a.N, a.D, a.Dw, a.w_offset, a.K, a.ldx = int(S), int(N), self.D, self.Dw, self.w_offset, self.K, int(ldx)
+        a.vi_type, a.scale_bijector, a.likelihood = self.vi_type, self.scale_bijector, self.lik_id
+        a.noise_src, a.noise_index, a.noise_value = self.noise_src, self.noise_index, self.noise_value
+        a.threefry_layout = layout
+        a.precision = self.precision
+        a.ll_scale, a.prior_weight = float(ll_scale), float(prior_weight)
+        a.coords = self.coords.data_ptr()
+        return a
+
+    def _workspace(self, a: nv.BjxElboArgs) -> torch.Tensor:
+        need = int(self.lib.bjx_elbo_workspace_bytes(C.byref(a)))
+        if need == 0:
+            raise nv.BjxError(nv.ERR_INVALID_ARGUMENT, self.lib.bjx_last_error().decode())
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _f32(t: torch.Tensor, device) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        if t.device != device or t.dtype != torch.float32:
+            t = t.to(device=device, dtype=torch.float32)
+        return t.contiguous()
+
+    def _data(self, X, y):
+        y = self._f32(y, self.device).reshape(-1)
+        N = y.numel()
+        if self.lik_id == nv.LIK_BERNOULLI_PROBS:
+            return None, y, N, 0
+        X = self._f32(X, self.device)
+        if X.dim() != 2 or X.shape[0] != N or X.shape[1] != self.Dw:
+            raise ValueError(f"X must be [N={N}, D={self.Dw}] (rows = data, row-major); got {tuple(X.shape)}")
+        return X, y, N, X.stride(0)
+
+    def kernel_choice(self, S, N) -> str:
+        a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        return nv.KERNEL_NAMES[nv.check(self.lib.bjx_elbo_kernel_choice(C.byref(a)))]
+
+    def step(self, key, loc, raw_scale, kwargs_vec, X, y, ll_scale, n_samples, prior_weight=1.0, out=None, eps_out=None,
+             partitionable=None) -> torch.Tensor:
+        """Enqueue one ELBO+grad step; returns the packed device tensor [loss | d loc | d raw_scale | d kwargs]."""
+        dev = self.device
+        key = brandom._check_key(key)
+        loc = self._f32(loc, dev).reshape(-1)
+        raw = self._f32(raw_scale, dev).reshape(-1)
+        if loc.numel() != self.D or raw.numel() != self.P:
+            raise ValueError(f"loc must have {self.D} and raw scale {self.P} elements")
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
+        a.key, a.loc, a.raw_scale = key.data_ptr(), loc.data_ptr(), raw.data_ptr()
+        kw = None
+        if self.K:
+            kw = self._f32(kwargs_vec, dev).reshape(-1)
+            if kw.numel() != self.K:
+                raise ValueError(f"expected {self.K} kwarg values")
+            a.kwargs = kw.data_ptr()
+        a.X = X.data_ptr() if X is not None else None
+        a.y = y.data_ptr()
+        if out is None:
+            out = torch.empty(1 + self.D + self.P + self.K, dtype=torch.float32, device=dev)
+        a.out = out.data_ptr()
+        if eps_out is not None:
+            a.eps_out = eps_out.data_ptr()
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(dev):
+            nv.check(self.lib.bjx_elbo_step(C.byref(a), nv.current_stream_ptr()))
+        return out
+
+    def step_host(self, key_host: np.ndarray, params_host: torch.Tensor, out_host: torch.Tensor, X, y, ll_scale, n_samples,
+                  prior_weight=1.0, partitionable=None) -> torch.Tensor:
+        """The same step through HOST buffers (pinned): key/params copied in, packed result copied out, stream synchronised.
+        X / y stay device-resident, as they do for the reference (closure constants of the jitted scan, utils.py:22-31)."""
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
+        a.X = X.data_ptr() if X is not None else None
+        a.y = y.data_ptr()
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        key_host = np.ascontiguousarray(key_host, dtype=np.uint32)
+        assert params_host.dtype == torch.float32 and params_host.numel() == self.D + self.P + self.K
+        assert out_host.dtype == torch.float32 and out_host.numel() == 1 + self.D + self.P + self.K
+        with torch.cuda.device(self.device):
+            nv.check(
+                self.lib.bjx_elbo_step_host(C.byref(a), key_host.ctypes.data, params_host.data_ptr(), out_host.data_ptr(), nv.current_stream_ptr())
+            )
+        return out_host
+
+    def posterior_sample(self, key, loc, raw_scale, n_samples, partitionable=None):
+        """theta[S, D] = bijector(loc + scale * normal(key, (S, D)))  (Posterior.sample, core.py:46-55)."""
+        dev = self.device
+        key = brandom._check_key(key)
+        loc = self._f32(loc, dev).reshape(-1)
+        raw = self._f32(raw_scale, dev).reshape(-1)
+        a = self._args(n_samples, 0, max(self.Dw, 1), 1.0, 1.0, brandom._layout(partitionable))
+        a.likelihood, a.w_offset, a.Dw = nv.LIK_BERNOULLI_PROBS, 0, 0
+        a.key, a.loc, a.raw_scale = key.data_ptr(), loc.data_ptr(), raw.data_ptr()
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        theta = torch.empty((int(n_samples), self.D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nv.check(self.lib.bjx_posterior_sample(C.byref(a), theta.data_ptr(), None, nv.current_stream_ptr()))
+        return theta

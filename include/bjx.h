@@ -1,0 +1,195 @@
+/* bjx.h -- C ABI of the B200-native ADVI engine (libbjx.so).
+ *
+ * This is the drop-in boundary for bijax's one hot path: the reparameterised
+ * Monte-Carlo ELBO and its gradient,
+ *     ADVI.loss_fn                     /root/reference/bijax/advi.py:80-95
+ *     under jax.value_and_grad          /root/reference/bijax/utils.py:7,25
+ * plus the PRNG calls that path makes (jax.random.normal / split / PRNGKey,
+ * call sites advi.py:77,83 and utils.py:30,53-55,70).
+ *
+ * Everything is plain pointers and sizes: no torch, no XLA types.  Three
+ * callers bind it:  (i) the XLA-FFI shim (bijax_b200/csrc/xla_ffi_shim.cc,
+ * built only where jaxlib's headers exist), (ii) the ctypes host layer
+ * (bijax_b200/_native.py) used by every test and by bench.py, (iii) any
+ * C/C++ driver.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - all array pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES
+ *     work on it (no device/stream synchronisation, no allocation), so a call
+ *     sequence is CUDA-graph capturable -- except the *_host entry points,
+ *     which copy and synchronise by design;
+ *   - return value 0 = success, negative = BJX_ERR_*; bjx_last_error() gives
+ *     the message for the calling thread.  Nothing throws across the ABI.
+ *   - float32 everywhere except PRNG keys / bits (uint32).
+ */
+#ifndef BJX_H_
+#define BJX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BJX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BJX_API __attribute__((visibility("default")))
+#else
+#define BJX_API
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+#define BJX_OK 0
+#define BJX_ERR_INVALID_ARGUMENT (-1)
+#define BJX_ERR_CUDA (-2)
+#define BJX_ERR_UNSUPPORTED (-3)
+#define BJX_ERR_WORKSPACE (-4)
+
+/* ---- jax.random counter layouts (jax_threefry_partitionable) ---------- */
+#define BJX_LAYOUT_LEGACY 0        /* default before JAX 0.5 */
+#define BJX_LAYOUT_PARTITIONABLE 1 /* default from JAX 0.5; counter = 64-bit flat index */
+
+/* ---- variational family: core.py:179-187 (mean field), 204-212 (full rank) */
+#define BJX_VI_MEAN_FIELD 0
+#define BJX_VI_FULL_RANK 1
+
+/* ---- bijector on the raw scale parameter (ordered_posterior_bijectors[1],
+ *      advi.py:33,45,65-67; default Exp, core.py:180-181) ------------------ */
+#define BJX_SCALE_EXP 0
+#define BJX_SCALE_SOFTPLUS 1
+#define BJX_SCALE_IDENTITY 2 /* full-rank default: identity on scale_tril */
+
+/* ---- bijector ops of prior_constraints (tfb.*), packed 4 bits each into
+ *      BjxCoord.chain, lowest nibble applied FIRST; 0 terminates.
+ *      tfb.Chain([b1, b2]) = b1 o b2  ->  chain = op(b2) | op(b1) << 4 ------ */
+#define BJX_BIJ_IDENTITY 0
+#define BJX_BIJ_EXP 1
+#define BJX_BIJ_SOFTPLUS 2
+#define BJX_BIJ_SIGMOID 3
+
+/* ---- prior families (tfd.*), one table row per latent coordinate -------- */
+#define BJX_PRIOR_NORMAL 0 /* p0 = loc, p1 = scale   (also each coordinate of MultivariateNormalDiag) */
+#define BJX_PRIOR_BETA 1   /* p0 = concentration1, p1 = concentration0 */
+#define BJX_PRIOR_GAMMA 2  /* p0 = concentration,  p1 = rate */
+
+typedef struct BjxCoord {
+  uint32_t prior; /* BJX_PRIOR_* */
+  uint32_t chain; /* packed BJX_BIJ_* ops */
+  float p0, p1;
+  float lognorm; /* additive normaliser of log p, computed on the host in double:
+                    Normal: -0.5*log(2pi) - log(scale); Beta: -lbeta(p0,p1);
+                    Gamma: p0*log(p1) - lgamma(p0) */
+} BjxCoord;
+
+/* ---- recognised likelihood families (advi.py:90-91; README.md:91-106) --- */
+#define BJX_LIK_BERNOULLI_LOGITS 0 /* tfd.Bernoulli(logits = X @ w).log_prob(y).sum() */
+#define BJX_LIK_GAUSSIAN 1         /* tfd.Normal(X @ w, tau).log_prob(y).sum(), tau from noise_src */
+#define BJX_LIK_BERNOULLI_PROBS 2  /* tfd.Bernoulli(probs = theta[w_offset]).log_prob(y).sum(); no X (coin toss) */
+
+/* where the Gaussian noise scale tau comes from */
+#define BJX_NOISE_CONST 0  /* tau = noise_value */
+#define BJX_NOISE_KWARG 1  /* tau = exp(kwargs[noise_index])  -- trainable log_noise_scale, README.md:104 */
+#define BJX_NOISE_LATENT 2 /* tau = theta[s, noise_index]     -- a constrained latent (e.g. Gamma prior + Exp) */
+
+/* ---- precision of the streaming contraction ----------------------------- */
+#define BJX_PREC_AUTO 0   /* tensor-core split path when the shape allows, else fp32 CUDA cores */
+#define BJX_PREC_FP32 1   /* fp32 FFMA on CUDA cores only */
+#define BJX_PREC_BF16X3 2 /* tcgen05, X/theta/dlogit each split in 3 bf16 terms (fp32-accurate) */
+#define BJX_PREC_BF16X2 3 /* tcgen05, 2-term split (about 2^-17 relative per product) */
+
+typedef struct BjxElboArgs {
+  /* sizes */
+  int64_t S;        /* n_samples (advi.py:80) */
+  int64_t N;        /* rows of X / entries of y held by THIS call (local shard) */
+  int64_t D;        /* size of the flat latent vector (core.py:168-176) */
+  int64_t Dw;       /* columns of X = number of regression weights (0 for BERNOULLI_PROBS) */
+  int64_t w_offset; /* first latent coordinate of the weights inside the flat vector */
+  int64_t K;        /* number of trainable likelihood kwargs (v1 surface, README.md:86) */
+  int64_t ldx;      /* row pitch of X in floats (>= Dw) */
+
+  /* static attributes */
+  int32_t vi_type;         /* BJX_VI_* */
+  int32_t scale_bijector;  /* BJX_SCALE_* */
+  int32_t likelihood;      /* BJX_LIK_* */
+  int32_t noise_src;       /* BJX_NOISE_* (Gaussian only) */
+  int32_t noise_index;     /* kwarg index or latent coordinate */
+  int32_t threefry_layout; /* BJX_LAYOUT_* */
+  int32_t precision;       /* BJX_PREC_* */
+  int32_t reserved0;
+  float noise_value;   /* BJX_NOISE_CONST */
+  float ll_scale;      /* full_data_size / len(outputs)   (advi.py:92; len = GLOBAL batch under sharding) */
+  float prior_weight;  /* weight of the q / prior terms in THIS call's outputs: 1 on one rank, 0 on the
+                          others (or 1/G everywhere) so that a sum over ranks is the reference's loss */
+  float reserved1;
+
+  /* inputs (device) */
+  const uint32_t* key;     /* [2]   per-step PRNG key (advi.py:83 seed) */
+  const float* loc;        /* [D]   params["posterior"].loc */
+  const float* raw_scale;  /* [D] raw scale_diag  |  [D*D] row-major raw scale_tril (upper part ignored) */
+  const float* kwargs;     /* [K]   or NULL */
+  const float* X;          /* [N, ldx] row-major, or NULL */
+  const float* y;          /* [N] */
+  const BjxCoord* coords;  /* [D]   prior + bijector table */
+
+  /* outputs (device) */
+  float* out;      /* packed [1 + D + P + K]: loss, d loc, d raw_scale (P = D or D*D), d kwargs.
+                      This buffer is the all-reduce message under data sharding. */
+  float* eps_out;  /* optional [S*D]: the standard-normal draws used (NULL to skip) */
+
+  /* scratch (device) */
+  void* workspace;
+  size_t workspace_bytes; /* >= bjx_elbo_workspace_bytes(args) */
+} BjxElboArgs;
+
+/* ---- library ------------------------------------------------------------ */
+BJX_API int bjx_abi_version(void);
+BJX_API const char* bjx_last_error(void);
+BJX_API int bjx_device_sm_count(void); /* SM count of the current device, cached; negative on error */
+
+/* ---- jax.random on the device (kernel 1) --------------------------------
+ * Flat indices [offset, offset+n) of the stream of `total` draws under `key`;
+ * `total` matters only to the legacy layout (the half split depends on it),
+ * where offset must be 0 and n == total. */
+BJX_API int bjx_random_bits(const uint32_t* key, int64_t total, int64_t offset, int64_t n, int32_t layout, uint32_t* out, void* stream);
+BJX_API int bjx_random_uniform(const uint32_t* key, int64_t total, int64_t offset, int64_t n, int32_t layout, float minval,
+                       float maxval, float* out, void* stream);
+BJX_API int bjx_random_normal(const uint32_t* key, int64_t total, int64_t offset, int64_t n, int32_t layout, float* out, void* stream);
+/* jax.random.split(key, num) -> out[num, 2]   (utils.py:30) */
+BJX_API int bjx_random_split(const uint32_t* key, int64_t num, int32_t layout, uint32_t* out, void* stream);
+
+/* ---- the hot path: loss and all gradients in one enqueue (kernels 2-6) --- */
+BJX_API size_t bjx_elbo_workspace_bytes(const BjxElboArgs* args);
+BJX_API int bjx_elbo_step(const BjxElboArgs* args, void* stream);
+/* Same step through HOST buffers: copies key / params in, packed result out, and synchronises the stream.
+ * params_host = [loc (D) | raw_scale (P) | kwargs (K)] contiguous; out_host = [1 + D + P + K].
+ * args->key / loc / raw_scale / kwargs / out are ignored (staging lives in the workspace); X, y, coords stay
+ * device-resident, as they are for the reference (closure constants of the jitted scan, utils.py:22-31). */
+BJX_API int bjx_elbo_step_host(const BjxElboArgs* args, const uint32_t* key_host, const float* params_host, float* out_host,
+                       void* stream);
+
+/* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = tcgen05 split-bf16 */
+BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
+
+/* ---- posterior access (.apply -> Posterior.sample / log_prob, core.py:39-75) */
+/* theta[S, D] = bijector(loc + scale * eps) for eps = normal(key, (S, D)); z_out optional */
+BJX_API int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out, void* stream);
+
+/* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27) */
+BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
+                    float b2, float eps, void* stream);
+
+/* ---- in-library timing of the dominant (streaming likelihood) kernel -------
+ * bjx_profile_begin(capacity): from now on every bjx_elbo_step on this thread records a CUDA event pair around its
+ * streaming-likelihood launch(es) on the caller's stream (no synchronisation); bjx_profile_collect synchronises on the
+ * recorded events and returns their durations in milliseconds; bjx_profile_end releases the events. */
+BJX_API int bjx_profile_begin(int32_t capacity);
+BJX_API int bjx_profile_collect(float* ms_out_host, int32_t max_out, int32_t* n_out_host);
+BJX_API int bjx_profile_end(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BJX_H_ */

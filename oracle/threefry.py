@@ -1,0 +1,183 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+CPU restatement, in NumPy, of the counter-based PRNG that sits under
+``jax.random`` -- the generator bijax reaches through
+``q.sample(seed=...)`` (/root/reference/bijax/advi.py:83), ``initialize_params``
+(/root/reference/bijax/utils.py:53-55, default initialiser advi.py:77) and
+``jax.random.split`` (/root/reference/bijax/utils.py:30,70).
+
+JAX / jaxlib are third-party, unpinned dependencies of the reference
+(/root/reference/requirements.txt:2-3) and are absent from this image, so
+this file restates their *published* algorithm:
+
+  * Threefry-2x32, 20 rounds (Salmon et al., "Parallel random numbers: as
+    easy as 1, 2, 3", SC'11; the Random123 known-answer vectors pin it);
+  * ``jax._src.prng`` counter layouts: the legacy one (default before JAX
+    0.5: iota split in halves) and the "partitionable" one (64-bit flat index
+    split hi/lo, outputs XOR-ed);
+  * ``jax.random.uniform`` bit trick (mantissa fill, minus one) and
+    ``jax.random.normal`` = sqrt(2) * erf_inv(uniform(-1, 1)), with XLA's
+    single-precision ``ErfInv`` (Giles' polynomial).
+
+Pinned spec of the float pipeline ("the spec" in DESIGN.md): every operation
+is IEEE-754 binary32 round-to-nearest with NO fused multiply-add, except
+``w = -log1p(-u*u)`` which is evaluated as
+``float32(-log1p(float64(float32(u*u))))`` -- i.e. the correctly rounded
+value of the true function of the rounded argument.  The CUDA kernel follows
+the same spec so that the two agree bit for bit.
+
+PARITY STATUS: pinned against the Random123 KATs and the publicly documented
+``jax.random`` outputs listed in tests/golden/threefry_kat.json; NOT pinned
+against a live JAX (none available here).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+U32 = np.uint32
+_MASK = np.uint64(0xFFFFFFFF)
+
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+LAYOUT_LEGACY = 0
+LAYOUT_PARTITIONABLE = 1
+
+
+def _rotl(x, r):
+    return ((x << U32(r)) | (x >> U32(32 - r))).astype(U32)
+
+
+def threefry2x32(k0, k1, x0, x1):
+    """Threefry-2x32-20 block function on uint32 arrays (broadcasting)."""
+    with np.errstate(over="ignore"):
+        k0 = np.asarray(k0, dtype=U32)
+        k1 = np.asarray(k1, dtype=U32)
+        x0 = np.asarray(x0, dtype=U32).copy()
+        x1 = np.asarray(x1, dtype=U32).copy()
+        ks = (k0, k1, (k0 ^ k1 ^ U32(0x1BD11BDA)).astype(U32))
+        x0 = (x0 + ks[0]).astype(U32)
+        x1 = (x1 + ks[1]).astype(U32)
+        for g in range(5):
+            for r in _ROT[g % 2]:
+                x0 = (x0 + x1).astype(U32)
+                x1 = _rotl(x1, r)
+                x1 = (x1 ^ x0).astype(U32)
+            x0 = (x0 + ks[(g + 1) % 3]).astype(U32)
+            x1 = (x1 + ks[(g + 2) % 3] + U32(g + 1)).astype(U32)
+    return x0, x1
+
+
+def prng_key(seed: int) -> np.ndarray:
+    """``jax.random.PRNGKey(seed)`` -> uint32[2] = [seed >> 32, seed & 0xffffffff]."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=U32)
+
+
+def random_bits(key, n: int, layout: int = LAYOUT_LEGACY, offset: int = 0) -> np.ndarray:
+    """n 32-bit draws for flat indices [offset, offset+n).
+
+    ``offset`` is only meaningful for the partitionable layout (counter =
+    global flat index, so any slice of a stream can be regenerated alone).
+    """
+    key = np.asarray(key, dtype=U32)
+    n = int(n)
+    if n == 0:
+        return np.zeros((0,), dtype=U32)
+    if layout == LAYOUT_LEGACY:
+        if offset:
+            raise ValueError("legacy layout is not prefix/shard stable; offset must be 0")
+        h = (n + 1) // 2
+        j = np.arange(h, dtype=np.uint64)
+        c0 = (j & _MASK).astype(U32)
+        c1 = ((j + np.uint64(h)) & _MASK).astype(U32)
+        if n % 2:
+            c1[-1] = 0  # the zero pad appended to the odd-sized iota
+        a, b = threefry2x32(key[0], key[1], c0, c1)
+        return np.concatenate([a, b])[:n]
+    if layout == LAYOUT_PARTITIONABLE:
+        i = np.arange(n, dtype=np.uint64) + np.uint64(offset)
+        hi = (i >> np.uint64(32)).astype(U32)
+        lo = (i & _MASK).astype(U32)
+        a, b = threefry2x32(key[0], key[1], hi, lo)
+        return (a ^ b).astype(U32)
+    raise ValueError(f"unknown layout {layout}")
+
+
+def split(key, num: int, layout: int = LAYOUT_LEGACY) -> np.ndarray:
+    """``jax.random.split(key, num)`` -> uint32[num, 2]."""
+    key = np.asarray(key, dtype=U32)
+    if layout == LAYOUT_LEGACY:
+        return random_bits(key, 2 * num, LAYOUT_LEGACY).reshape(num, 2)
+    i = np.arange(num, dtype=np.uint64)
+    a, b = threefry2x32(key[0], key[1], (i >> np.uint64(32)).astype(U32), (i & _MASK).astype(U32))
+    return np.stack([a, b], axis=-1)
+
+
+def bits_to_unit_float(bits: np.ndarray) -> np.ndarray:
+    """Mantissa fill: float32 in [0, 1) from the top 23 bits."""
+    bits = np.asarray(bits, dtype=U32)
+    f = ((bits >> U32(9)) | U32(0x3F800000)).view(np.float32)
+    return (f - np.float32(1.0)).astype(np.float32)
+
+
+def uniform_from_bits(bits, minval=0.0, maxval=1.0) -> np.ndarray:
+    """``jax.random.uniform`` float32: f*(maxval-minval)+minval, clamped below."""
+    f = bits_to_unit_float(bits)
+    lo = np.float32(minval)
+    hi = np.float32(maxval)
+    scale = np.float32(hi - lo)
+    u = (f * scale).astype(np.float32)
+    u = (u + lo).astype(np.float32)
+    return np.maximum(lo, u).astype(np.float32)
+
+
+_ERFINV_SMALL = [
+    2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087,
+    -0.00125372503, -0.00417768164, 0.246640727, 1.50140941,
+]
+_ERFINV_LARGE = [
+    -0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773,
+    -0.0076224613, 0.00943887047, 1.00167406, 2.83297682,
+]
+
+
+def erfinv_f32(u: np.ndarray) -> np.ndarray:
+    """XLA ErfInv (f32, Giles) under the pinned spec in the module docstring."""
+    u = np.asarray(u, dtype=np.float32)
+    t = (u * u).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = (-np.log1p(-(t.astype(np.float64)))).astype(np.float32)
+        small = w < np.float32(5.0)
+        ws = (w - np.float32(2.5)).astype(np.float32)
+        wl = (np.sqrt(w).astype(np.float32) - np.float32(3.0)).astype(np.float32)
+        ww = np.where(small, ws, wl).astype(np.float32)
+        p = np.where(small, np.float32(_ERFINV_SMALL[0]), np.float32(_ERFINV_LARGE[0])).astype(np.float32)
+        for cs, cl in zip(_ERFINV_SMALL[1:], _ERFINV_LARGE[1:]):
+            c = np.where(small, np.float32(cs), np.float32(cl)).astype(np.float32)
+            p = (p * ww).astype(np.float32)  # separate multiply ...
+            p = (c + p).astype(np.float32)   # ... and add: no FMA
+        r = (p * u).astype(np.float32)
+    r = np.where(np.abs(u) == np.float32(1.0), np.float32(np.inf) * u, r).astype(np.float32)
+    return r
+
+
+_LO = np.nextafter(np.float32(-1.0), np.float32(0.0))
+_SQRT2 = np.float32(np.sqrt(2.0))
+
+
+def normal_from_bits(bits) -> np.ndarray:
+    u = uniform_from_bits(bits, _LO, 1.0)
+    return (_SQRT2 * erfinv_f32(u)).astype(np.float32)
+
+
+def normal(key, shape, layout: int = LAYOUT_LEGACY, offset: int = 0) -> np.ndarray:
+    """``jax.random.normal(key, shape, float32)``."""
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    return normal_from_bits(random_bits(key, n, layout, offset)).reshape(shape)
+
+
+def uniform(key, shape, layout: int = LAYOUT_LEGACY, minval=0.0, maxval=1.0, offset: int = 0) -> np.ndarray:
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    return uniform_from_bits(random_bits(key, n, layout, offset), minval, maxval).reshape(shape)

@@ -1,0 +1,209 @@
+"""GPU: loss and every gradient of the fused CUDA step against the float64 oracle on the same key and inputs.
+Tolerance: rtol 1e-5 (north_star), with an absolute floor of 1e-5 x the largest entry of each gradient block."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from bijax_b200 import bijectors as tfb
+from bijax_b200 import distributions as tfd
+from bijax_b200 import likelihoods as lk
+from oracle import threefry as tf
+from tests import cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(model, ref, loc, raw, kwargs, y, X, full, seed, S, layout, expect_kernel=None):
+    from bijax_b200 import random as br
+
+    dev = torch.device("cuda")
+    key = br.PRNGKey(seed)
+    params = {"posterior": {"loc": torch.tensor(loc, device=dev), ("scale_diag" if model.vi_type == "mean_field" else "scale_tril"): torch.tensor(raw, device=dev)}}
+    for k, v in kwargs.items():
+        params[k] = torch.tensor(v, dtype=torch.float32, device=dev)
+    br.config.threefry_partitionable = bool(layout)
+    try:
+        yt = torch.tensor(y, device=dev)
+        inputs = {"X": torch.tensor(X, device=dev)} if X is not None else None
+        loss, grads = model.value_and_grad(params, yt, inputs, full, key, S)
+        # the autograd route must give the same numbers
+        leaves = {k: v.clone().requires_grad_(True) for k, v in kwargs.items()}
+        p2 = {"posterior": {k: v.clone().requires_grad_(True) for k, v in params["posterior"].items()}}
+        p2.update({k: torch.tensor(v, dtype=torch.float32, device=dev, requires_grad=True) for k, v in kwargs.items()})
+        l2 = model.loss_fn(p2, yt, inputs, full, key, S)
+        l2.backward()
+    finally:
+        br.config.threefry_partitionable = False
+    (wl, wgl, wgr, wgk), eps = C.oracle_step(ref, loc, raw, kwargs, y, X, full, tf.prng_key(seed), S, layout)
+    if expect_kernel is not None:
+        eng = next(iter(model._engines.values()))
+        assert eng.kernel_choice(S, len(y)) == expect_kernel
+    skey = "scale_diag" if model.vi_type == "mean_field" else "scale_tril"
+    C.assert_close(loss.item(), wl.item(), what="loss")
+    C.assert_close(grads["posterior"]["loc"].cpu().numpy(), wgl.numpy(), what="d loc")
+    C.assert_close(grads["posterior"][skey].cpu().numpy(), wgr.numpy(), what="d raw scale")
+    for k in kwargs:
+        C.assert_close(grads[k].cpu().numpy(), wgk[k].numpy(), what=f"d {k}")
+        assert torch.equal(p2[k].grad, grads[k].reshape(p2[k].shape))
+    assert l2.item() == loss.item()
+    assert torch.equal(p2["posterior"]["loc"].grad, grads["posterior"]["loc"])
+    assert torch.equal(p2["posterior"][skey].grad, grads["posterior"][skey])
+    return loss, grads
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_c1_coin_toss(layout):
+    """config c1: Beta(0.5,0.5) prior, Sigmoid bijector, 100 Bernoulli observations, S=16 (README.md:41,91-95)."""
+    model, ref = C.build_pair({"p_of_heads": tfd.Beta(0.5, 0.5)}, {"p_of_heads": tfb.Sigmoid()}, lk.BernoulliProbs("p_of_heads"))
+    init = tf.normal(tf.prng_key(0), (2,), layout)
+    y = np.array([1.0 if n % 10 < 7 else 0.0 for n in range(100)], dtype=np.float32)
+    loss, _ = _run_case(model, ref, init[:1], init[1:], {}, y, None, 100, 1, 16, layout, expect_kernel="coin")
+    if layout == 0:  # SURVEY.md appendix C known answer
+        assert abs(loss.item() - 200.757306865) < 200.76 * 1e-5
+
+
+@pytest.mark.parametrize("N,S", [(4096, 64), (1000, 7), (1, 3), (300, 300)])
+def test_c2_linear_regression_learnable_noise_small_d(N, S):
+    """config c2 shape family: D=5, Gaussian likelihood with trainable log_noise_scale (README.md:99-106)."""
+    D = 5
+    X, y = C.synth_linear(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.GaussianLinear())
+    loc = 0.1 * tf.normal(tf.prng_key(3), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32) + 0.05 * tf.normal(tf.prng_key(4), (D,), 1)
+    _run_case(model, ref, loc, raw, {"log_noise_scale": np.float32(math.log(0.3))}, y, X, 10 * N, 7, S, 0, expect_kernel="fp32_smalld")
+
+
+@pytest.mark.parametrize("D", [1, 3, 4, 8, 11, 15])
+def test_small_d_every_record_width(D):
+    N, S = 777, 16
+    X, y = C.synth_logistic(N, D)
+    prior = {"weights": tfd.Normal(np.zeros(D, np.float32), 2.0)}
+    model, ref = C.build_pair(prior, {}, lk.BernoulliLogits())
+    loc = 0.3 * tf.normal(tf.prng_key(13), (D,), 1)
+    raw = -1.0 + 0.1 * tf.normal(tf.prng_key(14), (D,), 1)
+    _run_case(model, ref, loc, raw, {}, y, X, N, 21, S, 1, expect_kernel="fp32_smalld")
+
+
+@pytest.mark.parametrize("N,D,S", [(3000, 48, 8), (129, 16, 33), (5000, 200, 32), (640, 512, 16)])
+def test_logistic_regression_fp32_tiled(N, D, S):
+    """config c3 shape family at sizes the oracle finishes in seconds, forced onto the CUDA-core fallback."""
+    X, y = C.synth_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="fp32")
+    loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    _run_case(model, ref, loc, raw, {}, y, X, 4 * N, 11, S, 0, expect_kernel="fp32_tiled")
+
+
+@pytest.mark.parametrize("D,S,lik", [(24, 10, "gauss"), (70, 5, "logit")])
+def test_full_rank(D, S, lik):
+    """config c4 shape family: dense D x D raw scale_tril (upper triangle ignored, zero gradient), well-conditioned M."""
+    N = 500
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if lik == "gauss":
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), vi_type="full_rank", precision="fp32")
+        kwargs = {"log_noise_scale": np.float32(math.log(0.2))}
+    else:
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), vi_type="full_rank", precision="fp32")
+        kwargs = {}
+    loc = 0.1 * tf.normal(tf.prng_key(6), (D,), 1)
+    M = (0.1 * np.eye(D) + 0.01 * tf.normal(tf.prng_key(8), (D, D), 1)).astype(np.float32)  # conditioning stated: 0.1 I + 0.01 noise
+    loss, grads = _run_case(model, ref, loc, M, kwargs, y, X, N, 17, S, 0)
+    g = grads["posterior"]["scale_tril"].cpu().numpy()
+    assert np.all(np.triu(g, 1) == 0.0)
+
+
+def test_constrained_latents_priors_and_chains():
+    """Gamma + Exp, Beta + Sigmoid, Normal + Softplus chain, plus a latent noise scale feeding the Gaussian likelihood."""
+    N, D, S = 600, 6, 12
+    X, y = C.synth_linear(N, D, noise=0.5)
+    prior = {
+        "weights": tfd.Normal(np.zeros(D, np.float32), 1.5),
+        "noise": tfd.Gamma(2.0, 3.0),
+        "aux_beta": tfd.Beta(np.array([2.0, 0.5], np.float32), np.array([3.0, 1.0], np.float32)),
+        "aux_pos": tfd.Gamma(1.0, 0.5),
+        "aux_chain": tfd.Normal(1.0, 0.7),
+    }
+    bij = {
+        "noise": tfb.Exp(),
+        "aux_beta": tfb.Sigmoid(),
+        "aux_pos": tfb.Softplus(),
+        "aux_chain": tfb.Chain([tfb.Softplus(), tfb.Exp()]),
+    }
+    model, ref = C.build_pair(prior, bij, lk.GaussianLinear(noise_latent="noise"))
+    Dtot = model.size
+    loc = 0.3 * tf.normal(tf.prng_key(31), (Dtot,), 1)
+    raw = -1.5 + 0.2 * tf.normal(tf.prng_key(32), (Dtot,), 1)
+    _run_case(model, ref, loc, raw, {}, y, X, N, 33, S, 1)
+
+
+def test_softplus_scale_bijector_and_constant_noise():
+    N, D, S = 400, 5, 9
+    X, y = C.synth_linear(N, D)
+    prior = {"weights": tfd.Normal(np.zeros(D, np.float32), 1.0)}
+    model, ref = C.build_pair(prior, {}, lk.GaussianLinear(noise_scale=0.25), scale_bijector=tfb.Softplus())
+    loc = 0.2 * tf.normal(tf.prng_key(41), (D,), 1)
+    raw = -2.0 + 0.3 * tf.normal(tf.prng_key(42), (D,), 1)
+    _run_case(model, ref, loc, raw, {}, y, X, 3 * N, 43, S, 0)
+
+
+def test_eps_is_bit_exact_and_step_is_deterministic():
+    from bijax_b200 import random as br
+
+    N, D, S = 2000, 64, 8
+    X, y = C.synth_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="fp32")
+    dev = torch.device("cuda")
+    params = {"posterior": {"loc": torch.zeros(D, device=dev), "scale_diag": torch.full((D,), -2.0, device=dev)}}
+    eng, _ = model._engine_for({})
+    key = br.PRNGKey(77)
+    for layout in (0, 1):
+        eps = torch.empty(S * D, device=dev)
+        out1 = eng.step(key, params["posterior"]["loc"], params["posterior"]["scale_diag"], None, torch.tensor(X, device=dev),
+                        torch.tensor(y, device=dev), 1.0, S, eps_out=eps, partitionable=bool(layout)).clone()
+        out2 = eng.step(key, params["posterior"]["loc"], params["posterior"]["scale_diag"], None, torch.tensor(X, device=dev),
+                        torch.tensor(y, device=dev), 1.0, S, partitionable=bool(layout))
+        want = tf.normal(tf.prng_key(77), (S, D), layout).ravel()
+        assert np.array_equal(eps.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        assert torch.equal(out1, out2), "two runs of the same step must agree bit for bit"
+
+
+def test_host_buffer_entry_point_matches_device_entry_point():
+    from bijax_b200 import random as br
+
+    N, D, S = 1500, 5, 16
+    X, y = C.synth_linear(N, D)
+    prior = {"weights": tfd.Normal(np.zeros(D, np.float32), 1.0)}
+    model, _ = C.build_pair(prior, {}, lk.GaussianLinear())
+    dev = torch.device("cuda")
+    loc = torch.linspace(-0.2, 0.2, D)
+    raw = torch.full((D,), -2.0)
+    lns = torch.tensor([-1.0])
+    eng, _ = model._engine_for({"log_noise_scale": lns})
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    out_dev = eng.step(br.PRNGKey(9), loc.to(dev), raw.to(dev), lns.to(dev), Xd, yd, 2.0, S)
+    ph = torch.cat([loc, raw, lns]).pin_memory()
+    oh = torch.empty(1 + 2 * D + 1).pin_memory()
+    eng.step_host(tf.prng_key(9), ph, oh, Xd, yd, 2.0, S)
+    assert torch.equal(out_dev.cpu(), oh)
+
+
+def test_error_paths():
+    from bijax_b200 import _native as nv
+    from bijax_b200 import random as br
+
+    D = 4
+    prior = {"weights": tfd.Normal(np.zeros(D, np.float32), 1.0)}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits())
+    dev = torch.device("cuda")
+    params = {"posterior": {"loc": torch.zeros(D, device=dev), "scale_diag": torch.zeros(D, device=dev)}}
+    with pytest.raises(ValueError):
+        model.value_and_grad(params, torch.zeros(10, device=dev), {"X": torch.zeros(10, D + 1, device=dev)}, 10, br.PRNGKey(0), 4)
+    with pytest.raises(TypeError):
+        model.value_and_grad(params, torch.zeros(10, device=dev), {"X": torch.zeros(10, D, device=dev)}, 10, torch.zeros(2), 4)

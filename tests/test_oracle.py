@@ -1,0 +1,129 @@
+"""CPU: pin the oracle against every known-answer vector we have, and its gradient against finite differences."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import advi_ref as R
+from oracle import threefry as tf
+
+KAT = json.loads((Path(__file__).parent / "golden" / "threefry_kat.json").read_text())
+
+
+def test_threefry_block_kats():
+    for v in KAT["threefry2x32"]:
+        k = [int(x, 16) for x in v["key"]]
+        c = [int(x, 16) for x in v["ctr"]]
+        a, b = tf.threefry2x32(k[0], k[1], c[0], c[1])
+        assert [int(a), int(b)] == [int(x, 16) for x in v["out"]]
+
+
+def test_split_legacy_doc_value():
+    assert tf.split(tf.prng_key(0), 2, tf.LAYOUT_LEGACY).tolist() == KAT["split_legacy_seed0_num2"]
+
+
+def test_normal_and_uniform_doc_values():
+    for v in KAT["normal"]:
+        key = tf.prng_key(v["seed"])
+        for name, layout in (("legacy", tf.LAYOUT_LEGACY), ("partitionable", tf.LAYOUT_PARTITIONABLE)):
+            got = tf.normal(key, tuple(v["shape"]), layout).ravel()[0]
+            ulp = abs(int(np.float32(got).view(np.int32)) - int(np.float32(v[name]).view(np.int32)))
+            assert ulp <= v["max_ulp"][name], (v, name, got)
+    assert tf.uniform(tf.prng_key(0), (), tf.LAYOUT_LEGACY) == np.float32(KAT["uniform_legacy_seed0"])
+
+
+def test_shape_invariance_and_offsets():
+    key = tf.prng_key(7)
+    for layout in (0, 1):
+        a = tf.normal(key, (6, 5), layout)
+        b = tf.normal(key, (30,), layout)
+        assert np.array_equal(a.ravel(), b)
+    full = tf.random_bits(key, 1000, tf.LAYOUT_PARTITIONABLE)
+    part = tf.random_bits(key, 100, tf.LAYOUT_PARTITIONABLE, offset=333)
+    assert np.array_equal(full[333:433], part)
+    # odd sizes exercise the zero pad of the legacy layout
+    assert tf.random_bits(key, 7, tf.LAYOUT_LEGACY).shape == (7,)
+
+
+def test_normal_moments():
+    x = tf.normal(tf.prng_key(3), (200000,), tf.LAYOUT_PARTITIONABLE).astype(np.float64)
+    assert abs(x.mean()) < 0.01 and abs(x.std() - 1.0) < 0.01
+    assert np.isfinite(x).all()
+
+
+def _coin_model():
+    return R.ADVIRef({"p": R.Beta(0.5, 0.5)}, {"p": R.Sigmoid()}, R.bernoulli_probs_loglik("p"))
+
+
+def test_golden_coin_toss_vector():
+    """SURVEY.md appendix C (legacy layout): restatement-derived known answer for config c1."""
+    init = tf.normal(tf.prng_key(0), (2,), tf.LAYOUT_LEGACY)
+    eps = tf.normal(tf.prng_key(1), (16, 1), tf.LAYOUT_LEGACY)
+    y = torch.tensor([1.0 if n % 10 < 7 else 0.0 for n in range(100)], dtype=torch.float64)
+    loc = torch.tensor([float(init[0])], dtype=torch.float64)
+    raw = torch.tensor([float(init[1])], dtype=torch.float64)
+    loss, gl, gr, _ = _coin_model().value_and_grad(loc, raw, {}, y, None, 100, torch.tensor(eps, dtype=torch.float64))
+    assert abs(loss.item() - 200.757306865) < 1e-6
+    assert abs(gl.item() - (-47.500152711)) < 1e-6
+    assert abs(gr.item() - 133.430885412) < 1e-6
+
+
+@pytest.mark.parametrize("vi_type", ["mean_field", "full_rank"])
+def test_gradient_matches_finite_differences(vi_type):
+    torch.manual_seed(0)
+    D, N, S = 4, 50, 6
+    X = torch.randn(N, D, dtype=torch.float64) / 2
+    y = (torch.rand(N, dtype=torch.float64) < 0.5).double()
+    m = R.ADVIRef({"weights": R.MultivariateNormalDiag(torch.zeros(D), torch.ones(D))}, {}, R.bernoulli_logits_loglik(), vi_type)
+    loc = torch.randn(D, dtype=torch.float64) * 0.3
+    raw = torch.randn(D, dtype=torch.float64) * 0.2 if vi_type == "mean_field" else (0.5 * torch.eye(D) + 0.1 * torch.randn(D, D)).double()
+    eps = torch.randn(S, D, dtype=torch.float64)
+    loss, gl, gr, _ = m.value_and_grad(loc, raw, {}, y, {"X": X}, 3 * N, eps)
+    h = 1e-6
+    for i in range(D):
+        e = torch.zeros(D, dtype=torch.float64)
+        e[i] = h
+        fd = (m.loss(loc + e, raw, {}, y, {"X": X}, 3 * N, eps) - m.loss(loc - e, raw, {}, y, {"X": X}, 3 * N, eps)) / (2 * h)
+        assert abs(fd.item() - gl[i].item()) < 1e-5 * max(1.0, abs(fd.item()))
+    flat = raw.reshape(-1)
+    for i in range(flat.numel()):
+        e = torch.zeros_like(flat)
+        e[i] = h
+        fp = m.loss(loc, (flat + e).reshape(raw.shape), {}, y, {"X": X}, 3 * N, eps)
+        fm = m.loss(loc, (flat - e).reshape(raw.shape), {}, y, {"X": X}, 3 * N, eps)
+        fd = (fp - fm) / (2 * h)
+        assert abs(fd.item() - gr.reshape(-1)[i].item()) < 1e-5 * max(1.0, abs(fd.item()))
+    if vi_type == "full_rank":  # MultivariateNormalTriL masks the strict upper triangle: zero gradient there
+        assert torch.all(torch.triu(gr, diagonal=1) == 0)
+
+
+def test_batched_restatements_agree_with_the_per_sample_one():
+    torch.manual_seed(1)
+    D, N, S = 5, 40, 7
+    X = torch.randn(N, D, dtype=torch.float64)
+    eps = torch.randn(S, D, dtype=torch.float64)
+    loc, raw = torch.randn(D, dtype=torch.float64) * 0.1, torch.randn(D, dtype=torch.float64) * 0.1 - 1
+    prior = {"weights": R.MultivariateNormalDiag(torch.zeros(D), torch.ones(D))}
+    y = (torch.rand(N, dtype=torch.float64) < 0.4).double()
+    a = R.ADVIRef(prior, {}, R.bernoulli_logits_loglik()).value_and_grad(loc, raw, {}, y, {"X": X}, N, eps)
+    b = R.logistic_meanfield_value_and_grad(loc, raw, X, y, N, eps)
+    for u, v in zip(a[:3], b):
+        assert torch.allclose(u, v, rtol=1e-12, atol=1e-12)
+    yl = torch.randn(N, dtype=torch.float64)
+    lns = torch.tensor(-0.7, dtype=torch.float64)
+    a = R.ADVIRef(prior, {}, R.gaussian_linear_loglik()).value_and_grad(loc, raw, {"log_noise_scale": lns}, yl, {"X": X}, 2 * N, eps)
+    b = R.linreg_meanfield_value_and_grad(loc, raw, lns, X, yl, 2 * N, eps)
+    assert torch.allclose(a[0], b[0], rtol=1e-12) and torch.allclose(a[1], b[1], rtol=1e-12) and torch.allclose(a[2], b[2], rtol=1e-12)
+    assert torch.allclose(a[3]["log_noise_scale"], b[3], rtol=1e-12)
+
+
+def test_coin_toss_loss_is_bounded_by_the_log_evidence():
+    """coin_toss.ipynb: tosses [0,1,1,1,1,0], prior Beta(1,2): log evidence -4.941642, so -ELBO >= 4.9416 for any q."""
+    y = torch.tensor([0, 1, 1, 1, 1, 0], dtype=torch.float64)
+    m = R.ADVIRef({"p": R.Beta(1.0, 2.0)}, {"p": R.Sigmoid()}, R.bernoulli_probs_loglik("p"))
+    eps = torch.tensor(tf.normal(tf.prng_key(5), (4000, 1), tf.LAYOUT_PARTITIONABLE), dtype=torch.float64)
+    # the exact posterior Beta(5,4) pushed through logit is close to N(0.24, 0.68): the bound must be near-tight there
+    loss = m.loss(torch.tensor([0.24], dtype=torch.float64), torch.log(torch.tensor([0.68], dtype=torch.float64)), {}, y, None, 6, eps)
+    assert 4.9416 - 0.02 < loss.item() < 5.0
