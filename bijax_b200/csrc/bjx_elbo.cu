@@ -170,6 +170,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   p.o_gprior = take(SD);
   p.o_gz = take(a.vi_type == BJX_VI_FULL_RANK ? SD : 0);
   p.o_qp = take((size_t)p.n_qp_blocks * sizeof(float));
+  p.o_aux = take((size_t)a.S * sizeof(float4));
   p.o_G = take((size_t)a.S * Dw * sizeof(float));
   p.o_stat = take((size_t)a.S * sizeof(float));
   p.o_Gpart = take((size_t)p.PG * a.S * Dw * sizeof(float));
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
                                                   float* __restrict__ eps_buf, const float* __restrict__ z_buf,
                                                   float* __restrict__ theta, float* __restrict__ bprime,
                                                   float* __restrict__ gprior, float* __restrict__ qp_part,
-                                                  float* __restrict__ eps_out) {
+                                                  float* __restrict__ eps_out, int64_t probs_coord,
+                                                  float4* __restrict__ probs_aux) {
   __shared__ float red[32];
   const int64_t total = S * D;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
     theta[i] = ce.theta;
     bprime[i] = ce.dtheta;
     gprior[i] = -ce.dlogp;
+    if (d == probs_coord) probs_aux[i / D] = make_float4(ce.lt, ce.l1t, ce.dlt, ce.dl1t);
     // q.log_prob per coordinate (z - loc)/sigma == eps, minus the unconstrained prior's log density
     term = (-0.5f * eps * eps - logsig - BJX_HALF_LOG_2PI) - ce.logp;
   }
@@ -317,18 +320,17 @@ __global__ void __launch_bounds__(256) k_fullrank_dM(const float* __restrict__ g
 }
 
 // ---- coin toss (tfd.Bernoulli(probs=p).log_prob(y).sum(), README.md:91-95): one block per sample ---------------------
-__global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
-                                                  int64_t D, int64_t w_off, float* __restrict__ G, float* __restrict__ stat) {
+// aux[s] = (log p, log(1-p), d log p / dz, d log(1-p) / dz) from the prologue; G[s] is d ll_s / d z (not d/d theta).
+__global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, int64_t N, const float4* __restrict__ aux,
+                                                  float* __restrict__ G, float* __restrict__ stat) {
   __shared__ float red[32];
   const int s = blockIdx.x;
-  const float p = theta[(int64_t)s * D + w_off];
-  const float lp = logf(p), l1p = log1pf(-p);
-  const float ip = 1.0f / p, i1p = 1.0f / (1.0f - p);
+  const float4 a = aux[s];
   float f = 0.0f, g = 0.0f;
   for (int64_t n = threadIdx.x; n < N; n += 256) {
     const float k = y[n];
-    f += (1.0f - k) * l1p + k * lp;
-    g += k * ip - (1.0f - k) * i1p;
+    f += (1.0f - k) * a.y + k * a.x;
+    g += (1.0f - k) * a.w + k * a.z;
   }
   const float fs = block_sum(f, red);
   const float gs = block_sum(g, red);
@@ -396,7 +398,9 @@ __global__ void __launch_bounds__(128) k_tail(TailArgs t, const float* __restric
       const float tau = theta[i];
       dll = (stat[s] / (tau * tau) - (float)t.N) / tau;  // d/dtau [ -Q/(2 tau^2) - N log tau ]
     }
-    const float gz = t.prior_weight * gprior[i] * invS - cS * dll * bprime[i];
+    // the coin kernel already differentiated with respect to z
+    const float bp = t.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1.0f : bprime[i];
+    const float gz = t.prior_weight * gprior[i] * invS - cS * dll * bp;
     if (gz_out) gz_out[i] = gz;
     acc_mu += gz;
     acc_rho = fmaf(gz, eps[i], acc_rho);
@@ -446,6 +450,8 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
   float* bprime = (float*)(ws + p.o_bprime);
   float* gprior = (float*)(ws + p.o_gprior);
   float* qp = (float*)(ws + p.o_qp);
+  float4* aux = (float4*)(ws + p.o_aux);
+  const int64_t probs_coord = (a.likelihood == BJX_LIK_BERNOULLI_PROBS && a.N > 0) ? a.w_offset : -1;
   const int64_t total = a.S * a.D;
   if (a.vi_type == BJX_VI_FULL_RANK) {
     k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, total, a.threefry_layout, eps);
@@ -454,10 +460,12 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
     k_fullrank_z<<<grid, 256, 0, st>>>(eps, a.raw_scale, a.loc, a.S, a.D, a.scale_bijector, z);
     BJX_LAUNCH_CHECK("k_fullrank_z");
     k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
-                                                    a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out);
+                                                    a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
+                                                    probs_coord, aux);
   } else {
     k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
-                                                     a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out);
+                                                     a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out,
+                                                     probs_coord, aux);
   }
   BJX_LAUNCH_CHECK("k_prologue");
   return BJX_OK;
@@ -483,7 +491,7 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   float* stat = (float*)(ws + p.o_stat);
   const int64_t Dw = a.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : a.Dw;
   if (p.kernel == KERNEL_COIN) {
-    k_lik_coin<<<(unsigned)a.S, 256, 0, st>>>(a.y, a.N, (const float*)(ws + p.o_theta), a.D, a.w_offset, G, stat);
+    k_lik_coin<<<(unsigned)a.S, 256, 0, st>>>(a.y, a.N, (const float4*)(ws + p.o_aux), G, stat);
     BJX_LAUNCH_CHECK("k_lik_coin");
   } else {
     if (a.N == 0) {

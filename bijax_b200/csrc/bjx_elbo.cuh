@@ -21,7 +21,7 @@ struct Plan {
   // tensor-core
   int tc_ctas, tc_terms;
   // byte offsets into the workspace
-  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta,
+  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta,
       o_stage_key, o_stage_params, o_stage_out, total;
 };
 

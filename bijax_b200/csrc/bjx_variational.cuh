@@ -36,6 +36,9 @@ struct CoordEval {
   float dtheta;   // d theta / d z
   float logp;     // log p(b(z)) + fldj_b(z)   (density of z under the unconstrained prior, core.py:117)
   float dlogp;    // d logp / d z
+  // log(theta), log(1 - theta) and their z-derivatives, free of the saturation of sigmoid in fp32 (used when theta
+  // feeds tfd.Bernoulli(probs=theta): the coin-toss likelihood)
+  float lt, l1t, dlt, dl1t;
 };
 
 // Forward pass of a bijector chain with its log-det-Jacobian and both first derivatives, then the prior at theta.
@@ -67,7 +70,7 @@ __device__ __forceinline__ CoordEval eval_coord(float z, const BjxCoord c) {
     } else {  // sigmoid
       const float sg = sigmoid_f(x);
       y = sg;
-      dy = sg * (1.0f - sg);
+      dy = sg * sigmoid_f(-x);
       f = -softplus_f(-x) - softplus_f(x);
       df = 1.0f - 2.0f * sg;
     }
@@ -90,7 +93,7 @@ __device__ __forceinline__ CoordEval eval_coord(float z, const BjxCoord c) {
       // log(theta) = -softplus(-x), log(1-theta) = -softplus(x): no cancellation when theta rounds to 0 or 1
       const float lt = -softplus_f(-x_in_last), l1t = -softplus_f(x_in_last);
       lp = (am1 == 0.0f ? 0.0f : am1 * lt) + (bm1 == 0.0f ? 0.0f : bm1 * l1t) + c.lognorm;
-      dlp_dz = (am1 * (1.0f - x) - bm1 * x) * dx_in_last;
+      dlp_dz = (am1 * sigmoid_f(-x_in_last) - bm1 * x) * dx_in_last;
     } else {
       lp = (am1 == 0.0f ? 0.0f : am1 * logf(x)) + (bm1 == 0.0f ? 0.0f : bm1 * log1pf(-x)) + c.lognorm;
       dlp_dz = (am1 / x - bm1 / (1.0f - x)) * dx;
@@ -107,6 +110,17 @@ __device__ __forceinline__ CoordEval eval_coord(float z, const BjxCoord c) {
   }
   r.logp = lp + ldj;
   r.dlogp = dlp_dz + dldj;
+  if (last_op == BJX_BIJ_SIGMOID) {
+    r.lt = -softplus_f(-x_in_last);
+    r.l1t = -softplus_f(x_in_last);
+    r.dlt = sigmoid_f(-x_in_last) * dx_in_last;
+    r.dl1t = -x * dx_in_last;
+  } else {
+    r.lt = logf(x);
+    r.l1t = log1pf(-x);
+    r.dlt = dx / x;
+    r.dl1t = -dx / (1.0f - x);
+  }
   return r;
 }
 

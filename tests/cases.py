@@ -115,6 +115,8 @@ def assert_close(got, want, rtol=1e-5, atol_scale=1e-5, what=""):
     """rtol 1e-5 as north_star states; entries that are tiny relative to the largest one get an absolute floor."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
+    assert np.isfinite(want).all(), f"{what}: oracle value is not finite"
+    assert np.isfinite(got).all(), f"{what}: result is not finite: {got}"
     scale = max(float(np.max(np.abs(want))), 1e-30)
     err = np.abs(got - want)
     tol = rtol * np.abs(want) + atol_scale * scale

@@ -29,7 +29,6 @@ def _run_case(model, ref, loc, raw, kwargs, y, X, full, seed, S, layout, expect_
         inputs = {"X": torch.tensor(X, device=dev)} if X is not None else None
         loss, grads = model.value_and_grad(params, yt, inputs, full, key, S)
         # the autograd route must give the same numbers
-        leaves = {k: v.clone().requires_grad_(True) for k, v in kwargs.items()}
         p2 = {"posterior": {k: v.clone().requires_grad_(True) for k, v in params["posterior"].items()}}
         p2.update({k: torch.tensor(v, dtype=torch.float32, device=dev, requires_grad=True) for k, v in kwargs.items()})
         l2 = model.loss_fn(p2, yt, inputs, full, key, S)
