@@ -1,8 +1,424 @@
-// placeholder until the tcgen05 kernel lands
+// Kernel 5+6 on the 5th-generation tensor cores (tcgen05 + TMEM), one pass over X.
+//
+// For a tile of 64 data rows the CTA computes
+//     eta[n, s]  = sum_d X[n, d] theta[s, d]              GEMM1  (M = 64 rows, N = samples, K = D)
+//     g[n, s]    = d/d eta log p(y_n | eta)                epilogue from TMEM (sigmoid / residual), stat[s] += f
+//     G^T[d, s] += sum_n X[n, d] g[n, s]                   GEMM2  (M = 128-column chunk of D, N = samples, K = 64 rows)
+// so the transposed contraction of the VJP (utils.py:7) reuses the X tile while it is still in shared memory: X is
+// read from HBM exactly once per step (4*N*D + 4*N algorithmic bytes).
+//
+// fp32 inputs are not representable on the tensor cores, so every operand is split on the fly into bf16 terms
+// (x = x1 + x2 + ..., |x2| <= 2^-9 |x1|): products x1*t1 + x1*t2 + x2*t1 (+ x2*t2) accumulate in fp32 in TMEM.  The X
+// tile is converted in registers by the loader warps straight after the coalesced 128-bit global loads and stored in the
+// canonical UMMA shared-memory layout (128-byte swizzle), which serves GEMM1 as a K-major A operand and GEMM2 as an
+// MN-major A operand without a second copy or a transpose.
+//
+// Warp roles (544 threads, 1 CTA per SM, persistent over row tiles):
+//   warps 0-7   loaders: LDG.128 (2 blocks in flight) -> bf16 split -> STS.128 swizzled -> mbarrier
+//   warp  8     MMA issuer (one elected lane), owns the TMEM allocation
+//   warps 9-16  epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
+#include <cuda_bf16.h>
+
 #include "bjx_elbo.cuh"
+
 namespace bjx {
-bool tc_eligible(const BjxElboArgs&) { return false; }
-int tc_plan(const BjxElboArgs&, Plan&) { return fail(BJX_ERR_UNSUPPORTED, "tcgen05 path not built"); }
+
+namespace tc {
+
+constexpr int TILE_ROWS = 64;      // rows per tile = UMMA M of GEMM1
+constexpr int BLK_COLS = 64;       // columns per shared-memory block (64 bf16 = one 128-byte swizzle row)
+constexpr int BLK_BYTES = TILE_ROWS * 128;  // 8 KB
+constexpr int NS = 32;             // samples per pass (padded)
+constexpr int NB = 64;             // UMMA N when both split terms of the B operand are used ([t1; t2] / [e1; e2])
+constexpr int LOADER_WARPS = 8, LOADER_THREADS = 256;
+constexpr int MMA_WARP = 8;
+constexpr int EPI_WARP0 = 9, EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 544
+constexpr int TMEM_COLS = 512;
+constexpr int ACC1_COL = 0;        // 64 columns: logits [x*t1 | x1*t2]
+constexpr int ACC2_COL = 128;      // 4 chunks x 64 columns: G^T [x*e1 | x1*e2]
+
+struct Bars {
+  unsigned long long x_full[8], x_empty[8];
+  unsigned long long acc1_full, dl_full, dl_empty, done;
+  uint32_t tmem_base;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(void* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----------------------------------------------------------
+// shared-memory matrix descriptor, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- bf16 splitting ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// x = x1 + x2 (+ dropped 2^-18 relative): returns packed pairs for two consecutive elements
+__device__ __forceinline__ void split2(float a, float b, uint32_t& p1, uint32_t& p2) {
+  p1 = pack_bf16x2(a, b);
+  const float a1 = __uint_as_float(p1 << 16), b1 = __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = pack_bf16x2(a - a1, b - b1);
+}
+
+}  // namespace tc
+
+// =========================================================================================================================
+template <int NBLK>  // D / 64
+__global__ void __launch_bounds__(tc::THREADS, 1)
+k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
+         int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart) {
+  using namespace tc;
+  constexpr int D = NBLK * BLK_COLS;
+  constexpr int NCH = NBLK / 2;  // 128-column chunks (UMMA M of GEMM2)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx1 = smem;                              // NBLK blocks of [64 rows][64 bf16], x1 term
+  uint8_t* sx2 = sx1 + NBLK * BLK_BYTES;            // x2 term
+  uint8_t* sth = sx2 + NBLK * BLK_BYTES;            // NBLK blocks of [64 rows: t1(32) | t2(32)][64 bf16]
+  uint8_t* sdl = sth + NBLK * BLK_BYTES;            // [64 rows n][64 bf16: e1(32 s) | e2(32 s)]  (MN-major B of GEMM2)
+  Bars* bars = (Bars*)(sdl + BLK_BYTES);
+  float* sred = (float*)(bars + 1);                 // [4][32] stat reduction scratch
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // ---- one-time setup ---------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int b = 0; b < 8; ++b) {
+      mbar_init(&bars->x_full[b], LOADER_WARPS);
+      mbar_init(&bars->x_empty[b], 1);
+    }
+    mbar_init(&bars->acc1_full, 1);
+    mbar_init(&bars->dl_full, EPI_WARPS);
+    mbar_init(&bars->dl_empty, 1);
+    mbar_init(&bars->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  // theta -> bf16 split B operand of GEMM1 (K-major, 128B swizzle): row n = s (t1) / 32 + s (t2)
+  for (int idx = tid; idx < NS * (D / 8); idx += THREADS) {
+    const int s = idx / (D / 8), d8 = idx % (D / 8);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = s < S ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
+    uint32_t p1[4], p2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], p1[j], p2[j]);
+    const int b = d8 / 8, c = d8 % 8;
+    uint8_t* blk = sth + b * BLK_BYTES;
+    *reinterpret_cast<uint4*>(blk + s * 128 + ((c ^ (s & 7)) << 4)) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    const int n2 = 32 + s;
+    *reinterpret_cast<uint4*>(blk + n2 * 128 + ((c ^ (n2 & 7)) << 4)) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp < LOADER_WARPS) {
+    // ===================================================== loaders =====================================================
+    // block g (flattened over tiles): rows r0 = tid/8 and r0+32, 16-byte chunk c = tid%8 (8 fp32 -> 8 bf16)
+    const int r0 = tid >> 3, c = tid & 7;
+    const int64_t total_blocks = my_tiles * NBLK;
+    float4 bufA[4], bufB[4];
+    auto issue = [&](int64_t g, float4 (&buf)[4]) {
+      const int64_t it = g / NBLK;
+      const int b = (int)(g % NBLK);
+      const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t row = row0 + r0 + 32 * h;
+        if (g < total_blocks && row < N) {
+          const float4* p = reinterpret_cast<const float4*>(X + row * ldx + b * BLK_COLS + c * 8);
+          buf[2 * h] = __ldg(p);
+          buf[2 * h + 1] = __ldg(p + 1);
+        } else {
+          buf[2 * h] = make_float4(0.f, 0.f, 0.f, 0.f);
+          buf[2 * h + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto commit = [&](int64_t g, const float4 (&buf)[4]) {
+      const int64_t it = g / NBLK;
+      const int b = (int)(g % NBLK);
+      mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r0 + 32 * h;
+        uint32_t p1[4], p2[4];
+        split2(buf[2 * h].x, buf[2 * h].y, p1[0], p2[0]);
+        split2(buf[2 * h].z, buf[2 * h].w, p1[1], p2[1]);
+        split2(buf[2 * h + 1].x, buf[2 * h + 1].y, p1[2], p2[2]);
+        split2(buf[2 * h + 1].z, buf[2 * h + 1].w, p1[3], p2[3]);
+        const uint32_t off = b * BLK_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sx1 + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+        *reinterpret_cast<uint4*>(sx2 + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->x_full[b]);
+    };
+    issue(0, bufA);
+    issue(1, bufB);
+    for (int64_t g = 0; g < total_blocks; g += 2) {
+      commit(g, bufA);
+      issue(g + 2, bufA);
+      commit(g + 1, bufB);
+      issue(g + 3, bufB);
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================================================== MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t ID_G1_N64 = make_idesc(64, NB, 0, 0);   // x1 * [t1; t2]
+      constexpr uint32_t ID_G1_N32 = make_idesc(64, NS, 0, 0);   // x2 * t1
+      constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);      // x^T * [e1; e2], both operands MN-major
+      const uint32_t ax1 = smem_u32(sx1), ax2 = smem_u32(sx2), ath = smem_u32(sth), adl = smem_u32(sdl);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        // ---- GEMM1: logits tile, block by block as the loaders publish them
+        for (int b = 0; b < NBLK; ++b) {
+          mbar_wait(&bars->x_full[b], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
+            const uint64_t da = make_desc(ax1 + b * BLK_BYTES + k * 32, 16, 1024);
+            const uint64_t db = make_desc(ath + b * BLK_BYTES + k * 32, 16, 1024);
+            umma_bf16(tmem + ACC1_COL, da, db, ID_G1_N64, (b | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc(ax2 + b * BLK_BYTES + k * 32, 16, 1024);
+            const uint64_t db = make_desc(ath + b * BLK_BYTES + k * 32, 16, 1024);
+            umma_bf16(tmem + ACC1_COL, da, db, ID_G1_N32, 1);
+          }
+        }
+        umma_commit(&bars->acc1_full);
+        // ---- GEMM2: G^T chunks; K = the 64 rows of the tile
+        mbar_wait(&bars->dl_full, ph);
+        tc_fence_after();
+        for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 rows = two 8-row swizzle atoms, 1024 bytes apart)
+            const uint64_t db = make_desc(adl + k * 2048, BLK_BYTES, 1024);
+            const uint64_t da1 = make_desc(ax1 + (2 * ch) * BLK_BYTES + k * 2048, BLK_BYTES, 1024);
+            umma_bf16(tmem + ACC2_COL + ch * NB, da1, db, ID_G2, (it | k) != 0);
+            const uint64_t da2 = make_desc(ax2 + (2 * ch) * BLK_BYTES + k * 2048, BLK_BYTES, 1024);
+            umma_bf16(tmem + ACC2_COL + ch * NB, da2, db, ID_G2, 1);
+          }
+          umma_commit(&bars->x_empty[2 * ch]);
+          umma_commit(&bars->x_empty[2 * ch + 1]);
+        }
+        umma_commit(&bars->dl_empty);
+      }
+      umma_commit(&bars->done);
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue =====================================================
+    const int q = warp & 3;                 // TMEM sub-partition this warp may access
+    const int h = (warp - EPI_WARP0) >> 2;  // which half of the 32 samples
+    const bool active = lane < 16;          // UMMA M = 64: row r lives in lane (r % 16) of sub-partition r / 16
+    const int r = 16 * q + (lane & 15);
+    float stat[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) stat[j] = 0.0f;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int64_t row = (blockIdx.x + it * gridDim.x) * TILE_ROWS + r;
+      const bool row_ok = active && row < N;
+      const float yv = row_ok ? y[row] : 0.0f;
+      mbar_wait(&bars->acc1_full, ph);
+      tc_fence_after();
+      uint32_t va[16], vb[16];
+      tmem_ld16(t_lane + ACC1_COL + h * 16, va);
+      tmem_ld16(t_lane + ACC1_COL + NS + h * 16, vb);
+      tmem_ld_wait();
+      uint32_t e1[8], e2[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float g[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float eta = __uint_as_float(va[j + u]) + __uint_as_float(vb[j + u]);
+          float f, gg;
+          link_eval(family, yv, eta, f, gg);
+          const bool ok = row_ok && (h * 16 + j + u) < S;
+          stat[j + u] += ok ? f : 0.0f;
+          g[u] = ok ? gg : 0.0f;
+        }
+        split2(g[0], g[1], e1[j >> 1], e2[j >> 1]);
+      }
+      mbar_wait(&bars->dl_empty, ph ^ 1);  // GEMM2 of the previous tile has consumed the dl buffer
+      if (active) {
+        uint8_t* rowp = sdl + r * 128;
+        const int sw = r & 7;
+        *reinterpret_cast<uint4*>(rowp + (((2 * h) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * h + 1) ^ sw) << 4)) = make_uint4(e1[4], e1[5], e1[6], e1[7]);
+        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+        *reinterpret_cast<uint4*>(rowp + (((5 + 2 * h) ^ sw) << 4)) = make_uint4(e2[4], e2[5], e2[6], e2[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dl_full);
+    }
+    // ---- per-CTA partial of stat[s]: reduce over the 64 rows (16 lanes x 4 sub-partitions)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = stat[j];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sred[q * NS + h * 16 + j] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+    if (warp == EPI_WARP0 && lane < S) {
+      statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+    }
+    // ---- per-CTA partial of G[s, d]: read the GEMM2 accumulators once all MMAs have retired
+    mbar_wait(&bars->done, 0);
+    tc_fence_after();
+    float* gp = Gpart + (size_t)blockIdx.x * S * D;
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t va[16], vb[16];
+      tmem_ld16(t_lane + ACC2_COL + ch * NB + h * 16, va);
+      tmem_ld16(t_lane + ACC2_COL + ch * NB + NS + h * 16, vb);
+      tmem_ld_wait();
+      const int d = ch * 128 + 32 * q + lane;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int s = h * 16 + j;
+        if (s < S) gp[(size_t)s * D + d] = my_tiles > 0 ? __uint_as_float(va[j]) + __uint_as_float(vb[j]) : 0.0f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// =========================================================================================================================
+static size_t tc_smem_bytes(int nblk) {
+  return (size_t)(3 * nblk + 1) * tc::BLK_BYTES + sizeof(tc::Bars) + 4 * tc::NS * sizeof(float) + 1024;
+}
+
+bool tc_eligible(const BjxElboArgs& a) {
+  if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
+  if (a.Dw < 128 || a.Dw > 512 || a.Dw % 128 != 0) return false;
+  if (a.S < 1 || a.S > tc::NS) return false;
+  if (a.ldx % 4 != 0 || ((uintptr_t)a.X & 15) != 0) return false;  // 128-bit row loads
+  if (a.precision == BJX_PREC_BF16X3) return false;                // three-term split not built yet
+  return true;
+}
+
+int tc_plan(const BjxElboArgs& a, Plan& p) {
+  const int sms = sm_count();
+  if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
+  const int64_t tiles = (a.N + tc::TILE_ROWS - 1) / tc::TILE_ROWS;
+  int64_t g = tiles < sms ? tiles : sms;
+  if (g < 1) g = 1;
+  p.tc_ctas = (int)g;
+  p.tc_terms = 2;
+  return BJX_OK;
+}
+
 size_t tc_theta_bytes(const BjxElboArgs&, const Plan&) { return 0; }
-int launch_lik_tc(const BjxElboArgs&, const Plan&, char*, cudaStream_t) { return fail(BJX_ERR_UNSUPPORTED, "tcgen05 path not built"); }
+
+int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+  const float* theta = (const float*)(ws + p.o_theta);
+  float* Gpart = (float*)(ws + p.o_Gpart);
+  float* statpart = (float*)(ws + p.o_statpart);
+  const int nblk = (int)(a.Dw / tc::BLK_COLS);
+  const size_t smem = tc_smem_bytes(nblk);
+#define BJX_TC_LAUNCH(NBLK)                                                                                           \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
+                                                         a.likelihood, Gpart, statpart);                              \
+  } while (0)
+  switch (nblk) {
+    case 2: BJX_TC_LAUNCH(2); break;
+    case 4: BJX_TC_LAUNCH(4); break;
+    case 6: BJX_TC_LAUNCH(6); break;
+    case 8: BJX_TC_LAUNCH(8); break;
+    default: return fail(BJX_ERR_UNSUPPORTED, "tcgen05 kernel needs D in {128, 256, 384, 512}");
+  }
+#undef BJX_TC_LAUNCH
+  BJX_LAUNCH_CHECK("k_lik_tc");
+  return BJX_OK;
+}
+
 }  // namespace bjx

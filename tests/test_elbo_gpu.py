@@ -206,3 +206,24 @@ def test_error_paths():
         model.value_and_grad(params, torch.zeros(10, device=dev), {"X": torch.zeros(10, D + 1, device=dev)}, 10, br.PRNGKey(0), 4)
     with pytest.raises(TypeError):
         model.value_and_grad(params, torch.zeros(10, device=dev), {"X": torch.zeros(10, D, device=dev)}, 10, torch.zeros(2), 4)
+
+
+@pytest.mark.parametrize(
+    "N,D,S,lik",
+    [(64, 128, 32, "logit"), (1, 128, 32, "logit"), (65, 256, 16, "logit"), (1000, 512, 32, "logit"),
+     (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss")],
+)
+def test_tensor_core_path(N, D, S, lik):
+    """config c3/c5 shape family on the tcgen05 kernel (bf16 split operands, fp32 accumulation in TMEM)."""
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if lik == "logit":
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="bf16x2")
+        kwargs = {}
+    else:
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), precision="bf16x2")
+        kwargs = {"log_noise_scale": np.float32(math.log(0.5))}
+    loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_bf16_split")
