@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "bjx_profile_begin",
     "bjx_profile_collect",
     "bjx_profile_end",
+    "bjx_debug_set_trace_buffer",
 )
 
 
@@ -127,6 +128,7 @@ def load() -> C.CDLL:
     lib.bjx_profile_begin.argtypes = [i32]
     lib.bjx_profile_collect.argtypes = [vp, i32, vp]
     lib.bjx_profile_end.argtypes = []
+    lib.bjx_debug_set_trace_buffer.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what bjx.h declares
         if name not in ("bjx_last_error", "bjx_elbo_workspace_bytes", "bjx_abi_version", "bjx_device_sm_count"):

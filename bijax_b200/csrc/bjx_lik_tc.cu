@@ -13,11 +13,15 @@
 // canonical UMMA shared-memory layout (128-byte swizzle), which serves GEMM1 as a K-major A operand and GEMM2 as an
 // MN-major A operand without a second copy or a transpose.
 //
-// Warp roles (544 threads, 1 CTA per SM, persistent over row tiles):
-//   warps 0-7   loaders: LDG.128 (2 blocks in flight) -> bf16 split -> STS.128 swizzled -> mbarrier
-//   warp  8     MMA issuer (one elected lane), owns the TMEM allocation
-//   warps 9-16  epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
+// Warp roles (800 threads, 1 CTA per SM, persistent over row tiles):
+//   warps 0-15  loaders: 8 x LDG.128 per lane (a quarter block per warp; 16 warps = 64 KB in flight per SM)
+//               -> bf16 split -> STS.128 swizzled -> mbarrier.  No software pipelining inside a warp: ptxas shares
+//               scoreboards between prefetch stages, which serialises them; depth comes from the number of warps.
+//   warp  16    MMA issuer (converged warp, elect.sync), owns the TMEM allocation
+//   warps 17-24 epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 
 #include "bjx_elbo.cuh"
 
@@ -30,10 +34,10 @@ constexpr int BLK_COLS = 64;       // columns per shared-memory block (64 bf16 =
 constexpr int BLK_BYTES = TILE_ROWS * 128;  // 8 KB
 constexpr int NS = 32;             // samples per pass (padded)
 constexpr int NB = 64;             // UMMA N when both split terms of the B operand are used ([t1; t2] / [e1; e2])
-constexpr int LOADER_WARPS = 8, LOADER_THREADS = 256;
-constexpr int MMA_WARP = 8;
-constexpr int EPI_WARP0 = 9, EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 544
+constexpr int LOADER_WARPS = 16;   // each owns a quarter block (16 rows x 64 cols = 4 KB) at a time, no intra-warp pipelining
+constexpr int MMA_WARP = 16;
+constexpr int EPI_WARP0 = 17, EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 800
 constexpr int TMEM_COLS = 512;
 constexpr int ACC1_COL = 0;        // 64 columns: logits [x*t1 | x1*t2]
 constexpr int ACC2_COL = 128;      // 4 chunks x 64 columns: G^T [x*e1 | x1*e2]
@@ -58,12 +62,12 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra D_%=;\n\t"
       "bra W_%=;\n\t"
       "D_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680)  // suspend-time hint: sleep in hardware instead of spinning on the shared-memory port
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -100,6 +104,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----------------------------------------------------------
@@ -126,14 +135,38 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& p1, uint32_t&
   p2 = pack_bf16x2(a - a1, b - b1);
 }
 
+// Link functions with ONE exponential per datum (MUFU.EX2 / LG2 / RCP): e = exp(-|eta|),
+// softplus(eta) = max(eta, 0) + log(1 + e), sigmoid(eta) = (eta >= 0 ? 1 : e) / (1 + e).  Absolute error ~1e-7 per datum.
+__device__ __forceinline__ void link_fast(int family, float y, float eta, float& f, float& g) {
+  if (family == BJX_LIK_BERNOULLI_LOGITS) {
+    const float e = __expf(-fabsf(eta));
+    const float ope = 1.0f + e;
+    const float r = __frcp_rn(ope);
+    f = y * eta - (fmaxf(eta, 0.0f) + __logf(ope));
+    g = y - (eta >= 0.0f ? r : e * r);
+  } else {
+    const float r = y - eta;
+    f = r * r;
+    g = r;
+  }
+}
+
 }  // namespace tc
 
 // =========================================================================================================================
 template <int NBLK>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
-         int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart) {
+         int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
+         long long* __restrict__ trace, int stagger_cycles) {
   using namespace tc;
+  // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
+  constexpr int64_t TRACE_T0 = 16;
+#define BJX_TRACE(it_, slot_)                                                                            \
+  do {                                                                                                   \
+    if (trace != nullptr && blockIdx.x == 0 && (it_) >= TRACE_T0 && (it_) < TRACE_T0 + 8)                \
+      trace[((it_)-TRACE_T0) * 64 + (slot_)] = clock64();                                                \
+  } while (0)
   constexpr int D = NBLK * BLK_COLS;
   constexpr int NCH = NBLK / 2;  // 128-column chunks (UMMA M of GEMM2)
   extern __shared__ uint8_t smem_raw[];
@@ -152,7 +185,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
   // ---- one-time setup ---------------------------------------------------------------------------------------------------
   if (tid == 0) {
     for (int b = 0; b < 8; ++b) {
-      mbar_init(&bars->x_full[b], LOADER_WARPS);
+      mbar_init(&bars->x_full[b], 4);  // the four quarter-block warps
       mbar_init(&bars->x_empty[b], 1);
     }
     mbar_init(&bars->acc1_full, 1);
@@ -185,159 +218,205 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 
   if (warp < LOADER_WARPS) {
     // ===================================================== loaders =====================================================
-    // block g (flattened over tiles): rows r0 = tid/8 and r0+32, 16-byte chunk c = tid%8 (8 fp32 -> 8 bf16)
-    const int r0 = tid >> 3, c = tid & 7;
+    // unit = quarter of a block: rows 16*qd .. 16*qd+15, 64 columns.  lane -> (row 4*i + lane/8, 16-byte chunk lane%8).
+    const int qd = warp & 3, bl = warp >> 2;
+    const int rl = lane >> 3, c = lane & 7;
     const int64_t total_blocks = my_tiles * NBLK;
-    float4 bufA[4], bufB[4];
-    auto issue = [&](int64_t g, float4 (&buf)[4]) {
+    // De-phase the CTAs: with identical work per tile all SMs would issue their 64 KB load bursts in lockstep (a 9.5 MB
+    // burst every tile period, ~3500-cycle load latency measured); a one-off start-up skew spreads the HBM demand.
+    if (stagger_cycles > 0 && my_tiles > 4) {
+      const long long t_start = clock64();
+      const long long delay = (long long)((blockIdx.x * 37) % 16) * stagger_cycles;
+      while (clock64() - t_start < delay) {
+      }
+    }
+    for (int64_t g = bl; g < total_blocks; g += 4) {
       const int64_t it = g / NBLK;
       const int b = (int)(g % NBLK);
-      const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
+      const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS + 16 * qd + rl;
+      float4 v[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t row = row0 + r0 + 32 * h;
-        if (g < total_blocks && row < N) {
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + 4 * i;
+        if (row < N) {
           const float4* p = reinterpret_cast<const float4*>(X + row * ldx + b * BLK_COLS + c * 8);
-          buf[2 * h] = __ldg(p);
-          buf[2 * h + 1] = __ldg(p + 1);
+          v[2 * i] = __ldg(p);
+          v[2 * i + 1] = __ldg(p + 1);
         } else {
-          buf[2 * h] = make_float4(0.f, 0.f, 0.f, 0.f);
-          buf[2 * h + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-    };
-    auto commit = [&](int64_t g, const float4 (&buf)[4]) {
-      const int64_t it = g / NBLK;
-      const int b = (int)(g % NBLK);
       mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
+      if (tid == 0) BJX_TRACE(it, b);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = r0 + 32 * h;
+      for (int i = 0; i < 4; ++i) {
+        const int r = 16 * qd + rl + 4 * i;
         uint32_t p1[4], p2[4];
-        split2(buf[2 * h].x, buf[2 * h].y, p1[0], p2[0]);
-        split2(buf[2 * h].z, buf[2 * h].w, p1[1], p2[1]);
-        split2(buf[2 * h + 1].x, buf[2 * h + 1].y, p1[2], p2[2]);
-        split2(buf[2 * h + 1].z, buf[2 * h + 1].w, p1[3], p2[3]);
+        split2(v[2 * i].x, v[2 * i].y, p1[0], p2[0]);
+        split2(v[2 * i].z, v[2 * i].w, p1[1], p2[1]);
+        split2(v[2 * i + 1].x, v[2 * i + 1].y, p1[2], p2[2]);
+        split2(v[2 * i + 1].z, v[2 * i + 1].w, p1[3], p2[3]);
         const uint32_t off = b * BLK_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(sx1 + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
         *reinterpret_cast<uint4*>(sx2 + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
       }
+      // writer-side generic->async proxy fence.  It lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, which is cheap HERE
+      // because this warp has no global loads in flight at this point (a MEMBAR drains them).
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->x_full[b]);
-    };
-    issue(0, bufA);
-    issue(1, bufB);
-    for (int64_t g = 0; g < total_blocks; g += 2) {
-      commit(g, bufA);
-      issue(g + 2, bufA);
-      commit(g + 1, bufB);
-      issue(g + 3, bufB);
+      if (tid == 0) BJX_TRACE(it, 8 + b);
+      if (lane == 0 && b == 0) BJX_TRACE(it, 40 + warp);   // all four quarter warps of block 0
+      if (lane == 0 && b == 1) BJX_TRACE(it, 44 + (warp & 3));
     }
   } else if (warp == MMA_WARP) {
     // ===================================================== MMA issuer ==================================================
-    if (lane == 0) {
-      constexpr uint32_t ID_G1_N64 = make_idesc(64, NB, 0, 0);   // x1 * [t1; t2]
-      constexpr uint32_t ID_G1_N32 = make_idesc(64, NS, 0, 0);   // x2 * t1
-      constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);      // x^T * [e1; e2], both operands MN-major
-      const uint32_t ax1 = smem_u32(sx1), ax2 = smem_u32(sx2), ath = smem_u32(sth), adl = smem_u32(sdl);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const uint32_t ph = (uint32_t)(it & 1);
-        // ---- GEMM1: logits tile, block by block as the loaders publish them
-        for (int b = 0; b < NBLK; ++b) {
-          mbar_wait(&bars->x_full[b], ph);
-          tc_fence_after();
+    // The whole warp walks the pipeline (waits are warp-uniform); one elected lane issues.  Issued this way a small
+    // UMMA is bound only by its operand bytes at 128 B/clk of shared-memory bandwidth (scripts/ubench/umma_rate.cu).
+    constexpr uint32_t ID_G1_N64 = make_idesc(64, NB, 0, 0);   // x1 * [t1; t2]
+    constexpr uint32_t ID_G1_N32 = make_idesc(64, NS, 0, 0);   // x2 * t1
+    constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);      // x1^T * [e1; e2], both operands MN-major
+    constexpr uint32_t ID_G2_N32 = make_idesc(128, NS, 1, 1);  // x2^T * e1
+    const uint64_t dx1 = make_desc(smem_u32(sx1), 16, 1024), dx2 = make_desc(smem_u32(sx2), 16, 1024);
+    const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
+    const uint64_t tx1 = make_desc(smem_u32(sx1), BLK_BYTES, 1024), tx2 = make_desc(smem_u32(sx2), BLK_BYTES, 1024);
+    const uint64_t tdl = make_desc(smem_u32(sdl), BLK_BYTES, 1024);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      // ---- GEMM1: logits tile, block by block as the loaders publish them
+      for (int b = 0; b < NBLK; ++b) {
+        // (no tcgen05.fence here: the operands come from generic-proxy stores ordered by the mbarrier + proxy fence, and
+        // tcgen05.fence::after_thread_sync would wait for the previous tile's GEMM2 to drain: ~900 cycles measured)
+        mbar_wait(&bars->x_full[b], ph);
+        if (lane == 0) BJX_TRACE(it, 16 + b);
+        if (elect_one()) {
+          const uint64_t boff = (uint64_t)((b * BLK_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
-            const uint64_t da = make_desc(ax1 + b * BLK_BYTES + k * 32, 16, 1024);
-            const uint64_t db = make_desc(ath + b * BLK_BYTES + k * 32, 16, 1024);
-            umma_bf16(tmem + ACC1_COL, da, db, ID_G1_N64, (b | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
+            umma_bf16(tmem + ACC1_COL, dx1 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N64, (b | k) != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_desc(ax2 + b * BLK_BYTES + k * 32, 16, 1024);
-            const uint64_t db = make_desc(ath + b * BLK_BYTES + k * 32, 16, 1024);
-            umma_bf16(tmem + ACC1_COL, da, db, ID_G1_N32, 1);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + ACC1_COL, dx2 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N32, 1);
         }
-        umma_commit(&bars->acc1_full);
-        // ---- GEMM2: G^T chunks; K = the 64 rows of the tile
-        mbar_wait(&bars->dl_full, ph);
-        tc_fence_after();
-        for (int ch = 0; ch < NCH; ++ch) {
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bars->acc1_full);
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(it, 24);
+      // ---- GEMM2: G^T chunks; K = the 64 rows of the tile
+      mbar_wait(&bars->dl_full, ph);
+      tc_fence_after();
+      if (lane == 0) BJX_TRACE(it, 25);
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (elect_one()) {
+          const uint64_t coff = (uint64_t)((2 * ch * BLK_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 rows = two 8-row swizzle atoms, 1024 bytes apart)
-            const uint64_t db = make_desc(adl + k * 2048, BLK_BYTES, 1024);
-            const uint64_t da1 = make_desc(ax1 + (2 * ch) * BLK_BYTES + k * 2048, BLK_BYTES, 1024);
-            umma_bf16(tmem + ACC2_COL + ch * NB, da1, db, ID_G2, (it | k) != 0);
-            const uint64_t da2 = make_desc(ax2 + (2 * ch) * BLK_BYTES + k * 2048, BLK_BYTES, 1024);
-            umma_bf16(tmem + ACC2_COL + ch * NB, da2, db, ID_G2, 1);
+            umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2, (it | k) != 0);
+            umma_bf16(tmem + ACC2_COL + ch * NB, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
           }
           umma_commit(&bars->x_empty[2 * ch]);
           umma_commit(&bars->x_empty[2 * ch + 1]);
         }
-        umma_commit(&bars->dl_empty);
+        __syncwarp();
       }
-      umma_commit(&bars->done);
+      if (elect_one()) umma_commit(&bars->dl_empty);
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(it, 26);
     }
+    if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else {
     // ===================================================== epilogue =====================================================
     const int q = warp & 3;                 // TMEM sub-partition this warp may access
     const int h = (warp - EPI_WARP0) >> 2;  // which half of the 32 samples
-    const bool active = lane < 16;          // UMMA M = 64: row r lives in lane (r % 16) of sub-partition r / 16
+    // UMMA M = 64: row r lives in lane (r % 16) of sub-partition r / 16, so tcgen05.ld fills lanes 0-15 only.  The upper
+    // half-warp takes over 8 of the 16 columns by shuffle, so all 32 lanes (and the whole MUFU pipe) do useful work.
+    const int hi = lane >> 4;
     const int r = 16 * q + (lane & 15);
-    float stat[16];
+    const int s0 = h * 16 + hi * 8;         // this lane's 8 samples
+    float stat[8], prod[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) stat[j] = 0.0f;
+    for (int j = 0; j < 8; ++j) {
+      stat[j] = 0.0f;
+      prod[j] = 1.0f;
+    }
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const int64_t row = (blockIdx.x + it * gridDim.x) * TILE_ROWS + r;
-      const bool row_ok = active && row < N;
+      const bool row_ok = row < N;
       const float yv = row_ok ? y[row] : 0.0f;
       mbar_wait(&bars->acc1_full, ph);
       tc_fence_after();
+      if (tid == EPI_WARP0 * 32) BJX_TRACE(it, 32);
       uint32_t va[16], vb[16];
       tmem_ld16(t_lane + ACC1_COL + h * 16, va);
       tmem_ld16(t_lane + ACC1_COL + NS + h * 16, vb);
       tmem_ld_wait();
-      uint32_t e1[8], e2[8];
+      if (tid == EPI_WARP0 * 32) BJX_TRACE(it, 33);
+      float eta[8];
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
+      for (int j = 0; j < 8; ++j) {
+        const float lo = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+        const float up = __shfl_sync(0xffffffffu, __uint_as_float(va[8 + j]) + __uint_as_float(vb[8 + j]), lane & 15);
+        eta[j] = hi ? up : lo;
+      }
+      uint32_t e1[4], e2[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
         float g[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float eta = __uint_as_float(va[j + u]) + __uint_as_float(vb[j + u]);
-          float f, gg;
-          link_eval(family, yv, eta, f, gg);
-          const bool ok = row_ok && (h * 16 + j + u) < S;
-          stat[j + u] += ok ? f : 0.0f;
-          g[u] = ok ? gg : 0.0f;
+          const bool ok = row_ok && (s0 + j + u) < S;
+          const float x = eta[j + u];
+          if (logit) {
+            // one exponential per datum: e = exp(-|x|); sigmoid = (x >= 0 ? 1 : e) / (1 + e);
+            // softplus = max(x, 0) + log(1 + e), with the logs taken of a running product (flushed every 32 tiles)
+            const float e = __expf(-fabsf(x));
+            const float ope = 1.0f + e;
+            const float rc = __fdividef(1.0f, ope);  // MUFU.RCP
+            stat[j + u] += ok ? (yv * x - fmaxf(x, 0.0f)) : 0.0f;
+            prod[j + u] *= ok ? ope : 1.0f;
+            g[u] = ok ? (yv - (x >= 0.0f ? rc : e * rc)) : 0.0f;
+          } else {
+            const float rr = yv - x;
+            stat[j + u] += ok ? rr * rr : 0.0f;
+            g[u] = ok ? rr : 0.0f;
+          }
         }
         split2(g[0], g[1], e1[j >> 1], e2[j >> 1]);
       }
+      if ((it & 31) == 31) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          stat[j] -= logf(prod[j]);
+          prod[j] = 1.0f;
+        }
+      }
+      if (tid == EPI_WARP0 * 32) BJX_TRACE(it, 34);
       mbar_wait(&bars->dl_empty, ph ^ 1);  // GEMM2 of the previous tile has consumed the dl buffer
-      if (active) {
+      {
         uint8_t* rowp = sdl + r * 128;
         const int sw = r & 7;
-        *reinterpret_cast<uint4*>(rowp + (((2 * h) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * h + 1) ^ sw) << 4)) = make_uint4(e1[4], e1[5], e1[6], e1[7]);
-        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
-        *reinterpret_cast<uint4*>(rowp + (((5 + 2 * h) ^ sw) << 4)) = make_uint4(e2[4], e2[5], e2[6], e2[7]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * h + hi) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + hi) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dl_full);
+      if (tid == EPI_WARP0 * 32) BJX_TRACE(it, 35);
     }
     // ---- per-CTA partial of stat[s]: reduce over the 64 rows (16 lanes x 4 sub-partitions)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float v = stat[j];
+    for (int j = 0; j < 8; ++j) {
+      float v = stat[j] - logf(prod[j]);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) sred[q * NS + h * 16 + j] = v;
+      if ((lane & 15) == 0) sred[q * NS + s0 + j] = v;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
     if (warp == EPI_WARP0 && lane < S) {
@@ -366,7 +445,12 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
   if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+#undef BJX_TRACE
+
 // =========================================================================================================================
+static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
+static long long* g_trace = nullptr;  // device buffer of 8 x 64 clock64 slots, or null (production)
+
 static size_t tc_smem_bytes(int nblk) {
   return (size_t)(3 * nblk + 1) * tc::BLK_BYTES + sizeof(tc::Bars) + 4 * tc::NS * sizeof(float) + 1024;
 }
@@ -394,6 +478,11 @@ int tc_plan(const BjxElboArgs& a, Plan& p) {
 size_t tc_theta_bytes(const BjxElboArgs&, const Plan&) { return 0; }
 
 int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+  static bool env_read = false;
+  if (!env_read) {
+    if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
+    env_read = true;
+  }
   const float* theta = (const float*)(ws + p.o_theta);
   float* Gpart = (float*)(ws + p.o_Gpart);
   float* statpart = (float*)(ws + p.o_statpart);
@@ -407,7 +496,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart);                              \
+                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger);                     \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;
@@ -422,3 +511,8 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
 }
 
 }  // namespace bjx
+
+extern "C" int bjx_debug_set_trace_buffer(void* device_buffer_4096_bytes) {
+  bjx::g_trace = (long long*)device_buffer_4096_bytes;
+  return BJX_OK;
+}

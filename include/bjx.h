@@ -189,6 +189,10 @@ BJX_API int bjx_profile_begin(int32_t capacity);
 BJX_API int bjx_profile_collect(float* ms_out_host, int32_t max_out, int32_t* n_out_host);
 BJX_API int bjx_profile_end(void);
 
+/* Development hook: when set to a device buffer of 8*64 int64 slots, CTA 0 of the tcgen05 kernel records clock64()
+ * timestamps of its pipeline events for tiles 16..23; NULL (default) disables it. */
+BJX_API int bjx_debug_set_trace_buffer(void* device_buffer_4096_bytes);
+
 #ifdef __cplusplus
 }
 #endif
