@@ -158,7 +158,7 @@ template <int NBLK>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
          int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
-         long long* __restrict__ trace, int stagger_cycles) {
+         long long* __restrict__ trace, int stagger_cycles, int ablate) {
   using namespace tc;
   // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
   constexpr int64_t TRACE_T0 = 16;
@@ -247,11 +247,17 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
           v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (tid == 0 && b == 4) BJX_TRACE(it, 48);                // loads issued
       mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
       if (tid == 0) BJX_TRACE(it, b);
+      if (trace != nullptr) {  // trace builds only: stamp the arrival of the last load of the unit
+        asm volatile("" ::"f"(v[7].w), "f"(v[0].x) : "memory");
+        if (tid == 0 && b == 4) BJX_TRACE(it, 49);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 16 * qd + rl + 4 * i;
+        if ((ablate & 8) && v[2 * i].x != 12345.678f) continue;  // keep the loads alive, skip convert + store
         uint32_t p1[4], p2[4];
         split2(v[2 * i].x, v[2 * i].y, p1[0], p2[0]);
         split2(v[2 * i].z, v[2 * i].w, p1[1], p2[1]);
@@ -290,7 +296,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
         // tcgen05.fence::after_thread_sync would wait for the previous tile's GEMM2 to drain: ~900 cycles measured)
         mbar_wait(&bars->x_full[b], ph);
         if (lane == 0) BJX_TRACE(it, 16 + b);
-        if (elect_one()) {
+        if (!(ablate & 1) && elect_one()) {
           const uint64_t boff = (uint64_t)((b * BLK_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
@@ -313,6 +319,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
           const uint64_t coff = (uint64_t)((2 * ch * BLK_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 rows = two 8-row swizzle atoms, 1024 bytes apart)
+            if (ablate & 2) continue;
             umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2, (it | k) != 0);
             umma_bf16(tmem + ACC2_COL + ch * NB, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
           }
@@ -372,7 +379,9 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
         for (int u = 0; u < 2; ++u) {
           const bool ok = row_ok && (s0 + j + u) < S;
           const float x = eta[j + u];
-          if (logit) {
+          if (ablate & 4) {
+            g[u] = ok ? x : 0.0f;
+          } else if (logit) {
             // one exponential per datum: e = exp(-|x|); sigmoid = (x >= 0 ? 1 : e) / (1 + e);
             // softplus = max(x, 0) + log(1 + e), with the logs taken of a running product (flushed every 32 tiles)
             const float e = __expf(-fabsf(x));
@@ -449,6 +458,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 
 // =========================================================================================================================
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
+static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
 static long long* g_trace = nullptr;  // device buffer of 8 x 64 clock64 slots, or null (production)
 
 static size_t tc_smem_bytes(int nblk) {
@@ -481,6 +491,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   static bool env_read = false;
   if (!env_read) {
     if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
+    if (const char* e = getenv("BJX_TC_ABLATE")) g_ablate = atoi(e);
     env_read = true;
   }
   const float* theta = (const float*)(ws + p.o_theta);
@@ -496,7 +507,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger);                     \
+                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate);                     \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;
