@@ -158,7 +158,7 @@ template <int NBLK>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
          int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
-         long long* __restrict__ trace, int stagger_cycles, int ablate) {
+         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist) {
   using namespace tc;
   // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
   constexpr int64_t TRACE_T0 = 16;
@@ -246,6 +246,14 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
           v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
           v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      }
+      // fire-and-forget L2 prefetch of the SAME unit of the next tile (16 rows x 256 B = 32 lines, one per lane): HBM keeps
+      // streaming into the 126 MB L2 while this warp's registers are tied up waiting for the shared-memory slot
+      if (pf_dist > 0) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
+        const int64_t gp = g + pf_dist;
+        const int64_t prow = (blockIdx.x + (gp / NBLK) * gridDim.x) * TILE_ROWS + 16 * qd + (lane >> 1);
+        if (gp < total_blocks && prow < N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(X + prow * ldx + (gp % NBLK) * BLK_COLS + (lane & 1) * 32));
       }
       if (tid == 0 && b == 4) BJX_TRACE(it, 48);                // loads issued
       mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
@@ -459,6 +467,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 // =========================================================================================================================
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
 static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
+static int g_pf = 8;                 // L2 prefetch distance in blocks (BJX_TC_PF overrides; 0 = off)
 static long long* g_trace = nullptr;  // device buffer of 8 x 64 clock64 slots, or null (production)
 
 static size_t tc_smem_bytes(int nblk) {
@@ -492,6 +501,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   if (!env_read) {
     if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
     if (const char* e = getenv("BJX_TC_ABLATE")) g_ablate = atoi(e);
+    if (const char* e = getenv("BJX_TC_PF")) g_pf = atoi(e);
     env_read = true;
   }
   const float* theta = (const float*)(ws + p.o_theta);
@@ -507,7 +517,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate);                     \
+                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf);                     \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;

@@ -16,13 +16,16 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
 }
 
 // mode 0: A K-major (rows x 128B blocks), B K-major; mode 1: both MN-major
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred = 0;
   asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
   return pred;
 }
-template <int NACC, int ELECT>
-__global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, long long* out) {
+template <int NACC, int ELECT, int mode>
+__global__ void __launch_bounds__(128, 1) k(int M, int N, int iters, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ unsigned long long bar;
@@ -42,12 +45,13 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, l
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base;
   if (ELECT ? (threadIdx.x < 32) : (threadIdx.x == 0)) {
-    const uint32_t idesc = make_idesc(M, N, mode, mode);
+    const uint32_t idesc = mode == 2 ? make_idesc(M, N, 0, 0) : mode == 3 ? make_idesc(M, N, 1, 0) : make_idesc(M, N, mode, mode);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 128 * 1024;
     // 16 distinct operand positions, descriptors hoisted out of the timed loop (constant offsets -> immediate adds)
     uint64_t da0, db0;
     uint32_t astep_blk, astep_k;
-    if (mode == 0) { da0 = make_desc(a0, 16, 1024); db0 = make_desc(b0, 16, 1024); astep_blk = 16384 >> 4; astep_k = 32 >> 4; }
+    if (mode == 0 || mode == 2) { da0 = make_desc(a0, 16, 1024); db0 = make_desc(b0, 16, 1024); astep_blk = 16384 >> 4; astep_k = 32 >> 4; }
+    else if (mode == 3) { da0 = make_desc(a0, 16384, 1024); db0 = make_desc(b0, 16, 1024); astep_blk = 16384 >> 4; astep_k = 2048 >> 4; }
     else           { da0 = make_desc(a0, 8192, 1024); db0 = make_desc(b0, 8192, 1024); astep_blk = 16384 >> 4; astep_k = 2048 >> 4; }
     long long t0 = clock64();
     for (int i = 0; i < iters; i += 16) {
@@ -55,6 +59,8 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, l
       for (int j = 0; j < 16; ++j) {
         const uint64_t da = da0 + (uint64_t)((j / 4) * astep_blk + (j % 4) * astep_k);
         const uint64_t db = db0 + (uint64_t)((j % 4) * astep_k);
+        if (mode == 2) { if (elect_one()) umma_ts(tmem + 256 + (j % 2) * 64, tmem + (j / 4) * 32 + (j % 4) * 8, da, idesc, 1); __syncwarp(); continue; }
+        if (mode == 3) { if (elect_one()) umma(tmem + 384 + (j / 4) * 16, da, db0 + (uint64_t)((j % 4) * 2), idesc, 1); __syncwarp(); continue; }
         if (ELECT) { if (elect_one()) umma(tmem + (j % NACC) * 256, da, db, idesc, 1); __syncwarp(); }
         else umma(tmem + (j % NACC) * 256, da, db, idesc, 1);
       }
@@ -72,24 +78,32 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, l
 
 int main() {
   long long* out; cudaMallocManaged(&out, 16);
-  cudaFuncSetAttribute(k<1,0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k<1,1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k<1,1,0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k<1,1,1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k<1,1,2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k<1,1,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct { int M, N, mode; const char* name; } cases[] = {
     {64, 64, 0, "G1 x1*[t1;t2]  M=64  N=64  K-major"}, {64, 32, 0, "G1 x2*t1       M=64  N=32  K-major"},
     {128, 64, 0, "             M=128 N=64  K-major"}, {128, 32, 0, "             M=128 N=32  K-major"},
     {128, 128, 0, "             M=128 N=128 K-major"}, {128, 256, 0, "             M=128 N=256 K-major"},
     {128, 64, 1, "G2 x1^T*[e1;e2] M=128 N=64 MN-major"}, {128, 32, 1, "G2 x2^T*e1    M=128 N=32 MN-major"},
-    {64, 16, 0, "             M=64  N=16  K-major"}, {64, 128, 0, "             M=64  N=128 K-major"},
+    {128, 64, 2, "T-G1 theta[tmem]*x  M=128 N=64 TS"}, {128, 128, 2, "T-G1 theta[tmem]*[x1;x2] M=128 N=128 TS"},
+    {128, 32, 3, "T-G2 x^T(MN)*e(K)   M=128 N=32"}, {128, 16, 3, "T-G2 x^T(MN)*e(K)   M=128 N=16"}, {64, 64, 2, "     theta[tmem]*x  M=64 N=64 TS"},
   };
   for (int grid : {148}) {
     printf("grid=%d CTAs (1 per SM)\n", grid);
     for (auto& c : cases) {
       const int iters = 2048;
-      for (int nacc : {1, 2}) {
-      if (nacc == 1) k<1,0><<<grid, 128, 200 * 1024>>>(c.M, c.N, c.mode, iters, out); else k<1,1><<<grid, 128, 200 * 1024>>>(c.M, c.N, c.mode, iters, out);
+      for (int nacc : {1}) {
+      switch (c.mode) {
+        case 0: k<1,1,0><<<grid, 128, 200 * 1024>>>(c.M, c.N, iters, out); break;
+        case 1: k<1,1,1><<<grid, 128, 200 * 1024>>>(c.M, c.N, iters, out); break;
+        case 2: k<1,1,2><<<grid, 128, 200 * 1024>>>(c.M, c.N, iters, out); break;
+        default: k<1,1,3><<<grid, 128, 200 * 1024>>>(c.M, c.N, iters, out); break;
+      }
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s: %s\n", c.name, cudaGetErrorString(e)); return 1; }
-      printf("  %-38s elect=%d issue %.1f cyc/mma, complete %.1f cyc/mma  (%.0f MAC/cyc/SM)\n", c.name, nacc - 1, (double)out[0] / iters, (double)out[1] / iters,
+      printf("  %-38s elect=%d issue %.1f cyc/mma, complete %.1f cyc/mma  (%.0f MAC/cyc/SM)\n", c.name, 1, (double)out[0] / iters, (double)out[1] / iters,
              (double)c.M * c.N * 16 / ((double)out[1] / iters));
       }
     }
