@@ -308,8 +308,12 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         alg_bytes = 4.0 * rows * D + 4.0 * rows  # X once + y once, per launch
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture of this workload
+        tp = ROOT / "profiles" / "r01_traffic.json"
+        if tp.exists() and kernel == "tcgen05_bf16_split" and rows == N_C3:
+            traffic = json.loads(tp.read_text()).get("traffic_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+                    "traffic": traffic, "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             xs = X[: args.cpu_rows].cpu()
