@@ -41,6 +41,12 @@ constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 800
 constexpr int TMEM_COLS = 512;
 constexpr int ACC1_COL = 0;        // 64 columns: logits [x*t1 | x1*t2]
 constexpr int ACC2_COL = 128;      // 4 chunks x 64 columns: G^T [x*e1 | x1*e2]
+// The tensor core's fp32 accumulate truncates: a TMEM accumulation chain picks up a systematic bias of ~1.4e-7 (relative)
+// per tile (measured, scripts/accum_check.py: 1.2e-4 on the gradient after 845 tiles).  The GEMM2 accumulators are
+// therefore flushed into an fp32 partial in global memory every ACC2_FLUSH tiles and the chain is restarted, which
+// bounds the bias near 2e-6.  The four 128-column chunks are drained in rotation (one every ACC2_FLUSH/4 tiles) so that
+// the work fits in the epilogue warps' idle window.
+constexpr int ACC2_FLUSH = 16;
 
 struct Bars {
   unsigned long long x_full[8], x_empty[8];
@@ -109,6 +115,12 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----------------------------------------------------------
@@ -158,7 +170,7 @@ template <int NBLK>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
          int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
-         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist) {
+         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist, int flush_tiles) {
   using namespace tc;
   // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
   constexpr int64_t TRACE_T0 = 16;
@@ -296,6 +308,8 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
     const uint64_t tx1 = make_desc(smem_u32(sx1), BLK_BYTES, 1024), tx2 = make_desc(smem_u32(sx2), BLK_BYTES, 1024);
     const uint64_t tdl = make_desc(smem_u32(sdl), BLK_BYTES, 1024);
+    const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;  // chunk ch is drained when phase == ch * flush_step
+    int phase = 0;                                                          // it % (NCH * flush_step)
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       // ---- GEMM1: logits tile, block by block as the loaders publish them
@@ -328,7 +342,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 rows = two 8-row swizzle atoms, 1024 bytes apart)
             if (ablate & 2) continue;
-            umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2, (it | k) != 0);
+            umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2, (k != 0) || !(it == 0 || phase == ch * flush_step));
             umma_bf16(tmem + ACC2_COL + ch * NB, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
           }
           umma_commit(&bars->x_empty[2 * ch]);
@@ -339,6 +353,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       if (elect_one()) umma_commit(&bars->dl_empty);
       __syncwarp();
       if (lane == 0) BJX_TRACE(it, 26);
+      if (++phase == NCH * flush_step) phase = 0;
     }
     if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
@@ -359,8 +374,48 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     }
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
     const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
+    float* gp = Gpart + (size_t)blockIdx.x * S * D;
+    // Move the GEMM2 accumulators (TMEM lanes = d, columns = [x*e1 | x1*e2]) into the per-CTA fp32 partial G[s, d], eight
+    // samples at a time, with fire-and-forget reductions.  Only this thread ever touches a given address and reductions of
+    // one thread to one address are applied in program order, so the sum is deterministic.
+    auto drain_chunk = [&](int ch, bool first) {
+      {
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+          const int sb = h * 16 + part * 8;
+          uint32_t fa[8], fb[8];
+          tmem_ld8(t_lane + ACC2_COL + ch * NB + sb, fa);
+          tmem_ld8(t_lane + ACC2_COL + ch * NB + NS + sb, fb);
+          float* base = gp + (size_t)sb * D + ch * 128 + 32 * q + lane;
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (sb + j < S) {
+              const float val = __uint_as_float(fa[j]) + __uint_as_float(fb[j]);
+              if (first)
+                __stcg(base + (size_t)j * D, val);
+              else
+                atomicAdd(base + (size_t)j * D, val);  // result unused -> RED.ADD.F32: no round trip
+            }
+          }
+        }
+      }
+    };
+    const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
+    int phase = 0;
+    uint32_t flushed = 0;  // bit ch: chunk ch has been stored to the partial at least once
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
+      if (it > 0 && phase % flush_step == 0 && phase / flush_step < NCH) {
+        // GEMM2 of the previous tile has retired (dl_empty); this warp would otherwise idle until the next logits arrive
+        const int ch = phase / flush_step;
+        mbar_wait(&bars->dl_empty, ph ^ 1);
+        tc_fence_after();
+        drain_chunk(ch, !((flushed >> ch) & 1u));  // the MMA warp restarts this chunk's chain with this tile's GEMM2
+        tc_fence_before();
+        flushed |= 1u << ch;
+      }
+      if (++phase == NCH * flush_step) phase = 0;
       const int64_t row = (blockIdx.x + it * gridDim.x) * TILE_ROWS + r;
       const bool row_ok = row < N;
       const float yv = row_ok ? y[row] : 0.0f;
@@ -439,21 +494,13 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     if (warp == EPI_WARP0 && lane < S) {
       statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
     }
-    // ---- per-CTA partial of G[s, d]: read the GEMM2 accumulators once all MMAs have retired
+    // ---- per-CTA partial of G[s, d]: add what is left in the GEMM2 accumulators once all MMAs have retired
     mbar_wait(&bars->done, 0);
     tc_fence_after();
-    float* gp = Gpart + (size_t)blockIdx.x * S * D;
-    for (int ch = 0; ch < NCH; ++ch) {
-      uint32_t va[16], vb[16];
-      tmem_ld16(t_lane + ACC2_COL + ch * NB + h * 16, va);
-      tmem_ld16(t_lane + ACC2_COL + ch * NB + NS + h * 16, vb);
-      tmem_ld_wait();
-      const int d = ch * 128 + 32 * q + lane;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int s = h * 16 + j;
-        if (s < S) gp[(size_t)s * D + d] = my_tiles > 0 ? __uint_as_float(va[j]) + __uint_as_float(vb[j]) : 0.0f;
-      }
+    if (my_tiles > 0) {
+      for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, !((flushed >> ch) & 1u));
+    } else {
+      for (int i = (warp - EPI_WARP0) * 32 + lane; i < S * D; i += EPI_WARPS * 32) gp[i] = 0.0f;
     }
   }
 
@@ -468,6 +515,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
 static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
 static int g_pf = 8;                 // L2 prefetch distance in blocks (BJX_TC_PF overrides; 0 = off)
+static int g_flush = tc::ACC2_FLUSH;  // tiles between flushes of the GEMM2 accumulators (BJX_TC_FLUSH overrides)
 static long long* g_trace = nullptr;  // device buffer of 8 x 64 clock64 slots, or null (production)
 
 static size_t tc_smem_bytes(int nblk) {
@@ -502,6 +550,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
     if (const char* e = getenv("BJX_TC_ABLATE")) g_ablate = atoi(e);
     if (const char* e = getenv("BJX_TC_PF")) g_pf = atoi(e);
+    if (const char* e = getenv("BJX_TC_FLUSH")) g_flush = atoi(e) > 0 ? atoi(e) : 1;
     env_read = true;
   }
   const float* theta = (const float*)(ws + p.o_theta);
@@ -517,7 +566,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf);                     \
+                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush);                     \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;

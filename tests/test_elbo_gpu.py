@@ -227,3 +227,79 @@ def test_tensor_core_path(N, D, S, lik):
     loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
     raw = np.full(D, math.log(0.1), np.float32)
     _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_bf16_split")
+
+
+def _tc_engine(D, lik=None, precision="auto"):
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lik or lk.BernoulliLogits(), precision=precision)
+    return model._engine_for({})[0]
+
+
+def _device_logistic(N, D, seed=1234):
+    """The bench's synthetic data, generated on the device (same generator as bench.py)."""
+    from bijax_b200 import random as br
+
+    X = br.normal(br.PRNGKey(seed), (N, D), partitionable=True)
+    X.mul_(1.0 / math.sqrt(D))
+    w = br.normal(br.PRNGKey(seed + 1), (D,), partitionable=True)
+    u = br.uniform(br.PRNGKey(seed + 2), (N,), partitionable=True)
+    y = (u < torch.sigmoid(X @ w)).float()
+    return X, y
+
+
+def test_full_size_c2_against_the_oracle():
+    """config c2 at BASELINE.json's full size: D=5 (+ learnable log_noise_scale), N=1M, S=64 -- the float64 oracle still
+    finishes in seconds at this size, so parity is checked directly."""
+    N, D, S = 1_000_000, 5, 64
+    X, y = C.synth_linear(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.GaussianLinear())
+    loc = np.zeros(D, np.float32)
+    raw = np.full(D, math.log(0.1), np.float32)
+    _run_case(model, ref, loc, raw, {"log_noise_scale": np.float32(math.log(0.1))}, y, X, N, 0, S, 0, expect_kernel="fp32_smalld")
+
+
+def test_large_shape_properties_of_the_tensor_core_path():
+    """config c3 shape (D=512, S=32) at 2M rows, where no CPU oracle is affordable: size-independent properties.
+    (1) idempotence: the step is bit-reproducible; (2) shard additivity: the packed outputs of row shards, with the
+    q/prior terms on one shard only, sum to the unsharded output; (3) agreement with the independent fp32 CUDA-core
+    kernel on the same device data."""
+    from bijax_b200 import random as br
+
+    N, D, S = 2_000_000, 512, 32
+    X, y = _device_logistic(N, D)
+    eng = _tc_engine(D)
+    assert eng.kernel_choice(S, N) == "tcgen05_bf16_split"
+    dev = X.device
+    loc = 0.02 * br.normal(br.PRNGKey(5), (D,), partitionable=True)
+    raw = torch.full((D,), math.log(0.1), device=dev)
+    key = br.PRNGKey(123)
+    full = eng.step(key, loc, raw, None, X, y, 1.0, S).clone()
+    again = eng.step(key, loc, raw, None, X, y, 1.0, S).clone()
+    assert torch.equal(full, again)
+    cut = 777_777  # deliberately not a multiple of the 64-row tile
+    a = eng.step(key, loc, raw, None, X[:cut], y[:cut], 1.0, S, prior_weight=1.0).clone()
+    b = eng.step(key, loc, raw, None, X[cut:], y[cut:], 1.0, S, prior_weight=0.0).clone()
+    C.assert_close((a + b).cpu().numpy(), full.cpu().numpy(), rtol=2e-6, atol_scale=2e-6, what="shard additivity")
+    ref_eng = _tc_engine(D, precision="fp32")
+    assert ref_eng.kernel_choice(S, N) == "fp32_tiled"
+    other = ref_eng.step(key, loc, raw, None, X, y, 1.0, S)
+    C.assert_close(full[:1].cpu().numpy(), other[:1].cpu().numpy(), what="loss vs fp32 kernel")
+    C.assert_close(full[1 : 1 + D].cpu().numpy(), other[1 : 1 + D].cpu().numpy(), what="d loc vs fp32 kernel")
+    C.assert_close(full[1 + D :].cpu().numpy(), other[1 + D :].cpu().numpy(), what="d rho vs fp32 kernel")
+
+
+def test_sample_count_invariance_of_eps_layout():
+    """eps for (S, D) is the flat stream reshaped, so the first S' < S samples of a partitionable draw are the S'-sample
+    draw: sharding the Monte-Carlo samples (small-N case) reproduces the same noise."""
+    from bijax_b200 import random as br
+
+    D = 128
+    eng = _tc_engine(D)
+    dev = torch.device("cuda")
+    X, y = _device_logistic(4096, D)
+    loc, raw = torch.zeros(D, device=dev), torch.full((D,), -1.0, device=dev)
+    e32, e8 = torch.empty(32 * D, device=dev), torch.empty(8 * D, device=dev)
+    eng.step(br.PRNGKey(3), loc, raw, None, X, y, 1.0, 32, eps_out=e32, partitionable=True)
+    eng.step(br.PRNGKey(3), loc, raw, None, X, y, 1.0, 8, eps_out=e8, partitionable=True)
+    assert torch.equal(e32[: 8 * D], e8)
