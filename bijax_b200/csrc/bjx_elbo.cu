@@ -120,7 +120,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
       p.sd_SB = next_pow2((int)(a.S < 256 ? a.S : 256));
       p.sd_grid_y = (int)((a.S + p.sd_SB - 1) / p.sd_SB);
       int64_t gx = (a.N + SD_CHUNK_ROWS - 1) / SD_CHUNK_ROWS;
-      const int64_t cap = (int64_t)sms * 4 / p.sd_grid_y;  // a whole number of resident waves (4 CTAs of 256 threads per SM)
+      const int64_t cap = (int64_t)sms * smalld_occupancy(p.sd_rec4) / p.sd_grid_y;  // exactly one resident wave
       if (gx > cap) gx = cap;
       if (gx < 1) gx = 1;
       p.sd_grid_x = (int)gx;
@@ -344,16 +344,36 @@ __global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, i
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ Gpart, int PG, const float* __restrict__ statpart,
                                                          int PS, int64_t SDw, int64_t S, float* __restrict__ G,
                                                          float* __restrict__ stat) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  // block = 32 consecutive outputs (coalesced) x 8 warps striding over the partial slots; the eight per-warp sums are
+  // combined in a fixed order through shared memory, so the result does not depend on timing
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  const float* src = nullptr;
+  int P = 0;
+  int64_t stride = 0;
+  float* dst = nullptr;
   if (i < SDw) {
-    float t = 0.0f;
-    for (int p = 0; p < PG; ++p) t += Gpart[(size_t)p * SDw + i];
-    G[i] = t;
+    src = Gpart + i; P = PG; stride = SDw; dst = G + i;
   } else if (i < SDw + S) {
-    const int64_t s = i - SDw;
+    src = statpart + (i - SDw); P = PS; stride = S; dst = stat + (i - SDw);
+  }
+  float t0 = 0.0f, t1 = 0.0f;
+  if (src != nullptr) {
+    int p = w;
+    for (; p + 8 < P; p += 16) {
+      t0 += src[(size_t)p * stride];
+      t1 += src[(size_t)(p + 8) * stride];
+    }
+    if (p < P) t0 += src[(size_t)p * stride];
+  }
+  red[w][lane] = t0 + t1;
+  __syncthreads();
+  if (w == 0 && dst != nullptr) {
     float t = 0.0f;
-    for (int p = 0; p < PS; ++p) t += statpart[(size_t)p * S + s];
-    stat[s] = t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    *dst = t;
   }
 }
 
@@ -369,15 +389,16 @@ __device__ __forceinline__ float tau_of(const TailArgs& t, const float* kwargs, 
   return t.noise_value;
 }
 
-// One thread per latent coordinate d; loops over the S samples.
+// One WARP per latent coordinate d; lanes stride over the S samples, fixed-shape shuffle reduction (deterministic).
 //   gz[s,d] = prior_weight * (-d log p~ / dz) / S  -  (ll_scale / S) * dll_s/dtheta_d * b'(z)
 //   d loc[d] = sum_s gz;   d rho[d] = sigma'(rho) * sum_s gz * eps  -  prior_weight * dlog sigma / d rho     (mean field)
-__global__ void __launch_bounds__(128) k_tail(TailArgs t, const float* __restrict__ raw, const float* __restrict__ kwargs,
+__global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restrict__ raw, const float* __restrict__ kwargs,
                                               const float* __restrict__ eps, const float* __restrict__ theta,
                                               const float* __restrict__ bprime, const float* __restrict__ gprior,
                                               const float* __restrict__ G, const float* __restrict__ stat,
                                               float* __restrict__ gz_out, float* __restrict__ out) {
-  const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t d = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (d >= t.D) return;
   const float invS = 1.0f / (float)t.S;
   const float cS = t.ll_scale * invS;
@@ -385,7 +406,7 @@ __global__ void __launch_bounds__(128) k_tail(TailArgs t, const float* __restric
   const bool is_noise = t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_LATENT && d == t.noise_index;
   const int64_t Dw = t.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : t.Dw;
   float acc_mu = 0.0f, acc_rho = 0.0f;
-  for (int64_t s = 0; s < t.S; ++s) {
+  for (int64_t s = lane; s < t.S; s += 32) {
     const int64_t i = s * t.D + d;
     float dll = 0.0f;  // d ll_s / d theta[s, d]
     if (is_w) {
@@ -405,10 +426,14 @@ __global__ void __launch_bounds__(128) k_tail(TailArgs t, const float* __restric
     acc_mu += gz;
     acc_rho = fmaf(gz, eps[i], acc_rho);
   }
-  out[1 + d] = acc_mu;
-  if (t.vi_type == BJX_VI_MEAN_FIELD) {
-    const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
-    out[1 + t.D + d] = acc_rho * sc.dsigma - t.prior_weight * sc.dlogsigma;
+  acc_mu = warp_sum(acc_mu);
+  acc_rho = warp_sum(acc_rho);
+  if (lane == 0) {
+    out[1 + d] = acc_mu;
+    if (t.vi_type == BJX_VI_MEAN_FIELD) {
+      const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
+      out[1 + t.D + d] = acc_rho * sc.dsigma - t.prior_weight * sc.dlogsigma;
+    }
   }
 }
 
@@ -510,7 +535,7 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
     }
     if (rc) return rc;
     const int64_t SDw = a.S * Dw;
-    k_reduce_partials<<<(unsigned)((SDw + a.S + 255) / 256), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
+    k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
                                                                           (const float*)(ws + p.o_statpart), p.PS, SDw,
                                                                           a.S, G, stat);
     BJX_LAUNCH_CHECK("k_reduce_partials");
@@ -522,7 +547,7 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   t.noise_src = a.noise_src; t.noise_index = a.noise_index; t.noise_value = a.noise_value;
   t.ll_scale = a.ll_scale; t.prior_weight = a.prior_weight;
   float* gz = a.vi_type == BJX_VI_FULL_RANK ? (float*)(ws + p.o_gz) : nullptr;
-  k_tail<<<(unsigned)((a.D + 127) / 128), 128, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
+  k_tail<<<(unsigned)((a.D + 7) / 8), 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
                                                        (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
                                                        (const float*)(ws + p.o_gprior), G, stat, gz, a.out);
   BJX_LAUNCH_CHECK("k_tail");

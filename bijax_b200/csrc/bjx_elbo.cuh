@@ -28,6 +28,7 @@ struct Plan {
 int make_plan(const BjxElboArgs& a, Plan& p);
 
 // streaming likelihood launchers: fill Gpart[PG][S][Dw] (sum_n dll/deta * X) and statpart[PS][S]
+int smalld_occupancy(int rec4);  // resident CTAs per SM of k_lik_smalld<rec4>
 int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
 int launch_lik_tiled(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
 int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);

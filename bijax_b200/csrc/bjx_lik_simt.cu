@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
                                                     int64_t N, int Dw, const float* __restrict__ theta, int64_t D,
                                                     int64_t w_off, int S, int family, int SB, int64_t rows_per_cta,
                                                     float* __restrict__ Gpart, float* __restrict__ statpart) {
-  constexpr int REC = REC4 * 4;
+  constexpr int REC = REC4 * 4;  // record = [y, x_0 .. x_{Dw-1}, 0 ...]: y sits at a fixed slot
+  constexpr int ROWS = 4;        // rows per inner iteration: independent eta chains give the FMA pipe some ILP
   __shared__ __align__(16) float sm[256 * (REC + 1)];
   const int tid = threadIdx.x;
   const int RL = 256 / SB;
@@ -29,10 +30,10 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
   const int s = blockIdx.y * SB + sl;
   const bool s_ok = s < S;
 
-  float th[REC], G[REC];
+  float th[REC], G[REC];  // th[0] = 0 (the y slot), th[1 + d] = theta[s, d]
 #pragma unroll
   for (int d = 0; d < REC; ++d) {
-    th[d] = (s_ok && d < Dw) ? theta[(int64_t)s * D + w_off + d] : 0.0f;
+    th[d] = (s_ok && d >= 1 && d <= Dw) ? theta[(int64_t)s * D + w_off + d - 1] : 0.0f;
     G[d] = 0.0f;
   }
   float stat = 0.0f;
@@ -42,36 +43,51 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
   for (int64_t base = row_begin; base < row_end; base += SD_CHUNK) {
     const int nvalid = (int)min((int64_t)SD_CHUNK, row_end - base);
     __syncthreads();  // previous chunk fully consumed
-    if (tid < nvalid) {
-      const float* xr = X + (base + tid) * ldx;
+    {
       float* rec = sm + tid * REC;
+      if (tid < nvalid) {
+        const float* xr = X + (base + tid) * ldx;
+        rec[0] = y[base + tid];
 #pragma unroll
-      for (int d = 0; d < REC; ++d) rec[d] = d < Dw ? xr[d] : 0.0f;
-      rec[Dw] = y[base + tid];
+        for (int d = 1; d < REC; ++d) rec[d] = d <= Dw ? xr[d - 1] : 0.0f;
+      } else {  // rows past the end: eta = 0 and y = 0 would still contribute f(0, 0); they are masked below
+#pragma unroll
+        for (int d = 0; d < REC; ++d) rec[d] = 0.0f;
+      }
     }
     __syncthreads();
-    for (int r = rl; r < nvalid; r += RL) {
-      float rec[REC];
-      const float4* rp = reinterpret_cast<const float4*>(sm + r * REC);
+    for (int r0 = rl; r0 < nvalid; r0 += ROWS * RL) {
+      float rec[ROWS][REC];
 #pragma unroll
-      for (int q = 0; q < REC4; ++q) {
-        const float4 v = rp[q];
-        rec[4 * q + 0] = v.x;
-        rec[4 * q + 1] = v.y;
-        rec[4 * q + 2] = v.z;
-        rec[4 * q + 3] = v.w;
+      for (int u = 0; u < ROWS; ++u) {
+        const int r = min(r0 + u * RL, SD_CHUNK - 1);
+        const float4* rp = reinterpret_cast<const float4*>(sm + r * REC);
+#pragma unroll
+        for (int q = 0; q < REC4; ++q) {
+          const float4 v = rp[q];
+          rec[u][4 * q + 0] = v.x;
+          rec[u][4 * q + 1] = v.y;
+          rec[u][4 * q + 2] = v.z;
+          rec[u][4 * q + 3] = v.w;
+        }
       }
-      float yv = 0.0f;
+      float eta[ROWS];
 #pragma unroll
-      for (int d = 0; d < REC; ++d) yv = (d == Dw) ? rec[d] : yv;
-      float eta = 0.0f;
+      for (int u = 0; u < ROWS; ++u) eta[u] = 0.0f;
 #pragma unroll
-      for (int d = 0; d < REC; ++d) eta = fmaf(rec[d], th[d], eta);  // th[d >= Dw] == 0: y and padding drop out
-      float f, g;
-      link_eval(family, yv, eta, f, g);
-      stat += f;
+      for (int d = 1; d < REC; ++d)
 #pragma unroll
-      for (int d = 0; d < REC; ++d) G[d] = fmaf(g, rec[d], G[d]);
+        for (int u = 0; u < ROWS; ++u) eta[u] = fmaf(rec[u][d], th[d], eta[u]);  // th[d > Dw] == 0: padding drops out
+#pragma unroll
+      for (int u = 0; u < ROWS; ++u) {
+        float f, g;
+        link_eval(family, rec[u][0], eta[u], f, g);
+        const bool ok = r0 + u * RL < nvalid;
+        stat += ok ? f : 0.0f;
+        g = ok ? g : 0.0f;
+#pragma unroll
+        for (int d = 1; d < REC; ++d) G[d] = fmaf(g, rec[u][d], G[d]);
+      }
     }
   }
 
@@ -93,10 +109,23 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
     }
     float* gp = Gpart + ((size_t)blockIdx.x * S + s) * Dw;
 #pragma unroll
-    for (int d = 0; d < REC; ++d)
-      if (d < Dw) gp[d] = acc[d];
+    for (int d = 1; d < REC; ++d)
+      if (d <= Dw) gp[d - 1] = acc[d];
     statpart[(size_t)blockIdx.x * S + s] = acc[REC];
   }
+}
+
+int smalld_occupancy(int rec4) {
+  int occ = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (rec4) {
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<1>, 256, 0); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<2>, 256, 0); break;
+    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<3>, 256, 0); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<4>, 256, 0); break;
+    default: break;
+  }
+  return (e == cudaSuccess && occ > 0) ? occ : 1;
 }
 
 int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
