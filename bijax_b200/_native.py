@@ -23,7 +23,8 @@ PRIOR_NORMAL, PRIOR_BETA, PRIOR_GAMMA = 0, 1, 2
 LIK_BERNOULLI_LOGITS, LIK_GAUSSIAN, LIK_BERNOULLI_PROBS = 0, 1, 2
 NOISE_CONST, NOISE_KWARG, NOISE_LATENT = 0, 1, 2
 PREC_AUTO, PREC_FP32, PREC_BF16X3, PREC_BF16X2 = 0, 1, 2, 3
-KERNEL_NAMES = {0: "fp32_tiled", 1: "fp32_smalld", 2: "tcgen05_bf16_split", 3: "coin"}
+KERNEL_NAMES = {0: "fp32_tiled", 1: "fp32_smalld", 2: "tcgen05_bf16_split", 3: "coin", 4: "tcgen05_gemm_two_pass"}
+KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 
 EXPORTED_SYMBOLS = (
     "bjx_abi_version",
@@ -66,7 +67,7 @@ class BjxElboArgs(C.Structure):
         ("noise_index", C.c_int32),
         ("threefry_layout", C.c_int32),
         ("precision", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("kernel_override", C.c_int32),
         ("noise_value", C.c_float),
         ("ll_scale", C.c_float),
         ("prior_weight", C.c_float),

@@ -95,14 +95,27 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
                     "latent noise coordinate out of range or inside the weights");
     }
     const bool want_tc = a.precision == BJX_PREC_BF16X2 || a.precision == BJX_PREC_BF16X3 || a.precision == BJX_PREC_AUTO;
-    if (a.precision != BJX_PREC_FP32 && a.precision != BJX_PREC_AUTO && !tc_eligible(a))
+    if (a.precision != BJX_PREC_FP32 && a.precision != BJX_PREC_AUTO && !tc_eligible(a) && !gemm_eligible(a))
       return fail(BJX_ERR_UNSUPPORTED, "tensor-core precision requested but the shape is outside the tcgen05 kernel's envelope");
+    // the two-pass GEMM path pays for operand planes and two launches: use it when the contraction is large
+    const bool gemm_worth = (double)a.N * (double)a.S * (double)a.Dw >= 134217728.0 || a.precision == BJX_PREC_BF16X2;
     if (want_tc && tc_eligible(a))
       p.kernel = KERNEL_TC_BF16;
+    else if (want_tc && gemm_eligible(a) && gemm_worth)
+      p.kernel = KERNEL_TC_GEMM;
     else if (a.Dw <= 15)
       p.kernel = KERNEL_FP32_SMALLD;
     else
       p.kernel = KERNEL_FP32_TILED;
+    if (a.kernel_override != 0) {  // tests and benchmarks: force a specific streaming kernel (KERNEL_* + 1)
+      const int k = a.kernel_override - 1;
+      BJX_REQUIRE(k == KERNEL_FP32_TILED || k == KERNEL_FP32_SMALLD || k == KERNEL_TC_BF16 || k == KERNEL_TC_GEMM,
+                  "kernel_override %d is not a streaming-likelihood kernel", a.kernel_override);
+      if (k == KERNEL_TC_BF16 && !tc_eligible(a)) return fail(BJX_ERR_UNSUPPORTED, "shape outside the fused tcgen05 kernel's envelope");
+      if (k == KERNEL_TC_GEMM && !gemm_eligible(a)) return fail(BJX_ERR_UNSUPPORTED, "shape outside the tcgen05 GEMM path's envelope");
+      if (k == KERNEL_FP32_SMALLD && a.Dw > 15) return fail(BJX_ERR_UNSUPPORTED, "small-D kernel needs Dw <= 15");
+      p.kernel = k;
+    }
   } else {
     return fail(BJX_ERR_INVALID_ARGUMENT, "unknown likelihood family %d", a.likelihood);
   }
@@ -153,7 +166,15 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
       p.PG = p.PS = p.tc_ctas;
       break;
     }
+    case KERNEL_TC_GEMM: {
+      int rc = gemm_plan(a, p);
+      if (rc) return rc;
+      p.PG = p.gm_splits;
+      p.PS = 4 * p.gm_grid1;
+      break;
+    }
   }
+  p.fr_tc = (a.vi_type == BJX_VI_FULL_RANK && a.precision != BJX_PREC_FP32 && fullrank_tc_eligible(a)) ? 1 : 0;
 
   // workspace carve-up (256-byte aligned regions)
   size_t off = 0;
@@ -177,6 +198,11 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   p.o_statpart = take((size_t)p.PS * a.S * sizeof(float));
   p.o_gbuf = take(p.kernel == KERNEL_FP32_TILED ? (size_t)a.N * a.S * sizeof(float) : 0);
   p.o_tc_theta = take(p.kernel == KERNEL_TC_BF16 ? tc_theta_bytes(a, p) : 0);
+  const bool gm = p.kernel == KERNEL_TC_GEMM;
+  p.o_gm_x = take(gm ? (size_t)2 * a.N * p.gm_Dp * 2 : 0);
+  p.o_gm_t = take(gm ? (size_t)2 * a.S * p.gm_Dp * 2 : 0);
+  p.o_gm_g = take(gm ? (size_t)2 * a.N * p.gm_Sp * 2 : 0);
+  p.o_fr_tc = take(p.fr_tc ? fullrank_tc_bytes(a) : 0);
   p.o_stage_key = take(16);
   p.o_stage_params = take((size_t)(a.D + p.Pn + a.K) * sizeof(float));
   p.o_stage_out = take((size_t)(1 + a.D + p.Pn + a.K) * sizeof(float));
@@ -481,9 +507,14 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
   if (a.vi_type == BJX_VI_FULL_RANK) {
     k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, total, a.threefry_layout, eps);
     BJX_LAUNCH_CHECK("k_eps");
-    dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.S + 63) / 64));
-    k_fullrank_z<<<grid, 256, 0, st>>>(eps, a.raw_scale, a.loc, a.S, a.D, a.scale_bijector, z);
-    BJX_LAUNCH_CHECK("k_fullrank_z");
+    if (p.fr_tc) {
+      int rc = launch_fullrank_z_tc(a, eps, z, ws + p.o_fr_tc, st);
+      if (rc) return rc;
+    } else {
+      dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.S + 63) / 64));
+      k_fullrank_z<<<grid, 256, 0, st>>>(eps, a.raw_scale, a.loc, a.S, a.D, a.scale_bijector, z);
+      BJX_LAUNCH_CHECK("k_fullrank_z");
+    }
     k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                     a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
                                                     probs_coord, aux);
@@ -528,6 +559,8 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
         rc = launch_lik_smalld(a, p, ws, st);
       } else if (p.kernel == KERNEL_FP32_TILED) {
         rc = launch_lik_tiled(a, p, ws, st);
+      } else if (p.kernel == KERNEL_TC_GEMM) {
+        rc = launch_lik_gemm(a, p, ws, st);
       } else {
         rc = launch_lik_tc(a, p, ws, st);
       }
@@ -552,10 +585,15 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
                                                        (const float*)(ws + p.o_gprior), G, stat, gz, a.out);
   BJX_LAUNCH_CHECK("k_tail");
   if (a.vi_type == BJX_VI_FULL_RANK) {
-    dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.D + 63) / 64));
-    k_fullrank_dM<<<grid, 256, 0, st>>>(gz, (const float*)(ws + p.o_eps), a.raw_scale, a.S, a.D, a.scale_bijector,
-                                        a.prior_weight, a.out + 1 + a.D);
-    BJX_LAUNCH_CHECK("k_fullrank_dM");
+    if (p.fr_tc) {
+      rc = launch_fullrank_dM_tc(a, gz, a.out + 1 + a.D, ws + p.o_fr_tc, st);
+      if (rc) return rc;
+    } else {
+      dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.D + 63) / 64));
+      k_fullrank_dM<<<grid, 256, 0, st>>>(gz, (const float*)(ws + p.o_eps), a.raw_scale, a.S, a.D, a.scale_bijector,
+                                          a.prior_weight, a.out + 1 + a.D);
+      BJX_LAUNCH_CHECK("k_fullrank_dM");
+    }
   }
   k_scalars<<<1, 256, 0, st>>>(t, a.K, p.Pn, a.kwargs, (const float*)(ws + p.o_theta), (const float*)(ws + p.o_qp),
                                p.n_qp_blocks, stat, a.out);

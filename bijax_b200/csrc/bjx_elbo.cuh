@@ -4,7 +4,7 @@
 
 namespace bjx {
 
-enum { KERNEL_FP32_TILED = 0, KERNEL_FP32_SMALLD = 1, KERNEL_TC_BF16 = 2, KERNEL_COIN = 3 };
+enum { KERNEL_FP32_TILED = 0, KERNEL_FP32_SMALLD = 1, KERNEL_TC_BF16 = 2, KERNEL_COIN = 3, KERNEL_TC_GEMM = 4 };
 
 constexpr int SD_CHUNK_ROWS = 256;  // rows staged per shared-memory chunk by the small-D kernel
 
@@ -20,8 +20,12 @@ struct Plan {
   int64_t tB_rows_per_slot;
   // tensor-core
   int tc_ctas, tc_terms;
+  // two-pass TMA-fed tensor-core GEMM path (bjx_gemm_tc.cu)
+  int gm_grid1, gm_grid2, gm_splits;
+  int64_t gm_Dp, gm_Sp;  // padded plane pitches (elements)
+  int fr_tc;             // full-rank contractions on the tensor cores
   // byte offsets into the workspace
-  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta,
+  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta, o_gm_x, o_gm_t, o_gm_g, o_fr_tc,
       o_stage_key, o_stage_params, o_stage_out, total;
 };
 
@@ -35,6 +39,14 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
 bool tc_eligible(const BjxElboArgs& a);
 int tc_plan(const BjxElboArgs& a, Plan& p);          // fills tc_ctas / tc_terms
 size_t tc_theta_bytes(const BjxElboArgs& a, const Plan& p);
+// two-pass GEMM path for shapes outside the fused kernel's envelope (S > 32 or D > 512), and the full-rank contractions
+bool gemm_eligible(const BjxElboArgs& a);
+int gemm_plan(const BjxElboArgs& a, Plan& p);  // fills gm_*
+int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
+bool fullrank_tc_eligible(const BjxElboArgs& a);
+size_t fullrank_tc_bytes(const BjxElboArgs& a);
+int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);
+int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, cudaStream_t st);
 
 // per-datum link functions (the elementwise part of advi.py:91 for the recognised families)
 //   Bernoulli(logits=eta): f = y*eta - softplus(eta)   (== -(1-y) softplus(eta) - y softplus(-eta)),  g = y - sigmoid(eta)

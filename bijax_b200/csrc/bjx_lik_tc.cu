@@ -19,11 +19,10 @@
 //               scoreboards between prefetch stages, which serialises them; depth comes from the number of warps.
 //   warp  16    MMA issuer (converged warp, elect.sync), owns the TMEM allocation
 //   warps 17-24 epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
-#include <cuda_bf16.h>
-
 #include <cstdlib>
 
 #include "bjx_elbo.cuh"
+#include "bjx_tc_ptx.cuh"
 
 namespace bjx {
 
@@ -54,99 +53,6 @@ struct Bars {
   uint32_t tmem_base;
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(void* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra D_%=;\n\t"
-      "bra W_%=;\n\t"
-      "D_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680)  // suspend-time hint: sleep in hardware instead of spinning on the shared-memory port
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(void* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(void* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) ----------------------------------------------------------
-// shared-memory matrix descriptor, 128-byte swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// ---- bf16 splitting ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// x = x1 + x2 (+ dropped 2^-18 relative): returns packed pairs for two consecutive elements
-__device__ __forceinline__ void split2(float a, float b, uint32_t& p1, uint32_t& p2) {
-  p1 = pack_bf16x2(a, b);
-  const float a1 = __uint_as_float(p1 << 16), b1 = __uint_as_float(p1 & 0xFFFF0000u);
-  p2 = pack_bf16x2(a - a1, b - b1);
-}
-
 // Link functions with ONE exponential per datum (MUFU.EX2 / LG2 / RCP): e = exp(-|eta|),
 // softplus(eta) = max(eta, 0) + log(1 + e), sigmoid(eta) = (eta >= 0 ? 1 : e) / (1 + e).  Absolute error ~1e-7 per datum.
 __device__ __forceinline__ void link_fast(int family, float y, float eta, float& f, float& g) {
@@ -170,7 +76,7 @@ template <int NBLK>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
          int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
-         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist, int flush_tiles) {
+         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist, int flush_tiles, int pf_mode) {
   using namespace tc;
   // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
   constexpr int64_t TRACE_T0 = 16;
@@ -261,11 +167,18 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       }
       // fire-and-forget L2 prefetch of the SAME unit of the next tile (16 rows x 256 B = 32 lines, one per lane): HBM keeps
       // streaming into the 126 MB L2 while this warp's registers are tied up waiting for the shared-memory slot
-      if (pf_dist > 0) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
+      if (pf_dist > 0 && pf_mode < 2) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
         const int64_t gp = g + pf_dist;
         const int64_t prow = (blockIdx.x + (gp / NBLK) * gridDim.x) * TILE_ROWS + 16 * qd + (lane >> 1);
-        if (gp < total_blocks && prow < N)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(X + prow * ldx + (gp % NBLK) * BLK_COLS + (lane & 1) * 32));
+        if (gp < total_blocks && prow < N) {
+          const float* pp = X + prow * ldx + (gp % NBLK) * BLK_COLS + (lane & 1) * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+          if (pf_mode == 1) {  // touch every 32-byte sector of the 128-byte line
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 24));
+          }
+        }
       }
       if (tid == 0 && b == 4) BJX_TRACE(it, 48);                // loads issued
       mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
@@ -312,6 +225,21 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     int phase = 0;                                                          // it % (NCH * flush_step)
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
+      if (pf_mode == 2 && pf_dist > 0) {
+        // asynchronous bulk prefetch (TMA engine, no LSU / scoreboard involvement) of a whole tile pf_dist/NBLK tiles ahead
+        const int64_t itp = it + pf_dist / NBLK;
+        if (itp < my_tiles && elect_one()) {
+          const int64_t row0 = (blockIdx.x + itp * gridDim.x) * TILE_ROWS;
+          const int64_t rows = (N - row0) < TILE_ROWS ? (N - row0) : TILE_ROWS;
+          if (ldx == D) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(X + row0 * ldx), "r"((uint32_t)(rows * D * 4)) : "memory");
+          } else {
+            for (int64_t rr = 0; rr < rows; ++rr)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(X + (row0 + rr) * ldx), "r"((uint32_t)(D * 4)) : "memory");
+          }
+        }
+        __syncwarp();
+      }
       // ---- GEMM1: logits tile, block by block as the loaders publish them
       for (int b = 0; b < NBLK; ++b) {
         // (no tcgen05.fence here: the operands come from generic-proxy stores ordered by the mbarrier + proxy fence, and
@@ -514,6 +442,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 // =========================================================================================================================
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
 static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
+static int g_pf_mode = 0;            // 0 per-lane line prefetch by the loaders, 1 per-sector, 2 bulk prefetch by the MMA warp (BJX_TC_PFMODE)
 static int g_pf = 8;                 // L2 prefetch distance in blocks (BJX_TC_PF overrides; 0 = off)
 static int g_flush = tc::ACC2_FLUSH;  // tiles between flushes of the GEMM2 accumulators (BJX_TC_FLUSH overrides)
 static long long* g_trace = nullptr;  // device buffer of 8 x 64 clock64 slots, or null (production)
@@ -550,6 +479,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
     if (const char* e = getenv("BJX_TC_ABLATE")) g_ablate = atoi(e);
     if (const char* e = getenv("BJX_TC_PF")) g_pf = atoi(e);
+    if (const char* e = getenv("BJX_TC_PFMODE")) g_pf_mode = atoi(e);
     if (const char* e = getenv("BJX_TC_FLUSH")) g_flush = atoi(e) > 0 ? atoi(e) : 1;
     env_read = true;
   }
@@ -566,7 +496,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush);                     \
+                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush, g_pf_mode);                     \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;

@@ -27,6 +27,7 @@ class ElboEngine:
         kwarg_layout: Sequence[Tuple[str, int]] = (),
         device=None,
         precision: str = "auto",
+        kernel: Optional[str] = None,
     ):
         nv.require_cuda()
         self.lib = nv.load()
@@ -47,6 +48,8 @@ class ElboEngine:
         self.kwarg_layout = list(kwarg_layout)  # [(name, numel)] in sorted-key order
         self.K = sum(n for _, n in self.kwarg_layout)
         self.precision = _PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        # tests / benchmarks may force one streaming kernel by name (nv.KERNEL_NAMES); None = the library's own choice
+        self.kernel_override = 0 if kernel is None else nv.KERNEL_IDS[kernel] + 1
         self.coords = torch.from_numpy(latents.coords.view(np.uint8).copy()).to(self.device)
         self._ws: Optional[torch.Tensor] = None
         self._resolve_likelihood()
@@ -96,6 +99,7 @@ class ElboEngine:
         a.noise_src, a.noise_index, a.noise_value = self.noise_src, self.noise_index, self.noise_value
         a.threefry_layout = layout
         a.precision = self.precision
+        a.kernel_override = self.kernel_override
         a.ll_scale, a.prior_weight = float(ll_scale), float(prior_weight)
         a.coords = self.coords.data_ptr()
         return a

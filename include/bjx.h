@@ -118,7 +118,8 @@ typedef struct BjxElboArgs {
   int32_t noise_index;     /* kwarg index or latent coordinate */
   int32_t threefry_layout; /* BJX_LAYOUT_* */
   int32_t precision;       /* BJX_PREC_* */
-  int32_t reserved0;
+  int32_t kernel_override; /* 0 = automatic choice; KERNEL id + 1 forces a streaming kernel (tests / benchmarks):
+                              1 fp32 tiled, 2 fp32 small-D, 3 fused tcgen05 single pass, 5 two-pass tcgen05 GEMM */
   float noise_value;   /* BJX_NOISE_CONST */
   float ll_scale;      /* full_data_size / len(outputs)   (advi.py:92; len = GLOBAL batch under sharding) */
   float prior_weight;  /* weight of the q / prior terms in THIS call's outputs: 1 on one rank, 0 on the
@@ -170,7 +171,8 @@ BJX_API int bjx_elbo_step(const BjxElboArgs* args, void* stream);
 BJX_API int bjx_elbo_step_host(const BjxElboArgs* args, const uint32_t* key_host, const float* params_host, float* out_host,
                        void* stream);
 
-/* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = tcgen05 split-bf16 */
+/* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = fused tcgen05 single pass
+ * (split-bf16), 3 = coin toss, 4 = two-pass TMA-fed tcgen05 GEMM (split-bf16) */
 BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
 
 /* ---- posterior access (.apply -> Posterior.sample / log_prob, core.py:39-75) */

@@ -229,6 +229,49 @@ def test_tensor_core_path(N, D, S, lik):
     _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_bf16_split")
 
 
+@pytest.mark.parametrize(
+    "N,D,S,lik",
+    [(300, 64, 40, "gauss"), (1000, 200, 64, "logit"), (4097, 512, 130, "gauss"), (2500, 1000, 256, "logit"),
+     (129, 2048, 256, "gauss"), (70000, 128, 33, "logit"), (1, 64, 1, "gauss")],
+)
+def test_two_pass_tensor_core_gemm_path(N, D, S, lik):
+    """config c4 shape family (S up to 256, D up to 2048): TMA-fed tcgen05 GEMMs with split-bf16 operand planes,
+    pass 1 = logits + link function, pass 2 = the transposed contraction of the VJP."""
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if lik == "logit":
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), kernel="tcgen05_gemm_two_pass")
+        kwargs = {}
+    else:
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), kernel="tcgen05_gemm_two_pass")
+        kwargs = {"log_noise_scale": np.float32(math.log(0.5))}
+    loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_gemm_two_pass")
+
+
+@pytest.mark.parametrize("D,S,lik", [(128, 10, "gauss"), (200, 130, "logit"), (384, 64, "gauss")])
+def test_full_rank_contractions_on_the_tensor_cores(D, S, lik):
+    """z = loc + tril(M) eps and dM = tril(sum_s gz eps^T) as TMA-fed tcgen05 GEMMs with a 3-term bf16 split (fp32-accurate);
+    taken for D >= 128 unless precision="fp32"."""
+    N = 600
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if lik == "gauss":
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), vi_type="full_rank")
+        kwargs = {"log_noise_scale": np.float32(math.log(0.2))}
+    else:
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), vi_type="full_rank")
+        kwargs = {}
+    loc = 0.1 * tf.normal(tf.prng_key(6), (D,), 1)
+    M = (0.1 * np.eye(D) + 0.01 * tf.normal(tf.prng_key(8), (D, D), 1)).astype(np.float32)  # conditioning stated: 0.1 I + 0.01 noise
+    loss, grads = _run_case(model, ref, loc, M, kwargs, y, X, N, 17, S, 0)
+    g = grads["posterior"]["scale_tril"].cpu().numpy()
+    assert np.all(np.triu(g, 1) == 0.0)
+
+
 def _tc_engine(D, lik=None, precision="auto"):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     model, _ = C.build_pair(prior, {}, lik or lk.BernoulliLogits(), precision=precision)
