@@ -13,7 +13,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_lib" / "libbjx.so"
 
 # ---- constants mirrored from include/bjx.h ----------------------------------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 LAYOUT_LEGACY, LAYOUT_PARTITIONABLE = 0, 1
 VI_MEAN_FIELD, VI_FULL_RANK = 0, 1
@@ -38,6 +38,8 @@ EXPORTED_SYMBOLS = (
     "bjx_elbo_step",
     "bjx_elbo_step_host",
     "bjx_elbo_kernel_choice",
+    "bjx_x_planes_bytes",
+    "bjx_prepare_x_planes",
     "bjx_posterior_sample",
     "bjx_adam_update",
     "bjx_profile_begin",
@@ -83,6 +85,7 @@ class BjxElboArgs(C.Structure):
         ("eps_out", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("x_planes", C.c_void_p),
     ]
 
 
@@ -124,6 +127,9 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step.argtypes = [C.POINTER(BjxElboArgs), vp]
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
+    lib.bjx_x_planes_bytes.argtypes = [i64, i64]
+    lib.bjx_x_planes_bytes.restype = C.c_size_t
+    lib.bjx_prepare_x_planes.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.bjx_posterior_sample.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp]
     lib.bjx_adam_update.argtypes = [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, vp]
     lib.bjx_profile_begin.argtypes = [i32]
@@ -132,7 +138,7 @@ def load() -> C.CDLL:
     lib.bjx_debug_set_trace_buffer.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what bjx.h declares
-        if name not in ("bjx_last_error", "bjx_elbo_workspace_bytes", "bjx_abi_version", "bjx_device_sm_count"):
+        if name not in ("bjx_last_error", "bjx_elbo_workspace_bytes", "bjx_abi_version", "bjx_device_sm_count", "bjx_x_planes_bytes"):
             fn.restype = C.c_int
     if lib.bjx_abi_version() != ABI_VERSION:
         raise ImportError(f"libbjx ABI {lib.bjx_abi_version()} != expected {ABI_VERSION}; rebuild with `python -m bijax_b200.build --force`")

@@ -199,7 +199,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   p.o_gbuf = take(p.kernel == KERNEL_FP32_TILED ? (size_t)a.N * a.S * sizeof(float) : 0);
   p.o_tc_theta = take(p.kernel == KERNEL_TC_BF16 ? tc_theta_bytes(a, p) : 0);
   const bool gm = p.kernel == KERNEL_TC_GEMM;
-  p.o_gm_x = take(gm ? (size_t)2 * a.N * p.gm_Dp * 2 : 0);
+  p.o_gm_x = take(gm && a.x_planes == nullptr ? x_planes_bytes(a.N, a.Dw) : 0);
   p.o_gm_t = take(gm ? (size_t)2 * a.S * p.gm_Dp * 2 : 0);
   p.o_gm_g = take(gm ? (size_t)2 * a.N * p.gm_Sp * 2 : 0);
   p.o_fr_tc = take(p.fr_tc ? fullrank_tc_bytes(a) : 0);
@@ -713,6 +713,19 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
     }
   }
   return BJX_OK;
+}
+
+size_t bjx_x_planes_bytes(int64_t N, int64_t Dw) {
+  if (N < 0 || Dw < 1) return 0;
+  return bjx::x_planes_bytes(N, Dw);
+}
+
+int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(X != nullptr && planes != nullptr, "null pointer");
+  BJX_REQUIRE(N >= 0 && Dw >= 1 && ldx >= Dw, "need N >= 0, Dw >= 1, ldx >= Dw");
+  BJX_REQUIRE(((uintptr_t)planes & 15) == 0, "planes must be 16-byte aligned");
+  return split_x_planes(X, N, Dw, ldx, planes, (cudaStream_t)stream);
 }
 
 int bjx_profile_begin(int32_t capacity) {

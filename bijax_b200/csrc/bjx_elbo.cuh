@@ -43,6 +43,8 @@ size_t tc_theta_bytes(const BjxElboArgs& a, const Plan& p);
 bool gemm_eligible(const BjxElboArgs& a);
 int gemm_plan(const BjxElboArgs& a, Plan& p);  // fills gm_*
 int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
+int split_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, cudaStream_t st);
+size_t x_planes_bytes(int64_t N, int64_t Dw);
 bool fullrank_tc_eligible(const BjxElboArgs& a);
 size_t fullrank_tc_bytes(const BjxElboArgs& a);
 int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);

@@ -5,7 +5,7 @@
 //
 //   EPI_LIK1  eta[n, s] = sum_d X[n, d] theta[s, d]   -> link function in the epilogue: g = dll/deta (written as bf16 split
 //                                                        planes for the next pass), stat[s] += f           (advi.py:90-91)
-//   EPI_LIK2  G[s, d]   = sum_n g[n, s] X[n, d]       -> the transposed contraction of the VJP             (utils.py:7)
+//   EPI_LIK2  G^T[d, s] = sum_n X[n, d] g[n, s]       -> the transposed contraction of the VJP             (utils.py:7)
 //   EPI_Z     z[s, i]   = loc[i] + sum_{j<=i} L[i, j] eps[s, j]   full-rank sample, tfd.MultivariateNormalTriL (advi.py:83)
 //   EPI_DM    dM[i, j]  = [j<=i] scale'(M_ij) sum_s gz[s, i] eps[s, j] - [i==j] prior_weight dlog|L_ii|     its VJP
 //
@@ -317,20 +317,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           if (s0 + lane < e.S) atomicAdd(statp + s0 + lane, tot);
         }
       } else if (EPI == EPI_LIK2) {
-        if (!empty) {  // warp-uniform; tcgen05.ld is warp-collective, only the stores are predicated per lane
-          const bool r_ok = r < e.S;
-          float* gp = e.Gpart + ((size_t)split * e.S + (r_ok ? r : 0)) * e.Dw;
+        // accumulator rows = weight column d, columns = sample s:  Gpart[split][s][d] += acc  (lanes contiguous in d: coalesced)
+        if (!empty) {  // warp-uniform; tcgen05.ld is warp-collective, only the reductions are predicated per lane
+          const bool r_ok = r < e.Dw;
+          float* gp = e.Gpart + (size_t)split * e.S * e.Dw + (r_ok ? r : 0);
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
-            const int64_t d0 = (int64_t)n_blk * BN + c * 32;
-            if (d0 >= e.Dw) break;
+            const int s0 = n_blk * BN + c * 32;
+            if (s0 >= e.S) break;
             uint32_t v[32];
             tmem_ld32(t_acc + c * 32, v);
             tmem_ld_wait();
             if (r_ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (d0 + j < e.Dw) atomicAdd(gp + d0 + j, __uint_as_float(v[j]));  // RED.ADD, same thread per address
+                if (s0 + j < e.S) atomicAdd(gp + (size_t)(s0 + j) * e.Dw, __uint_as_float(v[j]));  // RED.ADD, same thread per address
             }
           }
         }
@@ -522,6 +523,28 @@ static int64_t pad64(int64_t v) { return (v + 63) / 64 * 64; }
 
 }  // namespace gemm
 
+// X [N, ldx] fp32 -> two bf16 planes [N, pad64(Dw)] back to back (x = x1 + x2 to 2^-17 relative)
+int split_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, cudaStream_t st) {
+  using namespace gemm;
+  if (N <= 0) return BJX_OK;
+  const int64_t Dp = pad64(Dw);
+  __nv_bfloat16* x1 = (__nv_bfloat16*)planes;
+  __nv_bfloat16* x2 = x1 + (size_t)N * Dp;
+  const int64_t total = N * (Dp / 8);
+  if ((ldx % 4) == 0 && ((uintptr_t)X & 15) == 0) {
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_split_x<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, N, Dw, Dp, x1, x2);
+  } else {
+    k_split_planes<2, SrcPlain><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(SrcPlain{X, ldx}, N, Dw, Dp, x1, x2, nullptr);
+  }
+  BJX_LAUNCH_CHECK("k_split_x");
+  return BJX_OK;
+}
+
+size_t x_planes_bytes(int64_t N, int64_t Dw) { return (size_t)2 * (size_t)N * (size_t)gemm::pad64(Dw) * 2; }
+
 // =========================================================================================================================
 // Likelihood, two passes: eta + link (EPI_LIK1), then the transposed contraction (EPI_LIK2).
 bool gemm_eligible(const BjxElboArgs& a) {
@@ -533,15 +556,14 @@ bool gemm_eligible(const BjxElboArgs& a) {
 }
 
 static int lik1_bn(int64_t S) { return S <= 64 ? 64 : (S <= 128 ? 128 : 256); }
-static int lik2_bn(int64_t Dw) { return Dw <= 128 ? 128 : 256; }
 
 int gemm_plan(const BjxElboArgs& a, Plan& p) {
   const int sms = sm_count();
   if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
-  const int bn1 = lik1_bn(a.S), bn2 = lik2_bn(a.Dw);
+  const int bn1 = lik1_bn(a.S), bn2 = bn1;
   const int64_t tiles1 = ((a.N + 127) / 128) * ((a.S + bn1 - 1) / bn1);
   p.gm_grid1 = (int)(tiles1 < sms ? tiles1 : sms);
-  const int64_t tiles2 = ((a.S + 127) / 128) * ((a.Dw + bn2 - 1) / bn2);
+  const int64_t tiles2 = ((a.Dw + 127) / 128) * ((a.S + bn2 - 1) / bn2);
   const int64_t kb_total = (a.N + 63) / 64;
   int64_t splits = tiles2 >= sms ? 1 : sms / tiles2;
   const int64_t max_splits = (kb_total + 15) / 16;  // at least one full virtual tile per split
@@ -561,7 +583,8 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
   float* Gpart = (float*)(ws + p.o_Gpart);
   float* statpart = (float*)(ws + p.o_statpart);
   const int64_t Dp = p.gm_Dp, Sp = p.gm_Sp;
-  __nv_bfloat16* x1 = (__nv_bfloat16*)(ws + p.o_gm_x);
+  const bool prepared = a.x_planes != nullptr;  // bjx_prepare_x_planes output for exactly this X (caller's promise)
+  __nv_bfloat16* x1 = prepared ? (__nv_bfloat16*)a.x_planes : (__nv_bfloat16*)(ws + p.o_gm_x);
   __nv_bfloat16* x2 = x1 + (size_t)a.N * Dp;
   __nv_bfloat16* t1 = (__nv_bfloat16*)(ws + p.o_gm_t);
   __nv_bfloat16* t2 = t1 + (size_t)a.S * Dp;
@@ -569,17 +592,11 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
   __nv_bfloat16* g2 = g1 + (size_t)a.N * Sp;
 
   // operand planes
+  if (!prepared) {
+    int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, x1, st);
+    if (rc) return rc;
+  }
   {
-    const int64_t total = a.N * (Dp / 8);
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    if ((a.ldx % 4) == 0 && ((uintptr_t)a.X & 15) == 0) {
-      k_split_x<<<(unsigned)blocks, 256, 0, st>>>(a.X, a.ldx, a.N, a.Dw, Dp, x1, x2);
-    } else {
-      k_split_planes<2, SrcPlain><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(SrcPlain{a.X, a.ldx}, a.N, a.Dw, Dp, x1, x2, nullptr);
-    }
-    BJX_LAUNCH_CHECK("k_split_x");
     const int64_t tt = a.S * (Dp / 8);
     k_split_planes<2, SrcPlain><<<(unsigned)((tt + 255) / 256), 256, 0, st>>>(SrcPlain{theta + a.w_offset, a.D}, a.S, a.Dw, Dp, t1, t2, nullptr);
     BJX_LAUNCH_CHECK("k_split_planes(theta)");
@@ -617,18 +634,18 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     else rc = launch<256, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
     if (rc) return rc;
   }
-  // ---- pass 2: G[s, d] = sum_n g[n, s] X[n, d]
+  // ---- pass 2: G^T[d, s] = sum_n X[n, d] g[n, s]   (A = X planes, B = g planes, both MN-major; K = data rows)
   {
-    const int bn = lik2_bn(a.Dw);
+    const int bn = lik1_bn(a.S);
     Params P;
     memset(&P, 0, sizeof(P));
     int rc;
-    if ((rc = make_map(&P.mapA[0], g1, a.N, a.S, Sp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapA[1], g2, a.N, a.S, Sp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[0], x1, a.N, a.Dw, Dp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[1], x2, a.N, a.Dw, Dp, 64, 64))) return rc;
-    P.sched.tiles_m = (int)((a.S + 127) / 128);
-    P.sched.tiles_n = (int)((a.Dw + bn - 1) / bn);
+    if ((rc = make_map(&P.mapA[0], x1, a.N, a.Dw, Dp, 64, 64))) return rc;
+    if ((rc = make_map(&P.mapA[1], x2, a.N, a.Dw, Dp, 64, 64))) return rc;
+    if ((rc = make_map(&P.mapB[0], g1, a.N, a.S, Sp, 64, 64))) return rc;
+    if ((rc = make_map(&P.mapB[1], g2, a.N, a.S, Sp, 64, 64))) return rc;
+    P.sched.tiles_m = (int)((a.Dw + 127) / 128);
+    P.sched.tiles_n = (int)((a.S + bn - 1) / bn);
     P.sched.splits = p.gm_splits;
     P.sched.kb_total = (int)((a.N + 63) / 64);
     P.sched.kb_per_split = (P.sched.kb_total + p.gm_splits - 1) / p.gm_splits;
@@ -637,7 +654,8 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     P.epi.S = (int)a.S;
     P.epi.Gpart = Gpart;
     P.epi.Dw = a.Dw;
-    if (bn == 128) rc = launch<128, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
+    if (bn == 64) rc = launch<64, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
+    else if (bn == 128) rc = launch<128, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     else rc = launch<256, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     if (rc) return rc;
   }

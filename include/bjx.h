@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BJX_ABI_VERSION 1
+#define BJX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BJX_API __attribute__((visibility("default")))
@@ -143,6 +143,12 @@ typedef struct BjxElboArgs {
   /* scratch (device) */
   void* workspace;
   size_t workspace_bytes; /* >= bjx_elbo_workspace_bytes(args) */
+
+  /* optional (ABI 2): the dataset X pre-split into bf16 operand planes by bjx_prepare_x_planes, for the two-pass
+   * tcgen05 GEMM path.  X is a constant of the training loop (a closure constant of the reference's jitted scan,
+   * utils.py:22-31), so the split is done once per dataset instead of once per step.  NULL = split inside the step
+   * (into the workspace).  The caller promises the planes were made from exactly this X / N / Dw. */
+  const void* x_planes;
 } BjxElboArgs;
 
 /* ---- library ------------------------------------------------------------ */
@@ -170,6 +176,11 @@ BJX_API int bjx_elbo_step(const BjxElboArgs* args, void* stream);
  * device-resident, as they are for the reference (closure constants of the jitted scan, utils.py:22-31). */
 BJX_API int bjx_elbo_step_host(const BjxElboArgs* args, const uint32_t* key_host, const float* params_host, float* out_host,
                        void* stream);
+
+/* Dataset preparation for the two-pass tcgen05 GEMM path: X [N, ldx] fp32 -> two bf16 planes (x = x1 + x2 to 2^-17
+ * relative), each [N, round_up(Dw, 64)] row-major, back to back in `planes` (bjx_x_planes_bytes bytes, 16-byte aligned). */
+BJX_API size_t bjx_x_planes_bytes(int64_t N, int64_t Dw);
+BJX_API int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, void* stream);
 
 /* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = fused tcgen05 single pass
  * (split-bf16), 3 = coin toss, 4 = two-pass TMA-fed tcgen05 GEMM (split-bf16) */

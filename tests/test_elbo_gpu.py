@@ -272,6 +272,29 @@ def test_full_rank_contractions_on_the_tensor_cores(D, S, lik):
     assert np.all(np.triu(g, 1) == 0.0)
 
 
+def test_prepared_dataset_planes_match_the_in_step_split():
+    """The two-pass path with X pre-split once per dataset (bjx_prepare_x_planes, cached by the engine while the same
+    unmodified tensor is passed) is bit-identical to splitting inside every step; an in-place update of X invalidates the cache."""
+    from bijax_b200 import random as br
+    from bijax_b200.engine import ElboEngine
+
+    N, D, S = 3000, 192, 48
+    X, y = _device_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), kernel="tcgen05_gemm_two_pass")
+    warm = model._engine_for({})[0]
+    cold = ElboEngine(model.latents, model.likelihood_fn, kernel="tcgen05_gemm_two_pass", prepare_dataset=False)
+    loc, raw = torch.zeros(D, device=X.device), torch.full((D,), -2.0, device=X.device)
+    a = warm.step(br.PRNGKey(4), loc, raw, None, X, y, 1.0, S).clone()
+    b = cold.step(br.PRNGKey(4), loc, raw, None, X, y, 1.0, S).clone()
+    assert warm._planes is not None and cold._planes is None
+    assert torch.equal(a, b)
+    X.mul_(0.5)
+    a2 = warm.step(br.PRNGKey(4), loc, raw, None, X, y, 1.0, S).clone()
+    b2 = cold.step(br.PRNGKey(4), loc, raw, None, X, y, 1.0, S).clone()
+    assert torch.equal(a2, b2) and not torch.equal(a, a2)
+
+
 def _tc_engine(D, lik=None, precision="auto"):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     model, _ = C.build_pair(prior, {}, lik or lk.BernoulliLogits(), precision=precision)
