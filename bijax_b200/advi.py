@@ -57,7 +57,8 @@ class _ElboFunction(torch.autograd.Function):
 class ADVI:
     def __init__(self, prior: Dict[str, Any], *args, vi_type: str = "mean_field", rank: Optional[int] = None,
                  ordered_posterior_bijectors=None, bijector=None, log_likelihood_fn=None, likelihood_fn=None,
-                 prior_constraints=None, device=None, precision: str = "auto", kernel: Optional[str] = None):
+                 prior_constraints=None, device=None, precision: str = "auto", kernel: Optional[str] = None,
+                 prepare_dataset: bool = True):
         # positional forms: v1 (prior, bijector, log_likelihood_fn[, vi_type]); v2 (prior, likelihood_fn[, prior_constraints[, vi_type]])
         args = list(args)
         if args:
@@ -110,6 +111,7 @@ class ADVI:
         self.unravel_fn = self.latents.unravel
         self.device = device
         self.precision = precision
+        self.prepare_dataset = prepare_dataset  # keep X as split-bf16 operand planes, made once per dataset (engine.py)
         self.kernel = kernel  # None = the library picks the streaming kernel; a name from _native.KERNEL_NAMES forces one
         self._engines: Dict[Tuple, ElboEngine] = {}
         self._group = None  # torch.distributed process group for row-sharded data (see parallel.py)
@@ -153,7 +155,8 @@ class ADVI:
         sig = tuple(layout)
         if sig not in self._engines:
             self._engines[sig] = ElboEngine(self.latents, self.likelihood_fn, self.vi_type, self.posterior_params_bijector[1],
-                                            layout, device=self.device, precision=self.precision, kernel=self.kernel)
+                                            layout, device=self.device, precision=self.precision, kernel=self.kernel,
+                                            prepare_dataset=self.prepare_dataset)
         return self._engines[sig], leaves
 
     def distributed(self, group=None, global_len: Optional[int] = None):

@@ -506,6 +506,12 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   return BJX_OK;
 }
 
+}  // namespace gemm
+int make_bf16_tensor_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch, int box_cols, int box_rows) {
+  return gemm::make_map(m, base, rows, cols, pitch, box_cols, box_rows);
+}
+namespace gemm {
+
 template <int BN, int NT, bool A_MN, bool B_MN, int EPI>
 static int launch(const Params& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, NT>;

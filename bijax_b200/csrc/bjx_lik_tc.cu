@@ -19,6 +19,8 @@
 //               scoreboards between prefetch stages, which serialises them; depth comes from the number of warps.
 //   warp  16    MMA issuer (converged warp, elect.sync), owns the TMEM allocation
 //   warps 17-24 epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "bjx_elbo.cuh"
@@ -440,6 +442,335 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 #undef BJX_TRACE
 
 // =========================================================================================================================
+// The same single pass with the dataset held in HBM as split-bf16 planes (bjx_prepare_x_planes: x = x1 + x2, 4 bytes per
+// element like fp32): every 64 x 64 block of the tile is one TMA box per plane, written by the copy engine straight into
+// the swizzled UMMA image.  No loader warps, no registers in flight, no conversion and no generic-proxy stores or fences
+// on the shared-memory port: one producer thread, one MMA warp, eight epilogue warps (320 threads).
+namespace tcp {
+constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+struct Maps {
+  CUtensorMap x1, x2;
+};
+}  // namespace tcp
+
+template <int NBLK>  // D / 64
+__global__ void __launch_bounds__(tcp::THREADS, 1)
+k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
+             int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int S, int family,
+             float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
+             long long* __restrict__ trace) {
+#define BJX_TRACE(it_, slot_)                                                                 \
+  do {                                                                                        \
+    if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
+  } while (0)
+  using namespace tc;
+  constexpr int D = NBLK * BLK_COLS;
+  constexpr int NCH = NBLK / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx1 = smem;
+  uint8_t* sx2 = sx1 + NBLK * BLK_BYTES;
+  uint8_t* sth = sx2 + NBLK * BLK_BYTES;
+  uint8_t* sdl = sth + NBLK * BLK_BYTES;
+  Bars* bars = (Bars*)(sdl + BLK_BYTES);
+  float* sred = (float*)(bars + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int b = 0; b < 8; ++b) {
+      mbar_init(&bars->x_full[b], 1);  // the producer's expect_tx arrival; completion is counted in bytes
+      mbar_init(&bars->x_empty[b], 1);
+    }
+    mbar_init(&bars->acc1_full, 1);
+    mbar_init(&bars->dl_full, tcp::EPI_WARPS);
+    mbar_init(&bars->dl_empty, 1);
+    mbar_init(&bars->done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.x1);
+    tma_prefetch_desc(&maps.x2);
+  }
+  if (warp == tcp::MMA_WARP) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  for (int idx = tid; idx < NS * (D / 8); idx += tcp::THREADS) {
+    const int s = idx / (D / 8), d8 = idx % (D / 8);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = s < S ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
+    uint32_t p1[4], p2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], p1[j], p2[j]);
+    const int b = d8 / 8, c = d8 % 8;
+    uint8_t* blk = sth + b * BLK_BYTES;
+    *reinterpret_cast<uint4*>(blk + s * 128 + ((c ^ (s & 7)) << 4)) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    const int n2 = 32 + s;
+    *reinterpret_cast<uint4*>(blk + n2 * 128 + ((c ^ (n2 & 7)) << 4)) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == tcp::PROD_WARP) {
+    // ===================================================== TMA producer ================================================
+    const __nv_bfloat16* p1 = planes;
+    const __nv_bfloat16* p2 = planes + (size_t)N * D;
+    const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them, 2 per-lane line prefetch
+    const int pf_dist = pf_tiles & 255;
+    if (lane == 0) {
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
+        auto bulk_pf = [&]() {
+          // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
+          const int64_t rowp = (blockIdx.x + (it + pf_dist) * gridDim.x) * TILE_ROWS;
+          const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
+          const uint32_t bytes = (uint32_t)(rows * D * 2);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * D), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * D), "r"(bytes) : "memory");
+        };
+        if (pf_mode == 0 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
+        for (int b = 0; b < NBLK; ++b) {
+          mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
+          BJX_TRACE(it, b);
+          mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
+          tma_load_2d(sx1 + b * BLK_BYTES, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+          tma_load_2d(sx2 + b * BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+        }
+        if (pf_mode == 1 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
+      }
+    } else if (pf_mode == 2 && pf_dist > 0) {
+      // lanes 1..31: fire-and-forget line prefetches of a later tile, paced by the tile the MMA warp is consuming
+      for (int64_t it = 0; it + pf_dist < my_tiles; ++it) {
+        mbar_wait(&bars->x_full[0], (uint32_t)(it & 1));
+        const int64_t rowp = (blockIdx.x + (it + pf_dist) * gridDim.x) * TILE_ROWS;
+        const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
+        const int64_t lines = rows * D * 2 / 128;
+        const char* b1 = (const char*)(p1 + rowp * D);
+        const char* b2 = (const char*)(p2 + rowp * D);
+        for (int64_t l = lane - 1; l < lines; l += 31) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + l * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + l * 128));
+        }
+      }
+    }
+  } else if (warp == tcp::MMA_WARP) {
+    // ===================================================== MMA issuer ==================================================
+    constexpr uint32_t ID_G1_N64 = make_idesc(64, NB, 0, 0);
+    constexpr uint32_t ID_G1_N32 = make_idesc(64, NS, 0, 0);
+    constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);
+    constexpr uint32_t ID_G2_N32 = make_idesc(128, NS, 1, 1);
+    const uint64_t dx1 = make_desc(smem_u32(sx1), 16, 1024), dx2 = make_desc(smem_u32(sx2), 16, 1024);
+    const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
+    const uint64_t tx1 = make_desc(smem_u32(sx1), BLK_BYTES, 1024), tx2 = make_desc(smem_u32(sx2), BLK_BYTES, 1024);
+    const uint64_t tdl = make_desc(smem_u32(sdl), BLK_BYTES, 1024);
+    const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
+    int phase = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      for (int b = 0; b < NBLK; ++b) {
+        mbar_wait(&bars->x_full[b], ph);
+        if (lane == 0) BJX_TRACE(it, 16 + b);
+        if (!(ablate & 1) && elect_one()) {
+          const uint64_t boff = (uint64_t)((b * BLK_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + ACC1_COL, dx1 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N64, (b | k) != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dx2 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N32, 1);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bars->acc1_full);
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(it, 24);
+      mbar_wait(&bars->dl_full, ph);
+      tc_fence_after();
+      if (lane == 0) BJX_TRACE(it, 25);
+      for (int ch = 0; ch < NCH; ++ch) {
+        if (elect_one()) {
+          const uint64_t coff = (uint64_t)((2 * ch * BLK_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (ablate & 2) continue;
+            umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2,
+                      (k != 0) || !(it == 0 || phase == ch * flush_step));
+            umma_bf16(tmem + ACC2_COL + ch * NB, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
+          }
+          umma_commit(&bars->x_empty[2 * ch]);
+          umma_commit(&bars->x_empty[2 * ch + 1]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bars->dl_empty);
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(it, 26);
+      if (++phase == NCH * flush_step) phase = 0;
+    }
+    if (elect_one()) umma_commit(&bars->done);
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue =====================================================
+    const int q = warp & 3;
+    const int h = (warp - tcp::EPI_WARP0) >> 2;
+    const int hi = lane >> 4;
+    const int r = 16 * q + (lane & 15);
+    const int s0 = h * 16 + hi * 8;
+    float stat[8], prod[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      stat[j] = 0.0f;
+      prod[j] = 1.0f;
+    }
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
+    float* gp = Gpart + (size_t)blockIdx.x * S * D;
+    auto drain_chunk = [&](int ch, bool first) {
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+        const int sb = h * 16 + part * 8;
+        uint32_t fa[8], fb[8];
+        tmem_ld8(t_lane + ACC2_COL + ch * NB + sb, fa);
+        tmem_ld8(t_lane + ACC2_COL + ch * NB + NS + sb, fb);
+        float* base = gp + (size_t)sb * D + ch * 128 + 32 * q + lane;
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (sb + j < S) {
+            const float val = __uint_as_float(fa[j]) + __uint_as_float(fb[j]);
+            if (first)
+              __stcg(base + (size_t)j * D, val);
+            else
+              atomicAdd(base + (size_t)j * D, val);
+          }
+        }
+      }
+    };
+    const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
+    int phase = 0;
+    uint32_t flushed = 0;
+    int64_t row = (int64_t)blockIdx.x * TILE_ROWS + r;
+    float yv = (my_tiles > 0 && row < N) ? y[row] : 0.0f;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      if (it > 0 && phase % flush_step == 0 && phase / flush_step < NCH) {
+        const int ch = phase / flush_step;
+        mbar_wait(&bars->dl_empty, ph ^ 1);
+        tc_fence_after();
+        drain_chunk(ch, !((flushed >> ch) & 1u));
+        tc_fence_before();
+        flushed |= 1u << ch;
+      }
+      if (++phase == NCH * flush_step) phase = 0;
+      const bool row_ok = row < N;
+      const float ycur = yv;
+      // fetch the next tile's label now: its latency hides behind this tile's GEMM1
+      row += (int64_t)gridDim.x * TILE_ROWS;
+      yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
+      mbar_wait(&bars->acc1_full, ph);
+      tc_fence_after();
+      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
+      uint32_t va[16], vb[16];
+      tmem_ld16(t_lane + ACC1_COL + h * 16, va);
+      tmem_ld16(t_lane + ACC1_COL + NS + h * 16, vb);
+      tmem_ld_wait();
+      float eta[8], g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float lo = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+        const float up = __shfl_sync(0xffffffffu, __uint_as_float(va[8 + j]) + __uint_as_float(vb[8 + j]), lane & 15);
+        eta[j] = hi ? up : lo;
+      }
+      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
+      if (ablate & 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
+      } else if (logit) {
+        // one exponential per datum, stage by stage over the 8 values so that the MUFU latencies overlap
+        // The special-function pipe (16 lanes per clock per SM) bounds this stage, so only the exponential uses it:
+        // 1 / (1 + e) with 1 + e in (1, 2] is three Newton steps on the FMA pipe from the minimax line 24/17 - 8/17 x
+        // (relative error 1/17 -> 3.5e-3 -> 1.2e-5 -> 1.5e-10).
+        float e[8], ope[8], rc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = __expf(-fabsf(eta[j]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ope[j] = 1.0f + e[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rc[j] = fmaf(-0.47058824f, ope[j], 1.4117647f);
+#pragma unroll
+        for (int it2 = 0; it2 < 3; ++it2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rc[j] = fmaf(rc[j], fmaf(-ope[j], rc[j], 1.0f), rc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = row_ok && (s0 + j) < S;
+          stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
+          prod[j] *= ok ? ope[j] : 1.0f;
+          g[j] = ok ? (ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j])) : 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = row_ok && (s0 + j) < S;
+          const float rr = ycur - eta[j];
+          stat[j] += ok ? rr * rr : 0.0f;
+          g[j] = ok ? rr : 0.0f;
+        }
+      }
+      uint32_t e1[4], e2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
+      if ((it & 31) == 31) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          stat[j] -= logf(prod[j]);
+          prod[j] = 1.0f;
+        }
+      }
+      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 34);
+      mbar_wait(&bars->dl_empty, ph ^ 1);
+      {
+        uint8_t* rowp = sdl + r * 128;
+        const int sw = r & 7;
+        *reinterpret_cast<uint4*>(rowp + (((2 * h + hi) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + hi) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dl_full);
+      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 35);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = stat[j] - logf(prod[j]);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((lane & 15) == 0) sred[q * NS + s0 + j] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(tcp::EPI_WARPS * 32) : "memory");
+    if (warp == tcp::EPI_WARP0 && lane < S) {
+      statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+    }
+    mbar_wait(&bars->done, 0);
+    tc_fence_after();
+    if (my_tiles > 0) {
+      for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, !((flushed >> ch) & 1u));
+    } else {
+      for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * D; i += tcp::EPI_WARPS * 32) gp[i] = 0.0f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == tcp::MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+#undef BJX_TRACE
+}
+
+// =========================================================================================================================
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
 static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
 static int g_pf_mode = 0;            // 0 per-lane line prefetch by the loaders, 1 per-sector, 2 bulk prefetch by the MMA warp (BJX_TC_PFMODE)
@@ -488,6 +819,39 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   float* statpart = (float*)(ws + p.o_statpart);
   const int nblk = (int)(a.Dw / tc::BLK_COLS);
   const size_t smem = tc_smem_bytes(nblk);
+  if (a.x_planes != nullptr) {
+    // dataset prepared as split-bf16 planes: the TMA-fed variant
+    static int pf_tiles = -1;
+    if (pf_tiles < 0) {
+      const char* e = getenv("BJX_TC_PF_TILES");
+      pf_tiles = e ? atoi(e) : 257;  // low byte: distance in tiles; bits 8+: mode (see the producer warp); 257 = one tile ahead, issued after the tile's loads
+    }
+    tcp::Maps maps;
+    const __nv_bfloat16* planes = (const __nv_bfloat16*)a.x_planes;
+    int rc;
+    if ((rc = make_bf16_tensor_map(&maps.x1, planes, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * a.Dw, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
+#define BJX_TCP_LAUNCH(NBLK)                                                                                              \
+  do {                                                                                                                    \
+    static bool attr_set = false;                                                                                         \
+    if (!attr_set) {                                                                                                      \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      attr_set = true;                                                                                                    \
+    }                                                                                                                     \
+    k_lik_tc_tma<NBLK><<<p.tc_ctas, tcp::THREADS, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,    \
+                                                              a.likelihood, Gpart, statpart, pf_tiles, g_flush, g_ablate, g_trace); \
+  } while (0)
+    switch (nblk) {
+      case 2: BJX_TCP_LAUNCH(2); break;
+      case 4: BJX_TCP_LAUNCH(4); break;
+      case 6: BJX_TCP_LAUNCH(6); break;
+      case 8: BJX_TCP_LAUNCH(8); break;
+      default: return fail(BJX_ERR_UNSUPPORTED, "tcgen05 kernel needs D in {128, 256, 384, 512}");
+    }
+#undef BJX_TCP_LAUNCH
+    BJX_LAUNCH_CHECK("k_lik_tc_tma");
+    return BJX_OK;
+  }
 #define BJX_TC_LAUNCH(NBLK)                                                                                           \
   do {                                                                                                                \
     static bool attr_set = false;                                                                                     \

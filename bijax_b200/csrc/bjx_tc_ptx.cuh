@@ -3,7 +3,12 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+struct CUtensorMap_st;
+
 namespace bjx {
+// bf16 matrix [rows, pitch] row-major with logical width `cols`; box = box_cols x box_rows, 128-byte swizzle, zero OOB fill
+int make_bf16_tensor_map(CUtensorMap_st* m, const void* base, int64_t rows, int64_t cols, int64_t pitch, int box_cols, int box_rows);
+
 namespace tc {
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------

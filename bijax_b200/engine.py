@@ -140,7 +140,7 @@ class ElboEngine:
         """Device pointer of the prepared operand planes of X if this step takes the GEMM path, else None."""
         if not self.prepare_dataset or X is None:
             return None
-        if self.lib.bjx_elbo_kernel_choice(C.byref(a)) != nv.KERNEL_IDS["tcgen05_gemm_two_pass"]:
+        if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
             return None
         key = (X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()))
         if self._planes_key != key:
@@ -152,6 +152,13 @@ class ElboEngine:
                                                        nv.current_stream_ptr()))
             self._planes_key = key
         return self._planes.data_ptr()
+
+    def prepare(self, X, y, n_samples) -> bool:
+        """Prepare the dataset's operand planes now (otherwise the first step does it).  Returns True if this engine keeps
+        prepared planes for this problem, False if the selected kernel reads raw fp32 X."""
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        return self._x_planes(a, X) is not None
 
     def kernel_choice(self, S, N) -> str:
         a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)

@@ -21,13 +21,15 @@ torch.cuda.synchronize()
 nv.load().bjx_debug_set_trace_buffer(None)
 t = trace.cpu().numpy().reshape(8, 64)
 t0 = t[0, 0]
+if eng._planes is not None:
+    print("TMA-fed variant (prepared planes)")
 names = {**{b: f"ld wait_empty b{b}" for b in range(8)}, **{8 + b: f"ld stored b{b}" for b in range(8)},
          **{16 + b: f"mma x_full b{b}" for b in range(8)}, 24: "mma gemm1 issued+commit", 25: "mma dl_full", 26: "mma gemm2 issued",
          27: "mma x_full b0 (before tcgen05 fence)", **{40 + w: f"ld stored b0 quarter {w}" for w in range(4)},
          **{44 + w: f"ld stored b1 quarter {w}" for w in range(4)},
          48: "ld b4 loads issued", 49: "ld b4 data arrived",
          32: "epi acc1_full", 33: "epi tmem loaded", 34: "epi math done", 35: "epi dl stored"}
-for it in range(1, 4):
+for it in range(1, 3):
     ev = sorted((int(t[it, k] - t0), names[k]) for k in names if t[it, k])
     print(f"--- tile {16 + it} (tile period {int(t[it,0]-t[it-1,0])} cycles)")
     base = ev[0][0]

@@ -89,11 +89,12 @@ def oracle_likelihood(L):
     raise NotImplementedError
 
 
-def build_pair(prior, bijector, likelihood, vi_type="mean_field", scale_bijector=None, precision="auto", kernel=None):
+def build_pair(prior, bijector, likelihood, vi_type="mean_field", scale_bijector=None, precision="auto", kernel=None, prepare_dataset=True):
     opb = None
     if scale_bijector is not None:
         opb = [tfb.Identity(), scale_bijector]
-    model = bj.ADVI(prior, dict(bijector), likelihood, vi_type=vi_type, ordered_posterior_bijectors=opb, precision=precision, kernel=kernel)
+    model = bj.ADVI(prior, dict(bijector), likelihood, vi_type=vi_type, ordered_posterior_bijectors=opb, precision=precision, kernel=kernel,
+                    prepare_dataset=prepare_dataset)
     oprior = {k: oracle_prior(v) for k, v in prior.items()}
     obij = {k: oracle_bijector(v) for k, v in model.prior_constraints.items()}
     ref = R.ADVIRef(oprior, obij, oracle_likelihood(likelihood), vi_type,

@@ -213,16 +213,18 @@ def test_error_paths():
     [(64, 128, 32, "logit"), (1, 128, 32, "logit"), (65, 256, 16, "logit"), (1000, 512, 32, "logit"),
      (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss")],
 )
-def test_tensor_core_path(N, D, S, lik):
-    """config c3/c5 shape family on the tcgen05 kernel (bf16 split operands, fp32 accumulation in TMEM)."""
+@pytest.mark.parametrize("prepared", [True, False])
+def test_tensor_core_path(N, D, S, lik, prepared):
+    """config c3/c5 shape family on the fused tcgen05 kernel (bf16 split operands, fp32 accumulation in TMEM): the TMA-fed
+    variant over the dataset's prepared split-bf16 planes, and the register-converting variant over raw fp32 X."""
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     if lik == "logit":
         X, y = C.synth_logistic(N, D)
-        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="bf16x2")
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="bf16x2", prepare_dataset=prepared)
         kwargs = {}
     else:
         X, y = C.synth_linear(N, D)
-        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), precision="bf16x2")
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), precision="bf16x2", prepare_dataset=prepared)
         kwargs = {"log_noise_scale": np.float32(math.log(0.5))}
     loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
     raw = np.full(D, math.log(0.1), np.float32)
