@@ -164,7 +164,8 @@ def run_reference(args):
 
 def launches_per_step(kernel: str) -> int:
     # k_prologue + likelihood + k_reduce_partials + k_tail + k_scalars (mean field)
-    return {"tcgen05_bf16_split": 5, "fp32_smalld": 5, "fp32_tiled": 6, "coin": 4}[kernel]
+    # (two-pass GEMM path: + operand split of theta, pass 1, pass 2 instead of one likelihood launch)
+    return {"tcgen05_bf16_split": 5, "fp32_smalld": 5, "fp32_tiled": 6, "coin": 4, "tcgen05_gemm_two_pass": 7}[kernel]
 
 
 def run_ours(args):
@@ -320,9 +321,9 @@ def run_ours(args):
         traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture of this workload
         tp = ROOT / "profiles" / "r01_traffic.json"
         if tp.exists() and kernel == "tcgen05_bf16_split" and rows == N_C3:
-            traffic = json.loads(tp.read_text()).get("traffic_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get("k_lik_tc_tma<8>" if prepared else "k_lik_tc<8>", {}).get("traffic_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+                    "traffic": traffic, "kernel": kernel + (" (k_lik_tc_tma: TMA-fed, prepared planes)" if prepared and kernel == "tcgen05_bf16_split" else ""), "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             xs = X[: args.cpu_rows].cpu()
