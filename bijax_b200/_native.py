@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "bjx_elbo_step",
     "bjx_elbo_step_host",
     "bjx_elbo_kernel_choice",
+    "bjx_train_steps",
     "bjx_x_planes_bytes",
     "bjx_prepare_x_planes",
     "bjx_posterior_sample",
@@ -86,6 +87,7 @@ class BjxElboArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
         ("x_planes", C.c_void_p),
+        ("key_index", C.c_void_p),
     ]
 
 
@@ -127,6 +129,7 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step.argtypes = [C.POINTER(BjxElboArgs), vp]
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
+    lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
     lib.bjx_x_planes_bytes.argtypes = [i64, i64]
     lib.bjx_x_planes_bytes.restype = C.c_size_t
     lib.bjx_prepare_x_planes.argtypes = [vp, i64, i64, i64, vp, vp]

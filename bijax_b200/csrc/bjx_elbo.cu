@@ -214,7 +214,8 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
 // One thread per (s, d).  Mean field: draws eps, forms z = loc + sigma * eps.  Full rank: eps and z were produced by
 // k_eps / k_fullrank_z.  Then theta = b(z), and the per-coordinate pieces of q.log_prob - log p~ with d/dz.
 template <bool FULL>
-__global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ key, const float* __restrict__ loc,
+__global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ key, const int64_t* __restrict__ key_index,
+                                                  const float* __restrict__ loc,
                                                   const float* __restrict__ raw, const BjxCoord* __restrict__ coords,
                                                   int64_t S, int64_t D, int scale_bij, int layout,
                                                   float* __restrict__ eps_buf, const float* __restrict__ z_buf,
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
       const ScaleEval sc = eval_scale(raw[d * D + d], scale_bij);
       logsig = logf(fabsf(sc.sigma));
     } else {
-      const uint32_t bits = random_bits_at(key[0], key[1], (uint64_t)i, (uint64_t)total, layout);
+      const uint32_t* k = key_index ? key + 2 * (*key_index) : key;  // device-resident loop: key = keys[step counter]
+      const uint32_t bits = random_bits_at(k[0], k[1], (uint64_t)i, (uint64_t)total, layout);
       eps = bits_to_normal(bits);
       eps_buf[i] = eps;
       const float rho = raw[d];
@@ -256,10 +258,11 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
   if (threadIdx.x == 0) qp_part[blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(256) k_eps(const uint32_t* __restrict__ key, int64_t total, int layout,
-                                             float* __restrict__ eps) {
+__global__ void __launch_bounds__(256) k_eps(const uint32_t* __restrict__ key, const int64_t* __restrict__ key_index,
+                                             int64_t total, int layout, float* __restrict__ eps) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < total) eps[i] = bits_to_normal(random_bits_at(key[0], key[1], (uint64_t)i, (uint64_t)total, layout));
+  const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
+  if (i < total) eps[i] = bits_to_normal(random_bits_at(k[0], k[1], (uint64_t)i, (uint64_t)total, layout));
 }
 
 // ---- full-rank contractions (fp32 FFMA; S x D x D) -----------------------------------------------------------------
@@ -505,7 +508,7 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
   const int64_t probs_coord = (a.likelihood == BJX_LIK_BERNOULLI_PROBS && a.N > 0) ? a.w_offset : -1;
   const int64_t total = a.S * a.D;
   if (a.vi_type == BJX_VI_FULL_RANK) {
-    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, total, a.threefry_layout, eps);
+    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, total, a.threefry_layout, eps);
     BJX_LAUNCH_CHECK("k_eps");
     if (p.fr_tc) {
       int rc = launch_fullrank_z_tc(a, eps, z, ws + p.o_fr_tc, st);
@@ -515,11 +518,11 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
       k_fullrank_z<<<grid, 256, 0, st>>>(eps, a.raw_scale, a.loc, a.S, a.D, a.scale_bijector, z);
       BJX_LAUNCH_CHECK("k_fullrank_z");
     }
-    k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
+    k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                     a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
                                                     probs_coord, aux);
   } else {
-    k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
+    k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                      a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out,
                                                      probs_coord, aux);
   }
@@ -613,6 +616,29 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
   m[i] = mi;
   v[i] = vi;
   p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+// device-resident training loop: the step number lives on the device, so that a captured CUDA graph of whole training
+// steps (ELBO + gradient -> Adam -> bookkeeping) can be replayed without any per-replay update
+__global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                  const float* __restrict__ g, int64_t n, float lr, float b1, float b2,
+                                                  float eps, const int64_t* __restrict__ steps_done) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)(*steps_done + 1);
+  const float c1 = 1.0f - powf(b1, t), c2 = 1.0f - powf(b2, t);
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+__global__ void k_train_bump(int64_t* __restrict__ steps_done, const float* __restrict__ out, float* __restrict__ losses) {
+  const int64_t t = *steps_done;
+  if (losses) losses[t] = out[0];
+  *steps_done = t + 1;
 }
 
 }  // namespace bjx
@@ -711,6 +737,34 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
     } else {
       return fail(BJX_ERR_UNSUPPORTED, "z_out is only materialised for the full-rank family; invert the bijector instead");
     }
+  }
+  return BJX_OK;
+}
+
+int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
+                    float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr && params_flat && adam_m && adam_v && steps_done, "null pointer");
+  BJX_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
+  Plan p;
+  int rc = make_plan(*args, p);
+  if (rc) return rc;
+  BjxElboArgs a = *args;
+  a.loc = params_flat;
+  a.raw_scale = params_flat + a.D;
+  a.kwargs = a.K ? params_flat + a.D + p.Pn : nullptr;
+  a.key_index = steps_done;
+  rc = check_ptrs(a, p);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = a.D + p.Pn + a.K;
+  for (int64_t i = 0; i < n_steps; ++i) {
+    rc = run_step(a, p, st);
+    if (rc) return rc;
+    k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params_flat, adam_m, adam_v, a.out + 1, n, lr, b1, b2, eps, steps_done);
+    BJX_LAUNCH_CHECK("k_adam_dev");
+    k_train_bump<<<1, 1, 0, st>>>(steps_done, a.out, losses);
+    BJX_LAUNCH_CHECK("k_train_bump");
   }
   return BJX_OK;
 }

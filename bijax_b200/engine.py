@@ -216,6 +216,29 @@ class ElboEngine:
             )
         return out_host
 
+    def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
+                    n_samples, partitionable=None):
+        """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip
+        (bjx_train_steps; train_fn's scan body, utils.py:22-28).  ``keys`` is the [n, 2] uint32 array of per-step keys,
+        ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place."""
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, 1.0, brandom._layout(partitionable))
+        assert keys.dtype == torch.uint32 and keys.is_cuda and keys.is_contiguous()
+        assert params_flat.numel() == self.D + self.P + self.K and params_flat.is_contiguous()
+        a.key = keys.data_ptr()
+        a.X = X.data_ptr() if X is not None else None
+        a.y = y.data_ptr()
+        a.out = out.data_ptr()
+        a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
+        a.x_planes = self._x_planes(a, X)
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        lr, b1, b2, eps = hyper
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.bjx_train_steps(C.byref(a), int(n_steps), params_flat.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),
+                                              lr, b1, b2, eps, steps_done.data_ptr(), losses.data_ptr() if losses is not None else None,
+                                              nv.current_stream_ptr()))
+
     def posterior_sample(self, key, loc, raw_scale, n_samples, partitionable=None):
         """theta[S, D] = bijector(loc + scale * normal(key, (S, D)))  (Posterior.sample, core.py:46-55)."""
         dev = self.device

@@ -30,6 +30,14 @@ def sgd(learning_rate: float) -> GradientTransformation:
     return GradientTransformation(init, update)
 
 
+class AdamTransformation(NamedTuple):
+    """GradientTransformation that also names its hyper-parameters, so that train_fn can run the whole loop on the device."""
+
+    init: Any
+    update: Any
+    hyper: Any  # (learning_rate, b1, b2, eps)
+
+
 class AdamState(NamedTuple):
     count: int
     mu: Any
@@ -64,4 +72,4 @@ def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 
             ups.append(u)
         return tree_unflatten(td, ups), AdamState(count, state.mu, state.nu)
 
-    return GradientTransformation(init, update)
+    return AdamTransformation(init, update, (float(learning_rate), float(b1), float(b2), float(eps)))

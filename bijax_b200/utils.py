@@ -26,9 +26,103 @@ def value_and_grad(loss_fn: Callable) -> Callable:
     return fn
 
 
-def train_fn(loss_fn, params, optimizer, n_epochs, seed=None, return_args: Set[str] = frozenset()):
+GRAPH_STEPS = 16  # training steps per captured CUDA graph in the device-resident loop
+
+
+def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
+    """(model, call kwargs) if this train_fn call can run as the device-resident loop: loss_fn is
+    functools.partial(model.loss_fn, outputs=..., inputs=..., full_data_size=..., n_samples=...), the optimiser is
+    optim.adam, a seed is given, nothing per-step is asked back, and the model is not row-sharded."""
+    import functools
+
+    if seed is None or return_args or getattr(optimizer, "hyper", None) is None:
+        return None
+    if not isinstance(loss_fn, functools.partial) or loss_fn.args:
+        return None
+    model = getattr(loss_fn.func, "__self__", None)
+    if model is None or getattr(loss_fn.func, "__name__", "") != "loss_fn" or not hasattr(model, "_engine_for"):
+        return None
+    kw = dict(loss_fn.keywords)
+    if not {"outputs", "inputs", "full_data_size"} <= set(kw) or set(kw) - {"outputs", "inputs", "full_data_size", "n_samples"}:
+        return None
+    if getattr(model, "_group", None) is not None:
+        return None
+    return model, kw
+
+
+def _train_fused(model, kw, params, optimizer, n_epochs, seed):
+    """train_fn's scan (utils.py:22-31) resident on the device: bjx_train_steps captured in CUDA graphs of GRAPH_STEPS
+    steps; no per-step host work, no per-replay graph update (the step number lives on the device)."""
+    loc, raw, kwargs = model._split_params(params)
+    engine, kw_leaves = model._engine_for(kwargs)
+    dev = engine.device
+    f32 = lambda t: t.detach().to(dev, torch.float32).reshape(-1)
+    flat = torch.cat([f32(loc), f32(raw)] + [f32(l) for l in kw_leaves]).contiguous()
+    n_epochs = int(n_epochs)
+    keys = brandom.split(seed, max(n_epochs, 1)).contiguous()
+    outputs, inputs = kw["outputs"], kw["inputs"]
+    X = None
+    if engine.x_name is not None and inputs is not None:
+        X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
+    ll_scale = float(kw["full_data_size"]) / float(len(outputs))  # advi.py:92
+    S = int(kw.get("n_samples", 1))
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    done = torch.zeros(1, dtype=torch.int64, device=dev)
+    losses = torch.empty(max(n_epochs, 1), dtype=torch.float32, device=dev)
+    out = torch.empty(1 + flat.numel(), dtype=torch.float32, device=dev)
+
+    def enqueue(n, flat_, m_, v_, done_, losses_):
+        engine.train_steps(keys, n, flat_, m_, v_, optimizer.hyper, done_, losses_, out, X, outputs, ll_scale, S)
+
+    n_graphs, rest = divmod(n_epochs, GRAPH_STEPS)
+    if n_graphs >= 2:
+        # warm up on scratch state (first-use attribute calls, workspace and dataset preparation), then capture once
+        enqueue(1, flat.clone(), m.clone(), v.clone(), done.clone(), None)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                enqueue(GRAPH_STEPS, flat, m, v, done, losses)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        # capture does not execute: state is untouched, the counter is still 0
+        for _ in range(n_graphs):
+            graph.replay()
+    else:
+        rest = n_epochs
+    if rest:
+        enqueue(rest, flat, m, v, done, losses)
+    # back to the caller's pytree
+    D, P = engine.D, engine.P
+    key = next(k for k in ("posterior", "approx_posterior") if k in params)
+    post = params[key]
+    from .advi import _scale_key
+
+    new_post = {"loc": flat[:D].reshape(loc.shape), _scale_key(model.vi_type): flat[D : D + P].reshape(raw.shape)}
+    new_params = {key: new_post}
+    o = D + P
+    for name in sorted(kwargs):
+        ls, td = tree_flatten(kwargs[name])
+        nl = []
+        for l in ls:
+            nl.append(flat[o : o + l.numel()].reshape(l.shape))
+            o += l.numel()
+        new_params[name] = tree_unflatten(td, nl)
+    del post
+    return {"params": new_params, "losses": losses[:n_epochs]}
+
+
+def train_fn(loss_fn, params, optimizer, n_epochs, seed=None, return_args: Set[str] = frozenset(), fused: bool = True):
     """utils.py:6-36.  ``optimizer`` is optax-shaped (init / update).  Per-step keys are split(seed, n_epochs)[i] exactly
-    as the reference's lax.scan consumes them.  Losses stay on the device; nothing synchronises inside the loop."""
+    as the reference's lax.scan consumes them.  Losses stay on the device; nothing synchronises inside the loop.
+    When the call has the canonical shape (partial(model.loss_fn, ...) + optim.adam + seed) the whole loop runs on the
+    device (see _train_fused); ``fused=False`` forces the generic host-driven loop."""
+    spec = _fused_loop_spec(loss_fn, optimizer, seed, return_args) if fused else None
+    if spec is not None and isinstance(params, dict) and any(k in params for k in ("posterior", "approx_posterior")):
+        post = params[next(k for k in ("posterior", "approx_posterior") if k in params)]
+        if isinstance(post, dict):
+            return _train_fused(spec[0], spec[1], params, optimizer, n_epochs, seed)
     value_and_grad_fn = value_and_grad(loss_fn)
     state = optimizer.init(params)
     seeds = brandom.split(seed, n_epochs) if seed is not None else None

@@ -149,6 +149,10 @@ typedef struct BjxElboArgs {
    * utils.py:22-31), so the split is done once per dataset instead of once per step.  NULL = split inside the step
    * (into the workspace).  The caller promises the planes were made from exactly this X / N / Dw. */
   const void* x_planes;
+
+  /* optional (ABI 2): device-resident step counter.  When set, `key` is the base of a [n, 2] array of per-step keys
+   * (jax.random.split(seed, n_epochs), utils.py:30) and the step uses key[*key_index]; see bjx_train_steps. */
+  const int64_t* key_index;
 } BjxElboArgs;
 
 /* ---- library ------------------------------------------------------------ */
@@ -193,6 +197,17 @@ BJX_API int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, floa
 /* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27) */
 BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
                     float b2, float eps, void* stream);
+
+/* ---- the training loop of train_fn (utils.py:22-31) resident on the device -----------------------------------------
+ * Enqueues n_steps x { ELBO + gradients at key[*steps_done] -> Adam update of params_flat in place -> losses[*steps_done]
+ * = loss, ++*steps_done } with no host round trip; the sequence is CUDA-graph capturable and a captured graph can be
+ * replayed as is, because the step number (bias correction, key index, loss slot) lives in `steps_done` on the device.
+ * params_flat = [loc (D) | raw_scale (P) | kwargs (K)] (args->loc / raw_scale / kwargs are ignored), adam_m / adam_v the
+ * optax.adam moments (zero-initialised), args->key the [n, 2] key array, args->out the packed step output (scratch),
+ * losses (optional) at least as long as the total number of steps.  Single device: under row sharding run
+ * bjx_elbo_step + the all-reduce + bjx_adam_update from the host instead. */
+BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, float lr,
+                    float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream);
 
 /* ---- in-library timing of the dominant (streaming likelihood) kernel -------
  * bjx_profile_begin(capacity): from now on every bjx_elbo_step on this thread records a CUDA event pair around its

@@ -89,3 +89,42 @@ def test_posterior_sample_matches_prologue_arithmetic():
     z = loc + sig * eps
     assert np.allclose(s["a"].cpu().numpy().ravel(), np.exp(z[:, 0]), rtol=2e-6)
     assert np.allclose(s["b"].cpu().numpy().reshape(14, 3), z[:, 1:], rtol=2e-6, atol=1e-7)
+
+
+def test_device_resident_training_loop_matches_the_host_driven_loop():
+    """train_fn's scan (utils.py:22-31) as bjx_train_steps inside replayed CUDA graphs: same keys, same Adam, so the
+    trajectory must match the generic loop (value_and_grad -> optimizer.update -> apply_updates on the host) to float
+    rounding of the bias correction, and the graph-replayed loop must equal the eagerly enqueued one bit for bit."""
+    from bijax_b200 import random as br
+    from bijax_b200 import utils as U
+    from functools import partial
+    from tests import cases as C
+
+    N, D = 4096, 5
+    X, y = C.synth_linear(N, D, noise=0.1)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D), scale_diag=np.ones(D))}, {}, lk.GaussianLinear())
+
+    def fresh():
+        p = model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.01 * br.normal(k, shape))
+        p["log_noise_scale"] = torch.tensor(-1.0, device="cuda")
+        return p
+
+    loss_fn = partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=8)
+    n = 3 * U.GRAPH_STEPS + 5
+    fused = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
+    host = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3), fused=False)
+    assert fused["losses"].shape == host["losses"].shape == (n,)
+    assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-5)
+    for k in ("loc", "scale_diag"):
+        assert torch.allclose(fused["params"]["posterior"][k], host["params"]["posterior"][k], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(fused["params"]["log_noise_scale"], host["params"]["log_noise_scale"], rtol=1e-4, atol=1e-5)
+    assert fused["params"]["log_noise_scale"].shape == ()
+    old = U.GRAPH_STEPS
+    try:
+        U.GRAPH_STEPS = 10 ** 9  # no graph: everything enqueued eagerly
+        eager = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
+    finally:
+        U.GRAPH_STEPS = old
+    assert torch.equal(eager["losses"], fused["losses"])
+    assert torch.equal(eager["params"]["posterior"]["loc"], fused["params"]["posterior"]["loc"])
