@@ -83,17 +83,23 @@ out.append({"config": "c2 lin-reg D=5(+log_noise_scale) N=1M S=64", "kernel": en
             "likelihood_kernel_us": k_us, "cpu_us_per_step": cpu, "gflops_fp32_kernel": flops / k_us / 1e3, "bound": "fp32 FMA / L2 (X = 20 MB is L2-resident; not larger than L2)",
             "algorithmic_bytes": 4.0 * N * D + 4.0 * N, "gbs": (4.0 * N * D + 4.0 * N) / us / 1e3})
 
-# ---- c4 (reduced): full-rank linear regression, D=512 (instead of 2048), N=100k (instead of 1M), S=32 (instead of 256):
-# the full config is 2.15 PFLOP per step and outside the tcgen05 kernel's envelope (S <= 32, D <= 512) this round
-N, D, S = 100_000, 512, 32
-X = br.normal(br.PRNGKey(1234), (N, D), partitionable=True); X.mul_(1 / math.sqrt(D))
-w = br.normal(br.PRNGKey(1235), (D,), partitionable=True)
-yl = X @ w + 0.1 * br.normal(br.PRNGKey(1237), (N,), partitionable=True)
-m = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}, {}, lk.GaussianLinear(), vi_type="full_rank")
-eng, _ = m._engine_for({"log_noise_scale": lns})
-loc, M = torch.zeros(D, device=dev), 0.1 * torch.eye(D, device=dev)
-o = torch.empty(1 + D + D * D + 1, device=dev)
-us = time_gpu(lambda i: eng.step(keys[i], loc, M, lns, X, yl, 1.0, S, out=o), steps=50, warmup=5)
-out.append({"config": "c4 reduced: full-rank lin-reg D=512 N=100k S=32", "kernel": eng.kernel_choice(S, N), "gpu_us_per_step": us,
-            "note": "likelihood pass on tcgen05; L.eps and dM on fp32 FFMA tiles (tensor-core version is a next item)"})
+# ---- the training loop itself (train_fn, utils.py:22-31): ELBO + gradients + Adam per step, device-resident (CUDA graphs)
+from functools import partial
+from bijax_b200 import optim
+def time_train(model, params, loss_kw, n):
+    lf = partial(model.loss_fn, **loss_kw)
+    bj.train(lf, params, optim.adam(1e-3), n_epochs=64, seed=br.PRNGKey(5)); torch.cuda.synchronize()
+    t0 = time.perf_counter(); bj.train(lf, params, optim.adam(1e-3), n_epochs=n, seed=br.PRNGKey(5)); torch.cuda.synchronize()
+    fused = 1e6 * (time.perf_counter() - t0) / n
+    nh = max(n // 10, 50)
+    t0 = time.perf_counter(); bj.train(lf, params, optim.adam(1e-3), n_epochs=nh, seed=br.PRNGKey(5), fused=False); torch.cuda.synchronize()
+    return fused, 1e6 * (time.perf_counter() - t0) / nh
+m1 = bj.ADVI({"p_of_heads": tfd.Beta(0.5, 0.5)}, {"p_of_heads": tfb.Sigmoid()}, lk.BernoulliProbs("p_of_heads"))
+f1, h1 = time_train(m1, m1.init(br.PRNGKey(0)), dict(outputs=y, inputs=None, full_data_size=100, n_samples=16), 4000)
+out.append({"config": "c1 training loop (step + Adam), 4000 epochs", "fused_loop_us_per_epoch": f1, "host_driven_loop_us_per_epoch": h1})
+m2 = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}, {}, lk.GaussianLinear())
+p2 = m2.init(br.PRNGKey(0)); p2["log_noise_scale"] = torch.tensor(math.log(0.1), device=dev)
+f2, h2 = time_train(m2, p2, dict(outputs=yl, inputs={"X": X}, full_data_size=N, n_samples=S), 2000)
+out.append({"config": "c2 training loop (step + Adam), 2000 epochs", "fused_loop_us_per_epoch": f2, "host_driven_loop_us_per_epoch": h2})
+# c4 at full size: scripts/bench_c4.py
 print(json.dumps({"cores": os.cpu_count(), "results": out}, indent=1))
