@@ -1,7 +1,7 @@
 """Posterior access (bijax/core.py:39-75): what ``ADVI.apply(params)`` returns.
 
-``sample`` runs on the fused CUDA prologue (threefry -> z -> bijector); ``log_prob`` is post-training, off the per-step
-path, and is expressed with torch ops on the device.
+``sample`` runs on the fused CUDA prologue (threefry -> z -> bijector); ``log_prob`` is one fused kernel
+(bjx_posterior_log_prob: inverse bijector chains, log-det-Jacobians, diagonal or triangular-solve Gaussian log density).
 """
 from __future__ import annotations
 
@@ -11,37 +11,7 @@ from typing import Dict
 import torch
 
 from . import _native as nv
-from .spec import bijector_ops, flatten_tree, is_distribution
-
-_HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
-
-
-def _inverse_and_fldj(y: torch.Tensor, ops):
-    """z = b^{-1}(y) and fldj_b(z) for ops given in application order."""
-    sp = torch.nn.functional.softplus
-    xs = y
-    for op in reversed(ops):
-        if op == nv.BIJ_EXP:
-            xs = torch.log(xs)
-        elif op == nv.BIJ_SOFTPLUS:
-            xs = xs + torch.log(-torch.expm1(-xs))
-        elif op == nv.BIJ_SIGMOID:
-            xs = torch.log(xs) - torch.log1p(-xs)
-    z = xs
-    fldj = torch.zeros_like(z)
-    x = z
-    for op in ops:
-        if op == nv.BIJ_EXP:
-            fldj = fldj + x
-            x = torch.exp(x)
-        elif op == nv.BIJ_SOFTPLUS:
-            fldj = fldj - sp(-x)
-            x = sp(x)
-        elif op == nv.BIJ_SIGMOID:
-            fldj = fldj - sp(-x) - sp(x)
-            x = torch.sigmoid(x)
-    return z, fldj
-
+from .spec import flatten_tree
 
 class Posterior:
     def __init__(self, model, engine, loc: torch.Tensor, raw_scale: torch.Tensor):
@@ -62,30 +32,20 @@ class Posterior:
         return self.model.latents.unravel(theta.reshape(*shape, self.model.size))
 
     def log_prob(self, sample: Dict, sample_shape=()):
-        """core.py:57-71: q(z = b^{-1}(theta)) + sum inverse_log_det_jacobian(theta)."""
+        """core.py:57-71: q(z = b^{-1}(theta)) + sum inverse_log_det_jacobian(theta), one fused kernel over the flattened
+        samples (bjx_posterior_log_prob: inverse bijector chains, triangular solve for the full-rank family)."""
         lat = self.model.latents
         dev = self.engine.device
-        zs, ildj = [], 0.0
         leaves = dict(flatten_tree(sample, lambda x: isinstance(x, torch.Tensor)))
-        bij = dict(flatten_tree(self.model.prior_constraints, lambda x: not isinstance(x, dict)))
         nb = len(tuple(sample_shape) if not isinstance(sample_shape, int) else (sample_shape,))
-        for path, shp in zip(lat.paths, lat.shapes):
+        cols, batch = [], ()
+        for path in lat.paths:
             y = leaves[path].to(dev, torch.float32)
-            batch = y.shape[:nb]
-            z, fldj = _inverse_and_fldj(y.reshape(*batch, -1), bijector_ops(bij[path]))
-            zs.append(z)
-            ildj = ildj - fldj.sum(-1)
-        z = torch.cat(zs, dim=-1)
-        loc = self.loc.to(dev, torch.float32)
-        sc = self._scale()
-        if self.model.vi_type == "mean_field":
-            zz = (z - loc) / sc
-            q = (-0.5 * zz * zz - torch.log(sc) - _HALF_LOG_2PI).sum(-1)
-        else:
-            diff = (z - loc).reshape(-1, z.shape[-1]).T
-            zz = torch.linalg.solve_triangular(sc, diff, upper=False).T.reshape(z.shape)
-            q = -0.5 * (zz * zz).sum(-1) - torch.log(torch.abs(torch.diagonal(sc))).sum() - z.shape[-1] * _HALF_LOG_2PI
-        return q + ildj
+            batch = tuple(y.shape[:nb])
+            cols.append(y.reshape(*batch, -1))
+        theta = torch.cat(cols, dim=-1).reshape(-1, self.model.size)
+        out = self.engine.posterior_log_prob(theta, self.loc, self.raw_scale)
+        return out.reshape(batch)
 
     def prob(self, sample, sample_shape=()):
         return torch.exp(self.log_prob(sample, sample_shape))

@@ -216,6 +216,19 @@ class ElboEngine:
             )
         return out_host
 
+    def posterior_log_prob(self, theta: torch.Tensor, loc, raw_scale) -> torch.Tensor:
+        """log q(theta_i) for constrained samples theta [n, D] in the flat latent layout (Posterior.log_prob, core.py:57-71)."""
+        dev = self.device
+        theta = self._f32(theta, dev).reshape(-1, self.D)
+        loc = self._f32(loc, dev).reshape(-1)
+        raw = self._f32(raw_scale, dev).reshape(-1)
+        a = self._args(1, 0, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        a.loc, a.raw_scale = loc.data_ptr(), raw.data_ptr()
+        out = torch.empty(theta.shape[0], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nv.check(self.lib.bjx_posterior_log_prob(C.byref(a), theta.data_ptr(), theta.shape[0], out.data_ptr(), nv.current_stream_ptr()))
+        return out
+
     def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
                     n_samples, partitionable=None):
         """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip

@@ -193,6 +193,9 @@ BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
 /* ---- posterior access (.apply -> Posterior.sample / log_prob, core.py:39-75) */
 /* theta[S, D] = bijector(loc + scale * eps) for eps = normal(key, (S, D)); z_out optional */
 BJX_API int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out, void* stream);
+/* out[i] = log q(theta_i) = q.log_prob(b^{-1}(theta_i)) + sum inverse_log_det_jacobian(theta_i)   (core.py:57-71) for n
+ * constrained samples theta [n, D] in the flat latent layout; uses args->D, vi_type, scale_bijector, loc, raw_scale, coords */
+BJX_API int bjx_posterior_log_prob(const BjxElboArgs* args, const float* theta, int64_t n, float* out, void* stream);
 
 /* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27) */
 BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,

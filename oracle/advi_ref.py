@@ -272,6 +272,29 @@ class ADVIRef:
 
         return torch.stack([loss_no_batch(samples[s]) for s in range(samples.shape[0])]).mean()
 
+    def posterior_log_prob(self, loc, raw_scale, sample: Dict[str, torch.Tensor]):
+        """Posterior.log_prob (core.py:57-71) for ONE constrained sample tree: inverse-transform every leaf
+        (inverse_transform_tree), ravel, q.log_prob of the fitted Gaussian, plus the sum of inverse_log_det_jacobian
+        (= -fldj at the pre-image)."""
+        zs, ildj = [], 0.0
+        for k in self.names:
+            b = self.bijector[k]
+            th = torch.as_tensor(sample[k], dtype=loc.dtype).reshape(-1)
+            z = b.inverse(th)
+            zs.append(z)
+            ildj = ildj - b.fldj(z).sum()
+        z = torch.cat(zs)
+        D = self.size
+        if self.vi_type == "mean_field":
+            sigma = self.scale_bijector.forward(raw_scale)
+            zz = (z - loc) / sigma
+            q = (-0.5 * zz * zz - torch.log(sigma)).sum() - 0.5 * D * LOG_2PI
+        else:
+            tril = torch.tril(self.scale_bijector.forward(raw_scale))
+            zz = torch.linalg.solve_triangular(tril, (z - loc)[:, None], upper=False)[:, 0]
+            q = -0.5 * (zz * zz).sum() - torch.log(torch.abs(torch.diagonal(tril))).sum() - 0.5 * D * LOG_2PI
+        return q + ildj
+
     def value_and_grad(self, loc, raw_scale, kwargs, outputs, inputs, full_data_size, eps):
         """jax.value_and_grad(loss_fn) (utils.py:7): returns loss, dloc, draw_scale, {dkwargs}."""
         loc = loc.detach().clone().requires_grad_(True)

@@ -127,3 +127,23 @@ def test_coin_toss_loss_is_bounded_by_the_log_evidence():
     # the exact posterior Beta(5,4) pushed through logit is close to N(0.24, 0.68): the bound must be near-tight there
     loss = m.loss(torch.tensor([0.24], dtype=torch.float64), torch.log(torch.tensor([0.68], dtype=torch.float64)), {}, y, None, 6, eps)
     assert 4.9416 - 0.02 < loss.item() < 5.0
+
+
+def test_oracle_posterior_log_prob_is_the_logit_normal_density():
+    """core.py:57-71 restated: for one Sigmoid-constrained latent the fitted posterior is logit-normal,
+    log q(p) = Normal(logit p; m, s).log_prob - log(p (1 - p))."""
+    import math
+
+    import torch
+
+    from oracle import advi_ref as R
+
+    ref = R.ADVIRef({"p": R.Beta(0.5, 0.5)}, {"p": R.Sigmoid()}, R.bernoulli_probs_loglik("p"))
+    m, rho = 0.3, -0.4
+    s = math.exp(rho)
+    for p in (0.1, 0.5, 0.83):
+        got = ref.posterior_log_prob(torch.tensor([m], dtype=torch.float64), torch.tensor([rho], dtype=torch.float64),
+                                     {"p": torch.tensor(p, dtype=torch.float64)}).item()
+        z = math.log(p / (1 - p))
+        want = -0.5 * ((z - m) / s) ** 2 - math.log(s) - 0.5 * math.log(2 * math.pi) - math.log(p * (1 - p))
+        assert abs(got - want) < 1e-12
