@@ -43,6 +43,8 @@ EXPORTED_SYMBOLS = (
     "bjx_prepare_x_planes",
     "bjx_posterior_sample",
     "bjx_posterior_log_prob",
+    "bjx_fill_triangular",
+    "bjx_fill_triangular_vjp",
     "bjx_adam_update",
     "bjx_profile_begin",
     "bjx_profile_collect",
@@ -136,6 +138,8 @@ def load() -> C.CDLL:
     lib.bjx_prepare_x_planes.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.bjx_posterior_sample.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp]
     lib.bjx_posterior_log_prob.argtypes = [C.POINTER(BjxElboArgs), vp, i64, vp, vp]
+    lib.bjx_fill_triangular.argtypes = [vp, i64, vp, vp]
+    lib.bjx_fill_triangular_vjp.argtypes = [vp, i64, vp, vp]
     lib.bjx_adam_update.argtypes = [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, vp]
     lib.bjx_profile_begin.argtypes = [i32]
     lib.bjx_profile_collect.argtypes = [vp, i32, vp]

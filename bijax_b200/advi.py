@@ -54,11 +54,42 @@ class _ElboFunction(torch.autograd.Function):
         return d_loc, d_raw, d_kw, None
 
 
+class _FillTriangular(torch.autograd.Function):
+    """packed [D(D+1)/2] -> dense lower-triangular [D, D] in tfp.math.fill_triangular order (bjx_fill_triangular)."""
+
+    @staticmethod
+    def forward(ctx, packed, D):
+        packed = packed.detach().to(torch.float32).contiguous()
+        dense = torch.empty((D, D), dtype=torch.float32, device=packed.device)
+        with torch.cuda.device(packed.device):
+            nv.check(nv.load().bjx_fill_triangular(packed.data_ptr(), D, dense.data_ptr(), nv.current_stream_ptr()))
+        ctx.D = D
+        return dense
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.to(torch.float32).contiguous()
+        D = ctx.D
+        out = torch.empty(D * (D + 1) // 2, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            nv.check(nv.load().bjx_fill_triangular_vjp(g.data_ptr(), D, out.data_ptr(), nv.current_stream_ptr()))
+        return out, None
+
+
+def fill_triangular(packed: torch.Tensor) -> torch.Tensor:
+    """tfp.math.fill_triangular(x) (lower) on the device, differentiable."""
+    m = packed.numel()
+    D = int((math.sqrt(8 * m + 1) - 1) / 2)
+    if D * (D + 1) // 2 != m:
+        raise ValueError(f"{m} is not a triangular number")
+    return _FillTriangular.apply(packed.reshape(-1), D)
+
+
 class ADVI:
     def __init__(self, prior: Dict[str, Any], *args, vi_type: str = "mean_field", rank: Optional[int] = None,
                  ordered_posterior_bijectors=None, bijector=None, log_likelihood_fn=None, likelihood_fn=None,
                  prior_constraints=None, device=None, precision: str = "auto", kernel: Optional[str] = None,
-                 prepare_dataset: bool = True):
+                 prepare_dataset: bool = True, packed_tril: bool = False):
         # positional forms: v1 (prior, bijector, log_likelihood_fn[, vi_type]); v2 (prior, likelihood_fn[, prior_constraints[, vi_type]])
         args = list(args)
         if args:
@@ -112,6 +143,11 @@ class ADVI:
         self.device = device
         self.precision = precision
         self.prepare_dataset = prepare_dataset  # keep X as split-bf16 operand planes, made once per dataset (engine.py)
+        # extension (north_star item 2): full-rank scale_tril held as a packed D(D+1)/2 vector, L = fill_triangular(packed);
+        # the reference's own parameterisation is the dense D x D raw matrix (core.py:205-209), which stays the default
+        self.packed_tril = bool(packed_tril)
+        if self.packed_tril and vi_type != "full_rank":
+            raise ValueError("packed_tril applies to vi_type='full_rank' only")
         self.kernel = kernel  # None = the library picks the streaming kernel; a name from _native.KERNEL_NAMES forces one
         self._engines: Dict[Tuple, ElboEngine] = {}
         self._group = None  # torch.distributed process group for row-sharded data (see parallel.py)
@@ -121,9 +157,9 @@ class ADVI:
     def init(self, seed, initializer: Optional[Callable] = None):
         """advi.py:77-78: raw params = initializer(seed, (P,)), default normal(stddev=1), unraveled in (loc, scale) order."""
         D = self.size
-        P = D if self.vi_type == "mean_field" else D * D
+        P = D if self.vi_type == "mean_field" else (D * (D + 1) // 2 if self.packed_tril else D * D)
         flat = brandom.normal(seed, (D + P,)) if initializer is None else initializer(seed, (D + P,))
-        scale = flat[D:].reshape((D,) if self.vi_type == "mean_field" else (D, D))
+        scale = flat[D:].reshape((P,) if (self.vi_type == "mean_field" or self.packed_tril) else (D, D))
         return {"posterior": {"loc": flat[:D].clone(), _scale_key(self.vi_type): scale.clone()}}
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -141,6 +177,8 @@ class ADVI:
             if raw is None:
                 raw = getattr(post, "scale_tril")
         kwargs = {k: v for k, v in params.items() if k != key}
+        if self.packed_tril:
+            raw = fill_triangular(raw)  # differentiable: gradients come back in the packed layout
         return loc, raw, kwargs
 
     def _engine_for(self, kwargs) -> Tuple[ElboEngine, list]:
@@ -212,7 +250,13 @@ class ADVI:
         out = self._run(engine, seed, outputs, inputs, full_data_size, n_samples)(loc.detach(), raw.detach(), kw)
         D, P = engine.D, engine.P
         key = next(k for k in _POSTERIOR_KEYS if k in params)
-        grads: Dict[str, Any] = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), _scale_key(self.vi_type): out[1 + D : 1 + D + P].reshape(raw.shape)}}
+        d_raw = out[1 + D : 1 + D + P].reshape(raw.shape)
+        if self.packed_tril:  # gather the dense gradient back into the packed layout (VJP of fill_triangular)
+            packed = torch.empty(D * (D + 1) // 2, dtype=torch.float32, device=out.device)
+            with torch.cuda.device(out.device):
+                nv.check(nv.load().bjx_fill_triangular_vjp(d_raw.contiguous().data_ptr(), D, packed.data_ptr(), nv.current_stream_ptr()))
+            d_raw = packed
+        grads: Dict[str, Any] = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), _scale_key(self.vi_type): d_raw}}
         o = 1 + D + P
         for n in sorted(kwargs):
             ls, td = tree_flatten(kwargs[n])

@@ -117,7 +117,46 @@ __global__ void __launch_bounds__(256) k_post_logprob_fr(const float* __restrict
   if (tid == 0) out[s] = tot;
 }
 
+// tfp.math.fill_triangular (lower): the D x D matrix is reshape(concat(x[D:], reverse(x)), (D, D)) with the strict upper
+// triangle zeroed; element (i, j), j <= i, therefore comes from x[src] with k = i*D + j, m = D(D+1)/2:
+//     src = D + k            if k < m - D        else        src = m - 1 - (k - (m - D))
+__device__ __forceinline__ int64_t fill_tril_src(int64_t i, int64_t j, int64_t D) {
+  const int64_t m = D * (D + 1) / 2, k = i * D + j;
+  return k < m - D ? D + k : m - 1 - (k - (m - D));
+}
+
+__global__ void __launch_bounds__(256) k_fill_tril(const float* __restrict__ packed, int64_t D, float* __restrict__ dense) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= D * D) return;
+  const int64_t i = idx / D, j = idx % D;
+  dense[idx] = j <= i ? packed[fill_tril_src(i, j, D)] : 0.0f;
+}
+
+// VJP: every packed entry appears exactly once in the lower triangle
+__global__ void __launch_bounds__(256) k_fill_tril_vjp(const float* __restrict__ d_dense, int64_t D, float* __restrict__ d_packed) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= D * D) return;
+  const int64_t i = idx / D, j = idx % D;
+  if (j <= i) d_packed[fill_tril_src(i, j, D)] = d_dense[idx];
+}
+
 }  // namespace bjx
+
+extern "C" int bjx_fill_triangular(const float* packed, int64_t D, float* dense, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(packed && dense && D >= 1 && D < (1ll << 30), "bad arguments");
+  k_fill_tril<<<(unsigned)((D * D + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, D, dense);
+  BJX_LAUNCH_CHECK("k_fill_tril");
+  return BJX_OK;
+}
+
+extern "C" int bjx_fill_triangular_vjp(const float* d_dense, int64_t D, float* d_packed, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(d_dense && d_packed && D >= 1 && D < (1ll << 30), "bad arguments");
+  k_fill_tril_vjp<<<(unsigned)((D * D + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dense, D, d_packed);
+  BJX_LAUNCH_CHECK("k_fill_tril_vjp");
+  return BJX_OK;
+}
 
 extern "C" int bjx_posterior_log_prob(const BjxElboArgs* args, const float* theta, int64_t n, float* out, void* stream) {
   using namespace bjx;

@@ -197,6 +197,13 @@ BJX_API int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, floa
  * constrained samples theta [n, D] in the flat latent layout; uses args->D, vi_type, scale_bijector, loc, raw_scale, coords */
 BJX_API int bjx_posterior_log_prob(const BjxElboArgs* args, const float* theta, int64_t n, float* out, void* stream);
 
+/* ---- packed full-rank parameterisation (north_star item 2: "L built by fill-triangular") ------------------------------
+ * dense [D, D] = tfp.math.fill_triangular(packed [D(D+1)/2]) (lower; strict upper triangle = 0), and its VJP
+ * d_packed = gather of d_dense over the lower triangle.  The reference itself keeps a dense D x D raw scale_tril
+ * (core.py:205-209); the packed form is an extension of the host layer (ADVI(..., packed_tril=True)). */
+BJX_API int bjx_fill_triangular(const float* packed, int64_t D, float* dense, void* stream);
+BJX_API int bjx_fill_triangular_vjp(const float* d_dense, int64_t D, float* d_packed, void* stream);
+
 /* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27) */
 BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
                     float b2, float eps, void* stream);

@@ -297,6 +297,63 @@ def test_prepared_dataset_planes_match_the_in_step_split():
     assert torch.equal(a2, b2) and not torch.equal(a, a2)
 
 
+def _np_fill_triangular(x):
+    """tfp.math.fill_triangular(x, upper=False) restated in NumPy (documented example: [1..6] -> [[4,0,0],[6,5,0],[3,2,1]])."""
+    m = x.shape[-1]
+    n = int((math.sqrt(8 * m + 1) - 1) / 2)
+    full = np.concatenate([x[n:], x[::-1]]).reshape(n, n)
+    return np.tril(full)
+
+
+def test_packed_fill_triangular_parameterisation():
+    """north_star item 2: L = fill_triangular(packed).  The packed model must give the dense model's loss and d loc, and
+    a d packed that is the gather of the dense gradient over the lower triangle, through both gradient routes."""
+    from bijax_b200 import random as br
+    from bijax_b200.advi import fill_triangular
+
+    assert np.array_equal(_np_fill_triangular(np.arange(1.0, 7.0)), np.array([[4, 0, 0], [6, 5, 0], [3, 2, 1]], float))
+    dev = torch.device("cuda")
+    got = fill_triangular(torch.arange(1.0, 7.0, device=dev)).cpu().numpy()
+    assert np.array_equal(got, np.array([[4, 0, 0], [6, 5, 0], [3, 2, 1]], np.float32))
+    D, N, S = 33, 400, 6
+    X, y = C.synth_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    dense_model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), vi_type="full_rank")
+    import bijax_b200 as bj
+
+    packed_model = bj.ADVI(prior, {}, lk.BernoulliLogits(), vi_type="full_rank", packed_tril=True)
+    m = D * (D + 1) // 2
+    p0 = packed_model.init(br.PRNGKey(4))
+    assert p0["posterior"]["scale_tril"].shape == (m,)
+    packed = (0.05 * tf.normal(tf.prng_key(8), (m,), 1)).astype(np.float32)
+    dense = _np_fill_triangular(packed).astype(np.float32)
+    assert np.array_equal(fill_triangular(torch.tensor(packed, device=dev)).cpu().numpy(), dense)
+    loc = (0.1 * tf.normal(tf.prng_key(6), (D,), 1)).astype(np.float32)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    pd = {"posterior": {"loc": torch.tensor(loc, device=dev), "scale_tril": torch.tensor(dense + np.eye(D, dtype=np.float32), device=dev)}}
+    # same matrix in packed form: add the identity through the packed entries that land on the diagonal
+    eye_packed = np.zeros(m, np.float32)
+    for i in range(D):
+        k = i * D + i
+        eye_packed[D + k if k < m - D else m - 1 - (k - (m - D))] = 1.0
+    pp = {"posterior": {"loc": torch.tensor(loc, device=dev), "scale_tril": torch.tensor(packed + eye_packed, device=dev)}}
+    ld, gd = dense_model.value_and_grad(pd, yd, {"X": Xd}, N, br.PRNGKey(2), S)
+    lp, gp = packed_model.value_and_grad(pp, yd, {"X": Xd}, N, br.PRNGKey(2), S)
+    assert ld.item() == lp.item()
+    assert torch.equal(gd["posterior"]["loc"], gp["posterior"]["loc"])
+    gdn = gd["posterior"]["scale_tril"].cpu().numpy()
+    want = np.zeros(m, np.float32)
+    for i in range(D):
+        for j in range(i + 1):
+            k = i * D + j
+            want[D + k if k < m - D else m - 1 - (k - (m - D))] = gdn[i, j]
+    assert np.array_equal(gp["posterior"]["scale_tril"].cpu().numpy(), want)
+    # autograd route
+    q = {"posterior": {k: v.clone().requires_grad_(True) for k, v in pp["posterior"].items()}}
+    packed_model.loss_fn(q, yd, {"X": Xd}, N, br.PRNGKey(2), S).backward()
+    assert torch.equal(q["posterior"]["scale_tril"].grad, gp["posterior"]["scale_tril"])
+
+
 def _tc_engine(D, lik=None, precision="auto"):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     model, _ = C.build_pair(prior, {}, lik or lk.BernoulliLogits(), precision=precision)
