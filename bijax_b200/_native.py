@@ -91,6 +91,10 @@ class BjxElboArgs(C.Structure):
         ("workspace_bytes", C.c_size_t),
         ("x_planes", C.c_void_p),
         ("key_index", C.c_void_p),
+        ("S_total", C.c_int64),
+        ("s_offset", C.c_int64),
+        ("entropy_weight", C.c_float),
+        ("reserved2", C.c_float),
     ]
 
 

@@ -197,13 +197,17 @@ class ADVI:
                                             prepare_dataset=self.prepare_dataset)
         return self._engines[sig], leaves
 
-    def distributed(self, group=None, global_len: Optional[int] = None):
-        """Row-sharded data parallelism: ``outputs`` / ``inputs`` passed to loss_fn are this rank's shard; one all-reduce
-        of the packed [loss | grads] buffer per step."""
+    def distributed(self, group=None, global_len: Optional[int] = None, shard: str = "rows"):
+        """Data parallelism with one all-reduce of the packed [loss | grads] buffer per step.
+        ``shard="rows"``: ``outputs`` / ``inputs`` passed to loss_fn are this rank's row shard.  ``shard="samples"`` (for
+        small N): every rank passes the full data and evaluates its block of the ``n_samples`` Monte-Carlo samples."""
         import torch.distributed as dist
 
+        if shard not in ("rows", "samples"):
+            raise ValueError("shard must be 'rows' or 'samples'")
         self._group = group if group is not None else dist.group.WORLD
         self._global_len = global_len
+        self._shard = shard
         return self
 
     def _run(self, engine, seed, outputs, inputs, full_data_size, n_samples):
@@ -213,7 +217,17 @@ class ADVI:
         n_local = len(outputs)
         prior_weight = 1.0
         n_global = n_local
-        if self._group is not None:
+        sample_shard = None
+        if self._group is not None and getattr(self, "_shard", "rows") == "samples":
+            import torch.distributed as dist
+
+            from . import parallel as par
+
+            rank, world = dist.get_rank(self._group), dist.get_world_size(self._group)
+            s0, s1 = par.shard_samples(int(n_samples), rank, world)
+            sample_shard = (s0, int(n_samples), par.entropy_weight(rank))
+            n_samples = s1 - s0
+        elif self._group is not None:
             import torch.distributed as dist
 
             if self._global_len is None:
@@ -225,7 +239,10 @@ class ADVI:
         ll_scale = float(full_data_size) / float(n_global)  # advi.py:92
 
         def run(loc, raw, kw):
-            out = engine.step(seed, loc, raw, kw, X, outputs, ll_scale, n_samples, prior_weight)
+            if sample_shard is not None and n_samples == 0:  # more ranks than samples: this rank only joins the reduction
+                out = torch.zeros(1 + engine.D + engine.P + engine.K, dtype=torch.float32, device=engine.device)
+            else:
+                out = engine.step(seed, loc, raw, kw, X, outputs, ll_scale, n_samples, prior_weight, sample_shard=sample_shard)
             if self._group is not None:
                 import torch.distributed as dist
 

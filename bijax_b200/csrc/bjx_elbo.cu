@@ -77,7 +77,8 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
               a.scale_bijector);
   BJX_REQUIRE(a.threefry_layout == BJX_LAYOUT_LEGACY || a.threefry_layout == BJX_LAYOUT_PARTITIONABLE,
               "unknown threefry layout %d", a.threefry_layout);
-  BJX_REQUIRE(a.S * a.D <= 0xFFFFFFFFll, "S*D must fit the 32-bit legacy counter");
+  BJX_REQUIRE(a.S_total == 0 || (a.s_offset >= 0 && a.s_offset + a.S <= a.S_total), "sample shard [s_offset, s_offset+S) must lie in [0, S_total)");
+  BJX_REQUIRE((a.S_total ? a.S_total : a.S) * a.D <= 0xFFFFFFFFll, "S*D must fit the 32-bit legacy counter");
   const int sms = sm_count();
   if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
                                                   float* __restrict__ theta, float* __restrict__ bprime,
                                                   float* __restrict__ gprior, float* __restrict__ qp_part,
                                                   float* __restrict__ eps_out, int64_t probs_coord,
-                                                  float4* __restrict__ probs_aux) {
+                                                  float4* __restrict__ probs_aux, int64_t s_offset, int64_t S_total) {
   __shared__ float red[32];
   const int64_t total = S * D;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
       logsig = logf(fabsf(sc.sigma));
     } else {
       const uint32_t* k = key_index ? key + 2 * (*key_index) : key;  // device-resident loop: key = keys[step counter]
-      const uint32_t bits = random_bits_at(k[0], k[1], (uint64_t)i, (uint64_t)total, layout);
+      // sample sharding: the flat index and the stream length are those of the unsharded (S_total, D) draw
+      const uint32_t bits = random_bits_at(k[0], k[1], (uint64_t)(i + s_offset * D), (uint64_t)(S_total * D), layout);
       eps = bits_to_normal(bits);
       eps_buf[i] = eps;
       const float rho = raw[d];
@@ -259,10 +261,11 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
 }
 
 __global__ void __launch_bounds__(256) k_eps(const uint32_t* __restrict__ key, const int64_t* __restrict__ key_index,
-                                             int64_t total, int layout, float* __restrict__ eps) {
+                                             int64_t total, int64_t offset, int64_t global_total, int layout,
+                                             float* __restrict__ eps) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
-  if (i < total) eps[i] = bits_to_normal(random_bits_at(k[0], k[1], (uint64_t)i, (uint64_t)total, layout));
+  if (i < total) eps[i] = bits_to_normal(random_bits_at(k[0], k[1], (uint64_t)(i + offset), (uint64_t)global_total, layout));
 }
 
 // ---- full-rank contractions (fp32 FFMA; S x D x D) -----------------------------------------------------------------
@@ -410,6 +413,8 @@ struct TailArgs {
   int64_t S, D, Dw, w_off, N;
   int vi_type, scale_bij, likelihood, noise_src, noise_index;
   float noise_value, ll_scale, prior_weight;
+  float entropy_weight;  // weight of the per-step constant -d log sigma / d raw (once per step across sample shards)
+  int64_t S_total;       // samples of the whole step (means divide by this)
 };
 
 __device__ __forceinline__ float tau_of(const TailArgs& t, const float* kwargs, const float* theta, int64_t s) {
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
   const int lane = threadIdx.x & 31;
   const int64_t d = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (d >= t.D) return;
-  const float invS = 1.0f / (float)t.S;
+  const float invS = 1.0f / (float)t.S_total;
   const float cS = t.ll_scale * invS;
   const bool is_w = t.likelihood == BJX_LIK_BERNOULLI_PROBS ? (d == t.w_off) : (d >= t.w_off && d < t.w_off + t.Dw);
   const bool is_noise = t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_LATENT && d == t.noise_index;
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
     out[1 + d] = acc_mu;
     if (t.vi_type == BJX_VI_MEAN_FIELD) {
       const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
-      out[1 + t.D + d] = acc_rho * sc.dsigma - t.prior_weight * sc.dlogsigma;
+      out[1 + t.D + d] = acc_rho * sc.dsigma - t.entropy_weight * sc.dlogsigma;
     }
   }
 }
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t 
   ll = block_sum(ll, red);
   dk = block_sum(dk, red);
   if (threadIdx.x == 0) {
-    const float invS = 1.0f / (float)t.S;
+    const float invS = 1.0f / (float)t.S_total;
     out[0] = t.prior_weight * qp * invS - t.ll_scale * ll * invS;
     float* dkw = out + 1 + t.D + Pn;
     for (int64_t k = 0; k < K; ++k) dkw[k] = 0.0f;
@@ -507,8 +512,9 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
   float4* aux = (float4*)(ws + p.o_aux);
   const int64_t probs_coord = (a.likelihood == BJX_LIK_BERNOULLI_PROBS && a.N > 0) ? a.w_offset : -1;
   const int64_t total = a.S * a.D;
+  const int64_t S_total = a.S_total ? a.S_total : a.S, s_offset = a.S_total ? a.s_offset : 0;
   if (a.vi_type == BJX_VI_FULL_RANK) {
-    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, total, a.threefry_layout, eps);
+    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, total, s_offset * a.D, S_total * a.D, a.threefry_layout, eps);
     BJX_LAUNCH_CHECK("k_eps");
     if (p.fr_tc) {
       int rc = launch_fullrank_z_tc(a, eps, z, ws + p.o_fr_tc, st);
@@ -520,11 +526,11 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
     }
     k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                     a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
-                                                    probs_coord, aux);
+                                                    probs_coord, aux, s_offset, S_total);
   } else {
     k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                      a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out,
-                                                     probs_coord, aux);
+                                                     probs_coord, aux, s_offset, S_total);
   }
   BJX_LAUNCH_CHECK("k_prologue");
   return BJX_OK;
@@ -582,6 +588,8 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   t.vi_type = a.vi_type; t.scale_bij = a.scale_bijector; t.likelihood = a.likelihood;
   t.noise_src = a.noise_src; t.noise_index = a.noise_index; t.noise_value = a.noise_value;
   t.ll_scale = a.ll_scale; t.prior_weight = a.prior_weight;
+  t.entropy_weight = a.S_total ? a.entropy_weight : a.prior_weight;
+  t.S_total = a.S_total ? a.S_total : a.S;
   float* gz = a.vi_type == BJX_VI_FULL_RANK ? (float*)(ws + p.o_gz) : nullptr;
   k_tail<<<(unsigned)((a.D + 7) / 8), 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
                                                        (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
@@ -589,12 +597,12 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   BJX_LAUNCH_CHECK("k_tail");
   if (a.vi_type == BJX_VI_FULL_RANK) {
     if (p.fr_tc) {
-      rc = launch_fullrank_dM_tc(a, gz, a.out + 1 + a.D, ws + p.o_fr_tc, st);
+      rc = launch_fullrank_dM_tc(a, gz, a.out + 1 + a.D, ws + p.o_fr_tc, t.entropy_weight, st);
       if (rc) return rc;
     } else {
       dim3 grid((unsigned)((a.D + 63) / 64), (unsigned)((a.D + 63) / 64));
       k_fullrank_dM<<<grid, 256, 0, st>>>(gz, (const float*)(ws + p.o_eps), a.raw_scale, a.S, a.D, a.scale_bijector,
-                                          a.prior_weight, a.out + 1 + a.D);
+                                          t.entropy_weight, a.out + 1 + a.D);
       BJX_LAUNCH_CHECK("k_fullrank_dM");
     }
   }

@@ -48,7 +48,7 @@ size_t x_planes_bytes(int64_t N, int64_t Dw);
 bool fullrank_tc_eligible(const BjxElboArgs& a);
 size_t fullrank_tc_bytes(const BjxElboArgs& a);
 int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);
-int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, cudaStream_t st);
+int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, float entropy_weight, cudaStream_t st);
 
 // per-datum link functions (the elementwise part of advi.py:91 for the recognised families)
 //   Bernoulli(logits=eta): f = y*eta - softplus(eta)   (== -(1-y) softplus(eta) - y softplus(-eta)),  g = y - sigmoid(eta)

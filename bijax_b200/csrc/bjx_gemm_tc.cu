@@ -716,7 +716,7 @@ int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char*
 
 // dM[i, j] = [j <= i] scale'(M_ij) sum_s gz[s, i] eps[s, j] - [i == j] prior_weight dlog|L_ii|/draw_ii
 // (eps planes are still in `scratch` from launch_fullrank_z_tc of the same step)
-int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, cudaStream_t st) {
+int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, float entropy_weight, cudaStream_t st) {
   using namespace gemm;
   const int64_t Dp = pad64(a.D);
   __nv_bfloat16* e0 = (__nv_bfloat16*)scratch;
@@ -744,7 +744,7 @@ int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char
   P.epi.M = a.raw_scale;
   P.epi.out = dM;
   P.epi.scale_bij = a.scale_bijector;
-  P.epi.prior_weight = a.prior_weight;
+  P.epi.prior_weight = entropy_weight;  // weight of the -d log|L_ii| / d raw_ii constant
   const int64_t tiles = (int64_t)P.sched.tiles_m * P.sched.tiles_n;
   const int sms = sm_count();
   return launch<128, 3, true, true, EPI_DM>(P, (int)(tiles < sms ? tiles : sms), st);

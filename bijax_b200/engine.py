@@ -165,8 +165,11 @@ class ElboEngine:
         return nv.KERNEL_NAMES[nv.check(self.lib.bjx_elbo_kernel_choice(C.byref(a)))]
 
     def step(self, key, loc, raw_scale, kwargs_vec, X, y, ll_scale, n_samples, prior_weight=1.0, out=None, eps_out=None,
-             partitionable=None) -> torch.Tensor:
-        """Enqueue one ELBO+grad step; returns the packed device tensor [loss | d loc | d raw_scale | d kwargs]."""
+             partitionable=None, sample_shard=None) -> torch.Tensor:
+        """Enqueue one ELBO+grad step; returns the packed device tensor [loss | d loc | d raw_scale | d kwargs].
+        ``sample_shard = (s_offset, S_total, entropy_weight)`` evaluates samples [s_offset, s_offset + n_samples) of a
+        step with S_total samples (shard the Monte-Carlo samples when N is small); the packed
+        outputs of all shards sum to the unsharded step."""
         dev = self.device
         key = brandom._check_key(key)
         loc = self._f32(loc, dev).reshape(-1)
@@ -189,6 +192,8 @@ class ElboEngine:
         a.out = out.data_ptr()
         if eps_out is not None:
             a.eps_out = eps_out.data_ptr()
+        if sample_shard is not None:
+            a.s_offset, a.S_total, a.entropy_weight = int(sample_shard[0]), int(sample_shard[1]), float(sample_shard[2])
         a.x_planes = self._x_planes(a, X)
         ws = self._workspace(a)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()

@@ -153,6 +153,16 @@ typedef struct BjxElboArgs {
   /* optional (ABI 2): device-resident step counter.  When set, `key` is the base of a [n, 2] array of per-step keys
    * (jax.random.split(seed, n_epochs), utils.py:30) and the step uses key[*key_index]; see bjx_train_steps. */
   const int64_t* key_index;
+
+  /* optional (ABI 2): Monte-Carlo SAMPLE sharding ("where N is small, shard S").  This call
+   * evaluates samples [s_offset, s_offset + S) of a step with S_total samples in all: eps uses the global flat index
+   * (so every shard draws exactly the noise of the unsharded step), means divide by S_total, and the per-step constant
+   * of the entropy gradient (-d log sigma / d raw) is weighted by entropy_weight (1 on one shard, 0 on the others).
+   * S_total = 0 (default) means no sample sharding: S_total = S, s_offset = 0, entropy_weight = prior_weight. */
+  int64_t S_total;
+  int64_t s_offset;
+  float entropy_weight;
+  float reserved2;
 } BjxElboArgs;
 
 /* ---- library ------------------------------------------------------------ */

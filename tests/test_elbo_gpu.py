@@ -297,6 +297,37 @@ def test_prepared_dataset_planes_match_the_in_step_split():
     assert torch.equal(a2, b2) and not torch.equal(a, a2)
 
 
+@pytest.mark.parametrize("vi,layout", [("mean_field", 0), ("mean_field", 1), ("full_rank", 0)])
+def test_sample_shards_sum_to_the_unsharded_step(vi, layout):
+    """SURVEY.md section 8e, small-N case: the step evaluated as sample shards [0,5) + [5,12) (global eps indices, means over
+    the global S, the entropy-gradient constant on one shard) sums to the unsharded 12-sample step, and the shards draw
+    exactly the unsharded noise."""
+    from bijax_b200 import random as br
+
+    D, N, S = (40, 300, 12) if vi == "mean_field" else (130, 300, 12)
+    X, y = C.synth_linear(N, D)
+    dev = torch.device("cuda")
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.GaussianLinear(), vi_type=vi)
+    lns = torch.tensor([-0.7], device=dev)
+    eng = model._engine_for({"log_noise_scale": lns})[0]
+    loc = torch.tensor(0.1 * tf.normal(tf.prng_key(6), (D,), 1), device=dev)
+    if vi == "mean_field":
+        raw = torch.full((D,), -1.2, device=dev)
+    else:
+        raw = torch.tensor((0.2 * np.eye(D) + 0.01 * tf.normal(tf.prng_key(8), (D, D), 1)).astype(np.float32), device=dev)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    key = br.PRNGKey(21)
+    part = bool(layout)
+    e_all = torch.empty(S * D, device=dev)
+    full = eng.step(key, loc, raw, lns, Xd, yd, 2.0, S, eps_out=e_all, partitionable=part).clone()
+    e_a, e_b = torch.empty(5 * D, device=dev), torch.empty(7 * D, device=dev)
+    a = eng.step(key, loc, raw, lns, Xd, yd, 2.0, 5, eps_out=e_a, partitionable=part, sample_shard=(0, S, 1.0)).clone()
+    b = eng.step(key, loc, raw, lns, Xd, yd, 2.0, 7, eps_out=e_b, partitionable=part, sample_shard=(5, S, 0.0)).clone()
+    assert torch.equal(torch.cat([e_a, e_b]), e_all)
+    C.assert_close((a + b).cpu().numpy(), full.cpu().numpy(), rtol=3e-6, atol_scale=3e-6, what="sample-shard additivity")
+
+
 def _np_fill_triangular(x):
     """tfp.math.fill_triangular(x, upper=False) restated in NumPy (documented example: [1..6] -> [[4,0,0],[6,5,0],[3,2,1]])."""
     m = x.shape[-1]

@@ -63,6 +63,64 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _packed_oracle_samples(X, y, loc, raw, lns, full, eps_all, s0, s1, entropy_w):
+    """What one rank's bjx_elbo_step writes under SAMPLE sharding: sums over its samples [s0, s1) divided by the global S,
+    q / prior terms of its own samples at full weight, and the per-step constant of the entropy gradient
+    (-d sum log sigma / d raw = -1 under Exp) carried by one rank only."""
+    S = eps_all.shape[0]
+    loc_t = torch.tensor(loc, dtype=torch.float64, requires_grad=True)
+    raw_t = torch.tensor(raw, dtype=torch.float64, requires_grad=True)
+    lns_t = torch.tensor(lns, dtype=torch.float64, requires_grad=True)
+    D = loc_t.numel()
+    eps = eps_all[s0:s1]
+    sigma = torch.exp(raw_t)
+    z = loc_t + sigma * eps
+    logsig_const = torch.log(sigma).sum().detach()  # value counted per sample; its gradient is the once-per-step constant
+    q = (-0.5 * eps * eps).sum(-1) - logsig_const - 0.5 * D * R.LOG_2PI
+    p = (-0.5 * z * z - 0.5 * R.LOG_2PI).sum(-1)
+    tau = torch.exp(lns_t)
+    r = (torch.tensor(y, dtype=torch.float64)[:, None] - torch.tensor(X, dtype=torch.float64) @ z.T) / tau
+    ll = (-0.5 * r * r - 0.5 * R.LOG_2PI - torch.log(tau)).sum(0)
+    loss = ((q - p) - (full / len(y)) * ll).sum() / S - entropy_w * (torch.log(sigma).sum() - logsig_const)
+    g = torch.autograd.grad(loss, [loc_t, raw_t, lns_t])
+    return torch.cat([loss.detach().reshape(1), g[0], g[1], g[2].reshape(1)])
+
+
+def _worker_samples(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, D, S = 40, 6, 7  # small N: shard the Monte-Carlo samples instead of the rows (SURVEY.md section 8e)
+        X, y = C.synth_linear(N, D)
+        loc = 0.1 * tf.normal(tf.prng_key(3), (D,), 1).astype(np.float64)
+        raw = np.full(D, math.log(0.2))
+        eps = torch.tensor(tf.normal(tf.prng_key(9), (S, D), tf.LAYOUT_LEGACY), dtype=torch.float64)
+        s0, s1 = par.shard_samples(S, rank, world)
+        out = _packed_oracle_samples(X, y, loc, raw, -0.5, 3.0 * N, eps, s0, s1, par.entropy_weight(rank))
+        par.allreduce_packed(out)
+        if rank == 0:
+            want = _packed_oracle(X, y, loc, raw, -0.5, 3.0 * N, N, 1.0, eps)
+            q.put((out.numpy(), want.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sample_sharded_allreduce_matches_unsharded():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_samples, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, want = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    assert par.shard_samples(7, 0, 2) == (0, 4) and par.shard_samples(7, 1, 2) == (4, 7)
+    assert par.entropy_weight(0) == 1.0 and par.entropy_weight(1) == 0.0
+
+
 def test_row_sharded_allreduce_matches_unsharded():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
