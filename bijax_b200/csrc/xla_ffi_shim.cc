@@ -14,12 +14,14 @@
 
 namespace ffi = xla::ffi;
 
-// Operands: key u32[2], loc f32[D], raw_scale f32[P], kwargs f32[K], X f32[N, Dw], y f32[N], coords u8[D*20].
+// Operands: key u32[2], loc f32[D], raw_scale f32[P], kwargs f32[K], X f32[N, Dw], y f32[N], coords u8[D*20],
+//           planes u8[bjx_x_planes_bytes(N, Dw)] (output of BjxPrepareXPlanes, computed once outside the scan) or u8[0].
 // Result:   out f32[1 + D + P + K] (loss, then every gradient) and a u8 workspace sized by bjx_elbo_workspace_bytes.
 // Attributes carry the static configuration (S, family ids, ll_scale, prior_weight, ...).
 static ffi::Error ElboStepImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> key, ffi::Buffer<ffi::F32> loc,
                                ffi::Buffer<ffi::F32> raw_scale, ffi::Buffer<ffi::F32> kwargs, ffi::Buffer<ffi::F32> X,
-                               ffi::Buffer<ffi::F32> y, ffi::Buffer<ffi::U8> coords, ffi::ResultBuffer<ffi::F32> out,
+                               ffi::Buffer<ffi::F32> y, ffi::Buffer<ffi::U8> coords, ffi::Buffer<ffi::U8> planes,
+                               ffi::ResultBuffer<ffi::F32> out,
                                ffi::ResultBuffer<ffi::U8> workspace, int64_t S, int64_t w_offset, int32_t vi_type,
                                int32_t scale_bijector, int32_t likelihood, int32_t noise_src, int32_t noise_index,
                                int32_t threefry_layout, int32_t precision, float noise_value, float ll_scale,
@@ -50,6 +52,7 @@ static ffi::Error ElboStepImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> key, f
   a.X = a.Dw ? X.typed_data() : nullptr;
   a.y = y.typed_data();
   a.coords = reinterpret_cast<const BjxCoord*>(coords.typed_data());
+  a.x_planes = planes.element_count() ? planes.typed_data() : nullptr;  // dataset prepared once (bjx_prepare_x_planes)
   a.out = out->typed_data();
   a.workspace = workspace->typed_data();
   a.workspace_bytes = workspace->element_count();
@@ -69,6 +72,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxElboStep, ElboStepImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>()
                                   .Attr<int64_t>("S")
@@ -83,6 +87,24 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxElboStep, ElboStepImpl,
                                   .Attr<float>("noise_value")
                                   .Attr<float>("ll_scale")
                                   .Attr<float>("prior_weight"));
+
+// planes u8[bjx_x_planes_bytes(N, Dw)] = split-bf16 operand planes of X f32[N, Dw]: a pure function of X, called once per
+// dataset outside train_fn's scan.
+static ffi::Error PrepareXPlanesImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> X, ffi::ResultBuffer<ffi::U8> planes) {
+  const auto xd = X.dimensions();
+  if (xd.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "X must be [N, Dw]");
+  if (planes->element_count() < bjx_x_planes_bytes(xd[0], xd[1]))
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "planes buffer smaller than bjx_x_planes_bytes(N, Dw)");
+  const int rc = bjx_prepare_x_planes(X.typed_data(), xd[0], xd[1], xd[1], planes->typed_data(), stream);
+  if (rc == BJX_OK) return ffi::Error::Success();
+  return ffi::Error(ffi::ErrorCode::kInternal, bjx_last_error());
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxPrepareXPlanes, PrepareXPlanesImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
 #else
 // jaxlib headers not found: nothing to build (see the header comment).
 #endif
