@@ -452,6 +452,11 @@ constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 struct Maps {
   CUtensorMap x1, x2;
 };
+struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
+  unsigned long long x_full[9], x_empty[9];
+  unsigned long long acc1_full, dl_full, dl_empty, done;
+  uint32_t tmem_base;
+};
 }  // namespace tcp
 
 template <int NBLK>  // D / 64
@@ -469,11 +474,15 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   constexpr int NCH = NBLK / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sx1 = smem;
-  uint8_t* sx2 = sx1 + NBLK * BLK_BYTES;
+  // Block 0 of a tile alternates between its regular slot and a spare one (index 8) placed one block BEFORE it, so the
+  // producer can fetch block 0 of tile t+1 while tile t is still being consumed: GEMM1 of the next tile then starts the
+  // moment GEMM2 retires instead of waiting a TMA latency.  For GEMM2 (MN-major A, two 64-column blocks per chunk) the
+  // spare slot is reached by a leading-dimension byte offset of two blocks instead of one.
+  uint8_t* sx1 = smem + BLK_BYTES;  // spare slot at sx1 - BLK_BYTES
+  uint8_t* sx2 = sx1 + (NBLK + 1) * BLK_BYTES;  // spare slot at sx2 - BLK_BYTES
   uint8_t* sth = sx2 + NBLK * BLK_BYTES;
   uint8_t* sdl = sth + NBLK * BLK_BYTES;
-  Bars* bars = (Bars*)(sdl + BLK_BYTES);
+  tcp::BarsP* bars = (tcp::BarsP*)(sdl + BLK_BYTES);
   float* sred = (float*)(bars + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -481,7 +490,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 9; ++b) {
       mbar_init(&bars->x_full[b], 1);  // the producer's expect_tx arrival; completion is counted in bytes
       mbar_init(&bars->x_empty[b], 1);
     }
@@ -518,9 +527,20 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     // ===================================================== TMA producer ================================================
     const __nv_bfloat16* p1 = planes;
     const __nv_bfloat16* p2 = planes + (size_t)N * D;
-    const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them, 2 per-lane line prefetch
+    const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them
     const int pf_dist = pf_tiles & 255;
     if (lane == 0) {
+      auto issue_block0 = [&](int64_t t) {
+        const int alt = (int)(t & 1);
+        const int idx = alt ? 8 : 0;
+        const int64_t row0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
+        mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));  // released by chunk 0 of GEMM2 two tiles ago
+        BJX_TRACE(t, 0);
+        mbar_expect_tx(&bars->x_full[idx], 2u * BLK_BYTES);
+        tma_load_2d(alt ? sx1 - BLK_BYTES : sx1, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
+        tma_load_2d(alt ? sx2 - BLK_BYTES : sx2, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
+      };
+      if (my_tiles > 0) issue_block0(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
         auto bulk_pf = [&]() {
@@ -532,28 +552,15 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * D), "r"(bytes) : "memory");
         };
         if (pf_mode == 0 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
-        for (int b = 0; b < NBLK; ++b) {
+        for (int b = 1; b < NBLK; ++b) {
           mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
           BJX_TRACE(it, b);
           mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
           tma_load_2d(sx1 + b * BLK_BYTES, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
           tma_load_2d(sx2 + b * BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
         }
+        if (it + 1 < my_tiles) issue_block0(it + 1);  // into the other slot: free since chunk 0 of GEMM2(it - 1)
         if (pf_mode == 1 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
-      }
-    } else if (pf_mode == 2 && pf_dist > 0) {
-      // lanes 1..31: fire-and-forget line prefetches of a later tile, paced by the tile the MMA warp is consuming
-      for (int64_t it = 0; it + pf_dist < my_tiles; ++it) {
-        mbar_wait(&bars->x_full[0], (uint32_t)(it & 1));
-        const int64_t rowp = (blockIdx.x + (it + pf_dist) * gridDim.x) * TILE_ROWS;
-        const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
-        const int64_t lines = rows * D * 2 / 128;
-        const char* b1 = (const char*)(p1 + rowp * D);
-        const char* b2 = (const char*)(p2 + rowp * D);
-        for (int64_t l = lane - 1; l < lines; l += 31) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + l * 128));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + l * 128));
-        }
       }
     }
   } else if (warp == tcp::MMA_WARP) {
@@ -566,20 +573,29 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
     const uint64_t tx1 = make_desc(smem_u32(sx1), BLK_BYTES, 1024), tx2 = make_desc(smem_u32(sx2), BLK_BYTES, 1024);
     const uint64_t tdl = make_desc(smem_u32(sdl), BLK_BYTES, 1024);
+    // chunk 0 of GEMM2 when block 0 sits in the spare slot: blocks {spare, 1} are two block strides apart
+    const uint64_t tx1_alt = make_desc(smem_u32(sx1 - BLK_BYTES), 2 * BLK_BYTES, 1024);
+    const uint64_t tx2_alt = make_desc(smem_u32(sx2 - BLK_BYTES), 2 * BLK_BYTES, 1024);
     const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
     int phase = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
+      const bool alt = (it & 1) != 0;
+      const int idx0 = alt ? 8 : 0;
       for (int b = 0; b < NBLK; ++b) {
-        mbar_wait(&bars->x_full[b], ph);
+        if (b == 0)
+          mbar_wait(&bars->x_full[idx0], (uint32_t)((it >> 1) & 1));
+        else
+          mbar_wait(&bars->x_full[b], ph);
         if (lane == 0) BJX_TRACE(it, 16 + b);
         if (!(ablate & 1) && elect_one()) {
-          const uint64_t boff = (uint64_t)((b * BLK_BYTES) >> 4);
+          const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
+          const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(BLK_BYTES >> 4)) : toff;  // X block (spare slot for b = 0)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + ACC1_COL, dx1 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N64, (b | k) != 0);
+            umma_bf16(tmem + ACC1_COL, dx1 + boff + 2 * k, dth + toff + 2 * k, ID_G1_N64, (b | k) != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dx2 + boff + 2 * k, dth + boff + 2 * k, ID_G1_N32, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dx2 + boff + 2 * k, dth + toff + 2 * k, ID_G1_N32, 1);
         }
         __syncwarp();
       }
@@ -592,14 +608,16 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       for (int ch = 0; ch < NCH; ++ch) {
         if (elect_one()) {
           const uint64_t coff = (uint64_t)((2 * ch * BLK_BYTES) >> 4);
+          const uint64_t a1 = (ch == 0 && alt) ? tx1_alt : tx1 + coff;
+          const uint64_t a2 = (ch == 0 && alt) ? tx2_alt : tx2 + coff;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (ablate & 2) continue;
-            umma_bf16(tmem + ACC2_COL + ch * NB, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2,
+            umma_bf16(tmem + ACC2_COL + ch * NB, a1 + 128 * k, tdl + 128 * k, ID_G2,
                       (k != 0) || !(it == 0 || phase == ch * flush_step));
-            umma_bf16(tmem + ACC2_COL + ch * NB, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
+            umma_bf16(tmem + ACC2_COL + ch * NB, a2 + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
           }
-          umma_commit(&bars->x_empty[2 * ch]);
+          umma_commit(&bars->x_empty[ch == 0 ? idx0 : 2 * ch]);
           umma_commit(&bars->x_empty[2 * ch + 1]);
         }
         __syncwarp();
@@ -820,7 +838,8 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   const int nblk = (int)(a.Dw / tc::BLK_COLS);
   const size_t smem = tc_smem_bytes(nblk);
   if (a.x_planes != nullptr) {
-    // dataset prepared as split-bf16 planes: the TMA-fed variant
+    // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
+    const size_t smem = (size_t)(3 * nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 1024;
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");
