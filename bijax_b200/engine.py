@@ -131,7 +131,12 @@ class ElboEngine:
         N = y.numel()
         if self.lik_id == nv.LIK_BERNOULLI_PROBS:
             return None, y, N, 0
-        X = self._f32(X, self.device)
+        if not isinstance(X, torch.Tensor):
+            X = torch.as_tensor(X)
+        if X.device != self.device or X.dtype != torch.float32:
+            X = X.to(device=self.device, dtype=torch.float32)
+        if X.dim() == 2 and X.stride(1) != 1:
+            X = X.contiguous()  # rows may be pitched (ldx > Dw, e.g. a column slice of a wider matrix), columns must be dense
         if X.dim() != 2 or X.shape[0] != N or X.shape[1] != self.Dw:
             raise ValueError(f"X must be [N={N}, D={self.Dw}] (rows = data, row-major); got {tuple(X.shape)}")
         return X, y, N, X.stride(0)

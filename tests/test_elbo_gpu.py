@@ -274,6 +274,40 @@ def test_full_rank_contractions_on_the_tensor_cores(D, S, lik):
     assert np.all(np.triu(g, 1) == 0.0)
 
 
+@pytest.mark.parametrize("kernel,Dw,S,prepared", [("tcgen05_bf16_split", 256, 24, True), ("tcgen05_bf16_split", 256, 24, False),
+                                                  ("tcgen05_gemm_two_pass", 192, 70, True), ("tcgen05_gemm_two_pass", 192, 70, False)])
+def test_tensor_core_paths_with_offset_weights_latent_noise_and_strided_X(kernel, Dw, S, prepared):
+    """The weights are not the first latent (w_offset > 0: "a_first" sorts before "weights"), the Gaussian noise scale is a
+    constrained latent (Gamma prior + Exp bijector), and X is a column slice of a wider matrix (row pitch ldx > Dw)."""
+    from bijax_b200 import random as br
+
+    N = 3001
+    Xw, y = C.synth_linear(N, Dw + 8, noise=0.4)
+    prior = {
+        "a_first": tfd.Normal(np.zeros(3, np.float32), 2.0),
+        "noise": tfd.Gamma(2.0, 3.0),
+        "weights": tfd.MultivariateNormalDiag(loc=np.zeros(Dw, np.float32), scale_diag=np.ones(Dw, np.float32)),
+    }
+    model, ref = C.build_pair(prior, {"noise": tfb.Exp()}, lk.GaussianLinear(noise_latent="noise"), kernel=kernel,
+                              prepare_dataset=prepared)
+    D = model.size
+    assert D == Dw + 4
+    loc = (0.05 * tf.normal(tf.prng_key(5), (D,), 1)).astype(np.float32)
+    raw = np.full(D, math.log(0.1), np.float32)
+    dev = torch.device("cuda")
+    Xfull = torch.tensor(Xw, device=dev)
+    Xv = Xfull[:, :Dw]  # a view: stride(0) = Dw + 8
+    assert Xv.stride(0) == Dw + 8
+    eng = model._engine_for({})[0]
+    # the engine's host layer makes inputs contiguous, so drive the C ABI stride through the engine's own data path
+    out = eng.step(br.PRNGKey(11), torch.tensor(loc, device=dev), torch.tensor(raw, device=dev), None, Xv, torch.tensor(y, device=dev), 2.5, S)
+    (wl, wgl, wgr, _), _ = C.oracle_step(ref, loc, raw, {}, y, Xw[:, :Dw], 2.5 * N, tf.prng_key(11), S, 0)
+    assert eng.kernel_choice(S, N) == kernel
+    C.assert_close(out[0].item(), wl.item(), what="loss")
+    C.assert_close(out[1 : 1 + D].cpu().numpy(), wgl.numpy(), what="d loc")
+    C.assert_close(out[1 + D :].cpu().numpy(), wgr.numpy(), what="d rho")
+
+
 def test_prepared_dataset_planes_match_the_in_step_split():
     """The two-pass path with X pre-split once per dataset (bjx_prepare_x_planes, cached by the engine while the same
     unmodified tensor is passed) is bit-identical to splitting inside every step; an in-place update of X invalidates the cache."""
