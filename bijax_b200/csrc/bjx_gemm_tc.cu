@@ -79,9 +79,9 @@ struct Bars {
   uint32_t tmem_base;
 };
 
-template <int BN, int NT>
+template <int BN, int NT, int CG = 1>
 struct Cfg {
-  static constexpr int B_PLANE = BN * 128;
+  static constexpr int B_PLANE = (BN / CG) * 128;  // per CTA: a pair splits the B tile
   static constexpr int STAGE_BYTES = NT * (A_PLANE + B_PLANE);
   static constexpr int NSTAGE = (200 * 1024 / STAGE_BYTES) < 4 ? (200 * 1024 / STAGE_BYTES) : 4;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256;
@@ -91,11 +91,12 @@ struct Cfg {
 };
 
 // Walks the virtual tiles of this CTA in the one order every warp role agrees on.
-template <int BN, class F>
+template <int BN, int CG, class F>
 __device__ __forceinline__ void for_each_vtile(const Sched& sc, F&& f) {
+  constexpr int BMC = BM * CG;  // rows of one output tile (a CTA pair works on 256)
   const int n_tiles = sc.tiles_m * sc.tiles_n;
   const int n_units = n_tiles * sc.splits;
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  for (int u = blockIdx.x / CG; u < n_units; u += gridDim.x / CG) {
     const int tile = u % n_tiles, split = u / n_tiles;
     const int m_blk = tile / sc.tiles_n, n_blk = tile % sc.tiles_n;
     int kb_lo = split * sc.kb_per_split;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void for_each_vtile(const Sched& sc, F&& f) {
       const int lim = ((n_blk + 1) * BN + BK - 1) / BK;
       if (kb_hi > lim) kb_hi = lim;
     } else if (sc.tril == 2) {
-      if (n_blk * BN > m_blk * BM + BM - 1) kb_hi = kb_lo;
+      if (n_blk * BN > m_blk * BMC + BMC - 1) kb_hi = kb_lo;
     }
     if (kb_hi < kb_lo) kb_hi = kb_lo;
     int kb0 = kb_lo;
@@ -133,10 +134,12 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN, int NT, bool A_MN, bool B_MN, int EPI>
+template <int BN, int NT, bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Params P) {
   using namespace tc;
-  using C = Cfg<BN, NT>;
+  using C = Cfg<BN, NT, CG>;
+  constexpr int BMC = BM * CG;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // 0 = leader: issues the pair's MMAs, owns full / tmem_empty barriers
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   Bars* bars = (Bars*)(smem + C::NSTAGE * C::STAGE_BYTES);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4);
+      mbar_init(&bars->tmem_empty[s], 4 * CG);
     }
     fence_mbar_init();
   }
@@ -161,38 +164,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       tma_prefetch_desc(&P.mapB[t]);
     }
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_cg2(&bars->tmem_base, C::TMEM_COLS); else tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before multicast commits / remote arrivals reach them
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
     // ===================================================== TMA producer ================================================
+    // (pair: both CTAs load their own 128 rows of A and their half of B; every byte is counted on the leader's barrier)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for_each_vtile<BN>(sc, [&](int m_blk, int n_blk, int, int kb0, int kb1) {
+      auto load = [&](void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, void* bar) {
+        if (CG == 2) tma_load_2d_cg2(dst, map, c0, c1, bar); else tma_load_2d(dst, map, c0, c1, bar);
+      };
+      for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int, int kb0, int kb1) {
+        const int m0 = m_blk * BMC + rank * BM, n0 = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bars->full[stage], (uint32_t)C::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(&bars->full[stage], (uint32_t)(CG * C::STAGE_BYTES));
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + NT * A_PLANE;
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
             if (!A_MN) {
-              tma_load_2d(sa + t * A_PLANE, &P.mapA[t], kb * BK, m_blk * BM, &bars->full[stage]);
+              load(sa + t * A_PLANE, &P.mapA[t], kb * BK, m0, &bars->full[stage]);
             } else {
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i)
-                tma_load_2d(sa + t * A_PLANE + i * 8192, &P.mapA[t], m_blk * BM + 64 * i, kb * BK, &bars->full[stage]);
+              for (int i = 0; i < BM / 64; ++i) load(sa + t * A_PLANE + i * 8192, &P.mapA[t], m0 + 64 * i, kb * BK, &bars->full[stage]);
             }
             if (!B_MN) {
-              tma_load_2d(sb + t * C::B_PLANE, &P.mapB[t], kb * BK, n_blk * BN, &bars->full[stage]);
+              load(sb + t * C::B_PLANE, &P.mapB[t], kb * BK, n0, &bars->full[stage]);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_2d(sb + t * C::B_PLANE + i * 8192, &P.mapB[t], n_blk * BN + 64 * i, kb * BK, &bars->full[stage]);
+              for (int i = 0; i < BN / CG / 64; ++i) load(sb + t * C::B_PLANE + i * 8192, &P.mapB[t], n0 + 64 * i, kb * BK, &bars->full[stage]);
             }
           }
           if (++stage == C::NSTAGE) {
@@ -203,15 +212,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       });
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer ==================================================
-    constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================================================== MMA issuer (the leader CTA of a pair) ========================
+    if (rank == 0) {
+    constexpr uint32_t IDESC = make_idesc(BMC, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     // K-major tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart, K advances 32 bytes per UMMA (K = 16)
     // MN-major tile: blocks of [64 k-rows][64 mn] = 8 KB, 8-row atoms 1024 bytes apart, K advances 16 rows = 2048 bytes
     constexpr uint32_t A_LBO = A_MN ? 8192 : 16, B_LBO = B_MN ? 8192 : 16;
     constexpr uint64_t A_KADV = A_MN ? 128 : 2, B_KADV = B_MN ? 128 : 2;  // in 16-byte units
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
-    for_each_vtile<BN>(sc, [&](int, int, int, int kb0, int kb1) {
+    for_each_vtile<BN, CG>(sc, [&](int, int, int, int kb0, int kb1) {
       mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)(as * BN);
@@ -236,12 +246,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
               const int j = sum - i;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d_tmem, da[i] + A_KADV * k, db[j] + B_KADV * k, IDESC, first ? 0u : 1u);
+                if (CG == 2) umma_bf16_cg2(d_tmem, da[i] + A_KADV * k, db[j] + B_KADV * k, IDESC, first ? 0u : 1u);
+                else umma_bf16(d_tmem, da[i] + A_KADV * k, db[j] + B_KADV * k, IDESC, first ? 0u : 1u);
                 first = false;
               }
             }
           }
-          umma_commit(&bars->empty[stage]);
+          if (CG == 2) umma_commit_cg2(&bars->empty[stage]); else umma_commit(&bars->empty[stage]);
         }
         __syncwarp();
         if (++stage == C::NSTAGE) {
@@ -249,25 +260,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           phase ^= 1u;
         }
       }
-      if (elect_one()) umma_commit(&bars->tmem_full[as]);
+      if (elect_one()) {
+        if (CG == 2) umma_commit_cg2(&bars->tmem_full[as]); else umma_commit(&bars->tmem_full[as]);
+      }
       __syncwarp();
       if (++as == NACC) {
         as = 0;
         aphase ^= 1u;
       }
     });
+    }
   } else {
     // ===================================================== epilogue =====================================================
     const int q = warp & 3;  // TMEM sub-partition of this warp: accumulator rows 32q .. 32q+31
     const EpiArgs& e = P.epi;
     int as = 0;
     uint32_t aphase = 0;
-    for_each_vtile<BN>(sc, [&](int m_blk, int n_blk, int split, int kb0, int kb1) {
+    for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int split, int kb0, int kb1) {
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem + (uint32_t)(as * BN) + ((uint32_t)(32 * q) << 16);
       const bool empty = kb1 == kb0;
-      const int64_t r = (int64_t)m_blk * BM + 32 * q + lane;  // accumulator row of this thread
+      const int64_t r = (int64_t)m_blk * BMC + rank * BM + 32 * q + lane;  // accumulator row of this thread
       if (EPI == EPI_LIK1) {
         const bool row_ok = r < e.n_rows;
         const float yv = row_ok ? e.y[r] : 0.0f;
@@ -385,7 +399,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&bars->tmem_empty[as]); else mbar_arrive(&bars->tmem_empty[as]);
+      }
       if (++as == NACC) {
         as = 0;
         aphase ^= 1u;
@@ -395,7 +411,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+  if (CG == 2) cluster_sync_all();  // the peer may still be reading accumulators the leader's MMAs wrote
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_cg2(tmem, C::TMEM_COLS); else tmem_dealloc(tmem, C::TMEM_COLS);
+  }
 }
 
 // ---- fp32 -> bf16 split planes --------------------------------------------------------------------------------------
@@ -512,15 +531,32 @@ int make_bf16_tensor_map(CUtensorMap* m, const void* base, int64_t rows, int64_t
 }
 namespace gemm {
 
-template <int BN, int NT, bool A_MN, bool B_MN, int EPI>
+template <int BN, int NT, bool A_MN, bool B_MN, int EPI, int CG = 1>
 static int launch(const Params& P, int grid, cudaStream_t st) {
-  using C = Cfg<BN, NT>;
+  using C = Cfg<BN, NT, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    BJX_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BN, NT, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    BJX_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  k_gemm_tc<BN, NT, A_MN, B_MN, EPI><<<grid, THREADS, C::SMEM_BYTES, st>>>(P);
+  if (CG == 1) {
+    k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG><<<grid, THREADS, C::SMEM_BYTES, st>>>(P);
+  } else {
+    // CTA pairs: a cluster of two CTAs (same TPC) per 256-row tile
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BJX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG>, P));
+  }
   BJX_LAUNCH_CHECK("k_gemm_tc");
   return BJX_OK;
 }
@@ -563,21 +599,37 @@ bool gemm_eligible(const BjxElboArgs& a) {
 
 static int lik1_bn(int64_t S) { return S <= 64 ? 64 : (S <= 128 ? 128 : 256); }
 
+// CTA pairs (cta_group::2) for the widest tiles: the pair shares the B operand, which halves its shared-memory reads and
+// its TMA writes per SM -- the port both compete for (BJX_GEMM_CG=1 keeps single-CTA tiles, for A/B measurements)
+static int gemm_cg(int bn) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("BJX_GEMM_CG");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2) return bn == 256 ? forced : 1;
+  return bn == 256 ? 2 : 1;
+}
+
 int gemm_plan(const BjxElboArgs& a, Plan& p) {
   const int sms = sm_count();
   if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
-  const int bn1 = lik1_bn(a.S), bn2 = bn1;
-  const int64_t tiles1 = ((a.N + 127) / 128) * ((a.S + bn1 - 1) / bn1);
-  p.gm_grid1 = (int)(tiles1 < sms ? tiles1 : sms);
-  const int64_t tiles2 = ((a.Dw + 127) / 128) * ((a.S + bn2 - 1) / bn2);
+  const int bn = lik1_bn(a.S);
+  const int cg = gemm_cg(bn);
+  const int groups = sms / cg;  // CTAs, or CTA pairs
+  const int bmc = 128 * cg;
+  const int64_t tiles1 = ((a.N + bmc - 1) / bmc) * ((a.S + bn - 1) / bn);
+  p.gm_grid1 = cg * (int)(tiles1 < groups ? tiles1 : groups);
+  const int64_t tiles2 = ((a.Dw + bmc - 1) / bmc) * ((a.S + bn - 1) / bn);
   const int64_t kb_total = (a.N + 63) / 64;
-  int64_t splits = tiles2 >= sms ? 1 : sms / tiles2;
+  int64_t splits = tiles2 >= groups ? 1 : groups / tiles2;
   const int64_t max_splits = (kb_total + 15) / 16;  // at least one full virtual tile per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.gm_splits = (int)splits;
   int64_t units = tiles2 * splits;
-  p.gm_grid2 = (int)(units < sms ? units : sms);
+  p.gm_grid2 = cg * (int)(units < groups ? units : groups);
+  p.gm_cg = cg;
   p.gm_Dp = gemm::pad64(a.Dw);
   p.gm_Sp = gemm::pad64(a.S);
   return BJX_OK;
@@ -618,9 +670,10 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     int rc;
     if ((rc = make_map(&P.mapA[0], x1, a.N, a.Dw, Dp, 64, 128))) return rc;
     if ((rc = make_map(&P.mapA[1], x2, a.N, a.Dw, Dp, 64, 128))) return rc;
-    if ((rc = make_map(&P.mapB[0], t1, a.S, a.Dw, Dp, 64, bn))) return rc;
-    if ((rc = make_map(&P.mapB[1], t2, a.S, a.Dw, Dp, 64, bn))) return rc;
-    P.sched.tiles_m = (int)((a.N + 127) / 128);
+    const int cg = p.gm_cg, bmc = 128 * cg;
+    if ((rc = make_map(&P.mapB[0], t1, a.S, a.Dw, Dp, 64, bn / cg))) return rc;  // a pair loads half of the B tile per CTA
+    if ((rc = make_map(&P.mapB[1], t2, a.S, a.Dw, Dp, 64, bn / cg))) return rc;
+    P.sched.tiles_m = (int)((a.N + bmc - 1) / bmc);
     P.sched.tiles_n = (int)((a.S + bn - 1) / bn);
     P.sched.splits = 1;
     P.sched.kb_total = (int)(Dp / 64);
@@ -637,6 +690,7 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     P.epi.statpart = statpart;
     if (bn == 64) rc = launch<64, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
     else if (bn == 128) rc = launch<128, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
+    else if (cg == 2) rc = launch<256, 2, false, false, EPI_LIK1, 2>(P, p.gm_grid1, st);
     else rc = launch<256, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
     if (rc) return rc;
   }
@@ -650,7 +704,8 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     if ((rc = make_map(&P.mapA[1], x2, a.N, a.Dw, Dp, 64, 64))) return rc;
     if ((rc = make_map(&P.mapB[0], g1, a.N, a.S, Sp, 64, 64))) return rc;
     if ((rc = make_map(&P.mapB[1], g2, a.N, a.S, Sp, 64, 64))) return rc;
-    P.sched.tiles_m = (int)((a.Dw + 127) / 128);
+    const int cg = p.gm_cg, bmc = 128 * cg;
+    P.sched.tiles_m = (int)((a.Dw + bmc - 1) / bmc);
     P.sched.tiles_n = (int)((a.S + bn - 1) / bn);
     P.sched.splits = p.gm_splits;
     P.sched.kb_total = (int)((a.N + 63) / 64);
@@ -662,6 +717,7 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     P.epi.Dw = a.Dw;
     if (bn == 64) rc = launch<64, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     else if (bn == 128) rc = launch<128, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
+    else if (cg == 2) rc = launch<256, 2, true, true, EPI_LIK2, 2>(P, p.gm_grid2, st);
     else rc = launch<256, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     if (rc) return rc;
   }
