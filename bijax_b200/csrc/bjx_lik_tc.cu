@@ -478,12 +478,15 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   // producer can fetch block 0 of tile t+1 while tile t is still being consumed: GEMM1 of the next tile then starts the
   // moment GEMM2 retires instead of waiting a TMA latency.  For GEMM2 (MN-major A, two 64-column blocks per chunk) the
   // spare slot is reached by a leading-dimension byte offset of two blocks instead of one.
-  uint8_t* sx1 = smem + BLK_BYTES;  // spare slot at sx1 - BLK_BYTES
-  uint8_t* sx2 = sx1 + (NBLK + 1) * BLK_BYTES;  // spare slot at sx2 - BLK_BYTES
-  uint8_t* sth = sx2 + NBLK * BLK_BYTES;
+  // X slots are 16 KB: [x1 block | x2 block], i.e. 128 rows of 128 bytes -- GEMM1 takes the stacked pair as ONE UMMA A
+  // operand with M = 128 (rows 0-63 the x1 terms, rows 64-127 the x2 terms of the same 64 data rows); slot -1 is the spare.
+  constexpr int SLOT = 2 * BLK_BYTES;
+  uint8_t* sx = smem + SLOT;
+  uint8_t* sth = sx + NBLK * SLOT;
   uint8_t* sdl = sth + NBLK * BLK_BYTES;
   tcp::BarsP* bars = (tcp::BarsP*)(sdl + BLK_BYTES);
   float* sred = (float*)(bars + 1);
+  float* xch = (float*)(((uintptr_t)(sred + 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
@@ -502,6 +505,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     tma_prefetch_desc(&maps.x1);
     tma_prefetch_desc(&maps.x2);
   }
+  if (tid < 4 * NS) sred[tid] = 0.0f;
   if (warp == tcp::MMA_WARP) tmem_alloc(&bars->tmem_base, TMEM_COLS);
   for (int idx = tid; idx < NS * (D / 8); idx += tcp::THREADS) {
     const int s = idx / (D / 8), d8 = idx % (D / 8);
@@ -537,8 +541,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));  // released by chunk 0 of GEMM2 two tiles ago
         BJX_TRACE(t, 0);
         mbar_expect_tx(&bars->x_full[idx], 2u * BLK_BYTES);
-        tma_load_2d(alt ? sx1 - BLK_BYTES : sx1, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
-        tma_load_2d(alt ? sx2 - BLK_BYTES : sx2, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
+        uint8_t* slot = alt ? sx - SLOT : sx;
+        tma_load_2d(slot, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
+        tma_load_2d(slot + BLK_BYTES, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
       };
       if (my_tiles > 0) issue_block0(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
@@ -556,8 +561,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
           BJX_TRACE(it, b);
           mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
-          tma_load_2d(sx1 + b * BLK_BYTES, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-          tma_load_2d(sx2 + b * BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+          tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+          tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
         }
         if (it + 1 < my_tiles) issue_block0(it + 1);  // into the other slot: free since chunk 0 of GEMM2(it - 1)
         if (pf_mode == 1 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
@@ -565,17 +570,17 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     }
   } else if (warp == tcp::MMA_WARP) {
     // ===================================================== MMA issuer ==================================================
-    constexpr uint32_t ID_G1_N64 = make_idesc(64, NB, 0, 0);
-    constexpr uint32_t ID_G1_N32 = make_idesc(64, NS, 0, 0);
+    constexpr uint32_t ID_G1 = make_idesc(128, NB, 0, 0);      // [x1; x2] * [t1; t2]: all four partial products in one UMMA
     constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);
     constexpr uint32_t ID_G2_N32 = make_idesc(128, NS, 1, 1);
-    const uint64_t dx1 = make_desc(smem_u32(sx1), 16, 1024), dx2 = make_desc(smem_u32(sx2), 16, 1024);
+    const uint64_t dxa = make_desc(smem_u32(sx), 16, 1024);
     const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
-    const uint64_t tx1 = make_desc(smem_u32(sx1), BLK_BYTES, 1024), tx2 = make_desc(smem_u32(sx2), BLK_BYTES, 1024);
+    // GEMM2 (MN-major A): the two 64-column blocks of a chunk are one slot (16 KB) apart
+    const uint64_t tx1 = make_desc(smem_u32(sx), SLOT, 1024), tx2 = make_desc(smem_u32(sx + BLK_BYTES), SLOT, 1024);
     const uint64_t tdl = make_desc(smem_u32(sdl), BLK_BYTES, 1024);
-    // chunk 0 of GEMM2 when block 0 sits in the spare slot: blocks {spare, 1} are two block strides apart
-    const uint64_t tx1_alt = make_desc(smem_u32(sx1 - BLK_BYTES), 2 * BLK_BYTES, 1024);
-    const uint64_t tx2_alt = make_desc(smem_u32(sx2 - BLK_BYTES), 2 * BLK_BYTES, 1024);
+    // chunk 0 of GEMM2 when block 0 sits in the spare slot: slots {-1, 1} are two slot strides apart
+    const uint64_t tx1_alt = make_desc(smem_u32(sx - SLOT), 2 * SLOT, 1024);
+    const uint64_t tx2_alt = make_desc(smem_u32(sx - SLOT + BLK_BYTES), 2 * SLOT, 1024);
     const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
     int phase = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
@@ -590,12 +595,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         if (lane == 0) BJX_TRACE(it, 16 + b);
         if (!(ablate & 1) && elect_one()) {
           const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
-          const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(BLK_BYTES >> 4)) : toff;  // X block (spare slot for b = 0)
+          const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(SLOT >> 4)) : (uint64_t)((b * SLOT) >> 4);  // X slot
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + ACC1_COL, dx1 + boff + 2 * k, dth + toff + 2 * k, ID_G1_N64, (b | k) != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dx2 + boff + 2 * k, dth + toff + 2 * k, ID_G1_N32, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
         }
         __syncwarp();
       }
@@ -607,7 +609,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if (lane == 0) BJX_TRACE(it, 25);
       for (int ch = 0; ch < NCH; ++ch) {
         if (elect_one()) {
-          const uint64_t coff = (uint64_t)((2 * ch * BLK_BYTES) >> 4);
+          const uint64_t coff = (uint64_t)((2 * ch * SLOT) >> 4);
           const uint64_t a1 = (ch == 0 && alt) ? tx1_alt : tx1 + coff;
           const uint64_t a2 = (ch == 0 && alt) ? tx2_alt : tx2 + coff;
 #pragma unroll
@@ -631,11 +633,18 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     __syncwarp();
   } else {
     // ===================================================== epilogue =====================================================
+    // GEMM1 is an M = 128 UMMA: TMEM lane 64 * part + r holds, for data row r, the partial logits of the x1 terms
+    // (part = 0) or of the x2 terms (part = 1), columns [x*t1 (32) | x*t2 (32)].  The warp of sub-partition q (lanes
+    // 32q..32q+31) and its partner in sub-partition q ^ 2 hold the two parts of the same 32 rows; they swap halves of
+    // their 16 samples through shared memory, so that every thread finishes 8 (row, sample) pairs.
     const int q = warp & 3;
     const int h = (warp - tcp::EPI_WARP0) >> 2;
-    const int hi = lane >> 4;
-    const int r = 16 * q + (lane & 15);
-    const int s0 = h * 16 + hi * 8;
+    const int part = q >> 1;
+    const int r = 32 * (q & 1) + lane;
+    const int s0 = h * 16 + part * 8;
+    float* xch_mine = xch + (size_t)(warp - tcp::EPI_WARP0) * 256;                   // what the partner wrote for me
+    float* xch_peer = xch + (size_t)((warp - tcp::EPI_WARP0) ^ 2) * 256;             // (warp index ^ 2 flips q's high bit)
+    const int pair_bar = 2 + 2 * (q & 1) + h;                                        // named barriers 2..5, 64 threads each
     float stat[8], prod[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -697,10 +706,15 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       float eta[8], g[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        // samples [8 * (1 - part), +8) of my 16 go to the partner, [8 * part, +8) stay
         const float lo = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
-        const float up = __shfl_sync(0xffffffffu, __uint_as_float(va[8 + j]) + __uint_as_float(vb[8 + j]), lane & 15);
-        eta[j] = hi ? up : lo;
+        const float up = __uint_as_float(va[8 + j]) + __uint_as_float(vb[8 + j]);
+        xch_peer[j * 32 + lane] = part ? lo : up;
+        eta[j] = part ? up : lo;
       }
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+#pragma unroll
+      for (int j = 0; j < 8; ++j) eta[j] += xch_mine[j * 32 + lane];
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
       if (ablate & 4) {
 #pragma unroll
@@ -753,8 +767,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       {
         uint8_t* rowp = sdl + r * 128;
         const int sw = r & 7;
-        *reinterpret_cast<uint4*>(rowp + (((2 * h + hi) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
-        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + hi) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * h + part) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + part) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -766,8 +780,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     for (int j = 0; j < 8; ++j) {
       float v = stat[j] - logf(prod[j]);
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((lane & 15) == 0) sred[q * NS + s0 + j] = v;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sred[q * NS + s0 + j] = v;  // the other (q, sample) slots stay zero
     }
     asm volatile("bar.sync 1, %0;" ::"r"(tcp::EPI_WARPS * 32) : "memory");
     if (warp == tcp::EPI_WARP0 && lane < S) {
@@ -839,7 +853,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   const size_t smem = tc_smem_bytes(nblk);
   if (a.x_planes != nullptr) {
     // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
-    const size_t smem = (size_t)(3 * nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 1024;
+    const size_t smem = (size_t)(3 * nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 + 8 * 256 * sizeof(float) + 1024;
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");
