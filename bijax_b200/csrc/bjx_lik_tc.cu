@@ -716,32 +716,44 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) eta[j] += xch_mine[j * 32 + lane];
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
+      // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
+      // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
+      const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
       if (ablate & 4) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
       } else if (logit) {
-        // one exponential per datum, stage by stage over the 8 values so that the MUFU latencies overlap
-        // The special-function pipe (16 lanes per clock per SM) bounds this stage, so only the exponential uses it:
-        // 1 / (1 + e) with 1 + e in (1, 2] is three Newton steps on the FMA pipe from the minimax line 24/17 - 8/17 x
-        // (relative error 1/17 -> 3.5e-3 -> 1.2e-5 -> 1.5e-10).
+        // one exponential per datum: e = exp(-|x|); sigmoid = (x >= 0 ? 1 : e) / (1 + e); softplus = max(x, 0) + log(1 + e),
+        // the logs taken of a running product (every 32 tiles)
         float e[8], ope[8], rc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] = __expf(-fabsf(eta[j]));
 #pragma unroll
         for (int j = 0; j < 8; ++j) ope[j] = 1.0f + e[j];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rc[j] = fmaf(-0.47058824f, ope[j], 1.4117647f);
+        for (int j = 0; j < 8; ++j) rc[j] = __fdividef(1.0f, ope[j]);
+        if (all_ok) {
 #pragma unroll
-        for (int it2 = 0; it2 < 3; ++it2) {
+          for (int j = 0; j < 8; ++j) {
+            stat[j] += ycur * eta[j] - fmaxf(eta[j], 0.0f);
+            prod[j] *= ope[j];
+            g[j] = ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j]);
+          }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rc[j] = fmaf(rc[j], fmaf(-ope[j], rc[j], 1.0f), rc[j]);
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = row_ok && (s0 + j) < S;
+            stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
+            prod[j] *= ok ? ope[j] : 1.0f;
+            g[j] = ok ? (ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j])) : 0.0f;
+          }
         }
+      } else if (all_ok) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool ok = row_ok && (s0 + j) < S;
-          stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
-          prod[j] *= ok ? ope[j] : 1.0f;
-          g[j] = ok ? (ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j])) : 0.0f;
+          const float rr = ycur - eta[j];
+          stat[j] = fmaf(rr, rr, stat[j]);
+          g[j] = rr;
         }
       } else {
 #pragma unroll
