@@ -583,27 +583,34 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const uint64_t tx2_alt = make_desc(smem_u32(sx - SLOT + BLK_BYTES), 2 * SLOT, 1024);
     const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
     int phase = 0;
+    // GEMM1 of one block into the logits accumulator of tile t's parity (two accumulators: block 0 of the next tile is
+    // issued right after this tile's logits are committed, so it runs while the epilogue warps work on them)
+    auto gemm1_block = [&](int64_t t, int b) {
+      const bool alt = (t & 1) != 0;
+      if (b == 0)
+        mbar_wait(&bars->x_full[alt ? 8 : 0], (uint32_t)((t >> 1) & 1));
+      else
+        mbar_wait(&bars->x_full[b], (uint32_t)(t & 1));
+      if (lane == 0) BJX_TRACE(t, 16 + b);
+      if (!(ablate & 1) && elect_one()) {
+        const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
+        const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(SLOT >> 4)) : (uint64_t)((b * SLOT) >> 4);  // X slot
+        const uint32_t acc = tmem + ACC1_COL + (alt ? NB : 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(acc, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
+      }
+      __syncwarp();
+    };
+    if (my_tiles > 0) gemm1_block(0, 0);
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const bool alt = (it & 1) != 0;
       const int idx0 = alt ? 8 : 0;
-      for (int b = 0; b < NBLK; ++b) {
-        if (b == 0)
-          mbar_wait(&bars->x_full[idx0], (uint32_t)((it >> 1) & 1));
-        else
-          mbar_wait(&bars->x_full[b], ph);
-        if (lane == 0) BJX_TRACE(it, 16 + b);
-        if (!(ablate & 1) && elect_one()) {
-          const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
-          const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(SLOT >> 4)) : (uint64_t)((b * SLOT) >> 4);  // X slot
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + ACC1_COL, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
-        }
-        __syncwarp();
-      }
+      for (int b = 1; b < NBLK; ++b) gemm1_block(it, b);
       if (elect_one()) umma_commit(&bars->acc1_full);
       __syncwarp();
       if (lane == 0) BJX_TRACE(it, 24);
+      if (it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
       mbar_wait(&bars->dl_full, ph);
       tc_fence_after();
       if (lane == 0) BJX_TRACE(it, 25);
@@ -700,8 +707,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       tc_fence_after();
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
       uint32_t va[16], vb[16];
-      tmem_ld16(t_lane + ACC1_COL + h * 16, va);
-      tmem_ld16(t_lane + ACC1_COL + NS + h * 16, vb);
+      const uint32_t acc1 = t_lane + ACC1_COL + ((it & 1) ? NB : 0);  // the logits accumulator of this tile's parity
+      tmem_ld16(acc1 + h * 16, va);
+      tmem_ld16(acc1 + NS + h * 16, vb);
       tmem_ld_wait();
       float eta[8], g[8];
 #pragma unroll
