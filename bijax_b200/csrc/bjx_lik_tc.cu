@@ -563,8 +563,10 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
           tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
           tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+          // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue it
+          // now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
+          if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
         }
-        if (it + 1 < my_tiles) issue_block0(it + 1);  // into the other slot: free since chunk 0 of GEMM2(it - 1)
         if (pf_mode == 1 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
       }
     }
