@@ -419,6 +419,34 @@ def test_packed_fill_triangular_parameterisation():
     assert torch.equal(q["posterior"]["scale_tril"].grad, gp["posterior"]["scale_tril"])
 
 
+def test_fresh_minibatches_fall_back_to_raw_fp32_and_a_repeated_dataset_is_prepared_again():
+    """advi.py:92 scales a minibatch to the full data size; a caller passing a NEW tensor every step must not pay a dataset
+    preparation per step: after two consecutive cache misses the engine reads raw fp32 X, and prepares again once a tensor
+    repeats.  Results do not depend on which route was taken (two-pass path: bit-identical)."""
+    from bijax_b200 import random as br
+
+    N, D, S = 2048, 128, 40
+    X, y = _device_logistic(4 * N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), kernel="tcgen05_gemm_two_pass")
+    eng = model._engine_for({})[0]
+    ref_model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), kernel="tcgen05_gemm_two_pass", prepare_dataset=False)
+    ref = ref_model._engine_for({})[0]
+    loc, raw = torch.zeros(D, device=X.device), torch.full((D,), -2.0, device=X.device)
+    used_planes = []
+    for i in range(4):
+        xb, yb = X[i * N : (i + 1) * N].clone(), y[i * N : (i + 1) * N].clone()  # a fresh tensor per step
+        a = eng.step(br.PRNGKey(i), loc, raw, None, xb, yb, 4.0, S).clone()
+        used_planes.append(eng._planes is not None)
+        b = ref.step(br.PRNGKey(i), loc, raw, None, xb, yb, 4.0, S).clone()
+        assert torch.equal(a, b)
+    assert used_planes == [True, True, False, False]
+    xb, yb = X[:N].clone(), y[:N].clone()
+    for i in range(3):  # the same tensor again and again: a dataset
+        eng.step(br.PRNGKey(9), loc, raw, None, xb, yb, 4.0, S)
+    assert eng._planes is not None
+
+
 def _tc_engine(D, lik=None, precision="auto"):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     model, _ = C.build_pair(prior, {}, lik or lk.BernoulliLogits(), precision=precision)
