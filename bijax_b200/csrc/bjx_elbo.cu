@@ -99,7 +99,8 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
     if (a.precision != BJX_PREC_FP32 && a.precision != BJX_PREC_AUTO && !tc_eligible(a) && !gemm_eligible(a))
       return fail(BJX_ERR_UNSUPPORTED, "tensor-core precision requested but the shape is outside the tcgen05 kernel's envelope");
     // the two-pass GEMM path pays for operand planes and two launches: use it when the contraction is large
-    const bool gemm_worth = (double)a.N * (double)a.S * (double)a.Dw >= 134217728.0 || a.precision == BJX_PREC_BF16X2;
+    const bool gemm_worth = (double)a.N * (double)a.S * (double)a.Dw >= 134217728.0 || a.precision == BJX_PREC_BF16X2 ||
+                            a.precision == BJX_PREC_BF16X3;
     if (want_tc && tc_eligible(a))
       p.kernel = KERNEL_TC_BF16;
     else if (want_tc && gemm_eligible(a) && gemm_worth)
@@ -200,9 +201,9 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   p.o_gbuf = take(p.kernel == KERNEL_FP32_TILED ? (size_t)a.N * a.S * sizeof(float) : 0);
   p.o_tc_theta = take(p.kernel == KERNEL_TC_BF16 ? tc_theta_bytes(a, p) : 0);
   const bool gm = p.kernel == KERNEL_TC_GEMM;
-  p.o_gm_x = take(gm && a.x_planes == nullptr ? x_planes_bytes(a.N, a.Dw) : 0);
-  p.o_gm_t = take(gm ? (size_t)2 * a.S * p.gm_Dp * 2 : 0);
-  p.o_gm_g = take(gm ? (size_t)2 * a.N * p.gm_Sp * 2 : 0);
+  p.o_gm_x = take(gm && (a.x_planes == nullptr || p.gm_nt == 3) ? x_planes_bytes(a.N, a.Dw) / 2 * p.gm_nt : 0);
+  p.o_gm_t = take(gm ? (size_t)p.gm_nt * a.S * p.gm_Dp * 2 : 0);
+  p.o_gm_g = take(gm ? (size_t)p.gm_nt * a.N * p.gm_Sp * 2 : 0);
   p.o_fr_tc = take(p.fr_tc ? fullrank_tc_bytes(a) : 0);
   p.o_stage_key = take(16);
   p.o_stage_params = take((size_t)(a.D + p.Pn + a.K) * sizeof(float));

@@ -21,7 +21,7 @@ struct Plan {
   // tensor-core
   int tc_ctas, tc_terms;
   // two-pass TMA-fed tensor-core GEMM path (bjx_gemm_tc.cu)
-  int gm_grid1, gm_grid2, gm_splits, gm_cg;  // gm_cg = 2: CTA pairs (cta_group::2)
+  int gm_grid1, gm_grid2, gm_splits, gm_cg, gm_nt;  // gm_cg = 2: CTA pairs (cta_group::2); gm_nt = split terms per operand
   int64_t gm_Dp, gm_Sp;  // padded plane pitches (elements)
   int fr_tc;             // full-rank contractions on the tensor cores
   // byte offsets into the workspace

@@ -53,7 +53,8 @@ struct EpiArgs {
   int family;
   __nv_bfloat16* g1;
   __nv_bfloat16* g2;
-  int64_t g_pitch;  // elements
+  __nv_bfloat16* g3;  // third split term (NT = 3, BJX_PREC_BF16X3) or null
+  int64_t g_pitch;    // elements
   float* statpart;  // [4 * grid][S]
   // EPI_LIK2
   float* Gpart;  // [splits][S][Dw]
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           tmem_ld32(t_acc + c * 32, v);
           tmem_ld_wait();
           float f[32];
-          uint32_t p1[16], p2[16];
+          uint32_t p1[16], p2[16], p3[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float g[2];
@@ -316,6 +317,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
               }
             }
             split2(g[0], g[1], p1[j >> 1], p2[j >> 1]);
+            if (NT == 3) {  // third term: what the first two left over
+              const float q0 = (g[0] - __uint_as_float(p1[j >> 1] << 16)) - __uint_as_float(p2[j >> 1] << 16);
+              const float q1 = (g[1] - __uint_as_float(p1[j >> 1] & 0xFFFF0000u)) - __uint_as_float(p2[j >> 1] & 0xFFFF0000u);
+              p3[j >> 1] = pack_bf16x2(q0, q1);
+            }
           }
           if (row_ok) {
             uint4* d1 = reinterpret_cast<uint4*>(e.g1 + r * e.g_pitch + s0);
@@ -324,6 +330,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {
               d1[k] = make_uint4(p1[4 * k], p1[4 * k + 1], p1[4 * k + 2], p1[4 * k + 3]);
               d2[k] = make_uint4(p2[4 * k], p2[4 * k + 1], p2[4 * k + 2], p2[4 * k + 3]);
+            }
+            if (NT == 3) {
+              uint4* d3 = reinterpret_cast<uint4*>(e.g3 + r * e.g_pitch + s0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) d3[k] = make_uint4(p3[4 * k], p3[4 * k + 1], p3[4 * k + 2], p3[4 * k + 3]);
             }
           }
           const float tot = transpose_reduce32(f, lane);
@@ -593,11 +604,11 @@ bool gemm_eligible(const BjxElboArgs& a) {
   if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
   if (a.Dw < 64 || a.S < 1 || a.S > 4096 || a.N < 1) return false;
   if (a.N >= (1ll << 31) - 256 || a.Dw >= (1ll << 31) - 256) return false;  // 32-bit TMA coordinates
-  if (a.precision == BJX_PREC_BF16X3) return false;
-  return true;
+  return true;  // BJX_PREC_BF16X3 (three-term split, fp32-accurate) runs here with 128-wide tiles
 }
 
-static int lik1_bn(int64_t S) { return S <= 64 ? 64 : (S <= 128 ? 128 : 256); }
+static int gemm_nt(const BjxElboArgs& a) { return a.precision == BJX_PREC_BF16X3 ? 3 : 2; }
+static int lik1_bn(int64_t S, int nt = 2) { return nt == 3 ? 128 : (S <= 64 ? 64 : (S <= 128 ? 128 : 256)); }
 
 // CTA pairs (cta_group::2) for the widest tiles: the pair shares the B operand, which halves its shared-memory reads and
 // its TMA writes per SM -- the port both compete for (BJX_GEMM_CG=1 keeps single-CTA tiles, for A/B measurements)
@@ -614,8 +625,9 @@ static int gemm_cg(int bn) {
 int gemm_plan(const BjxElboArgs& a, Plan& p) {
   const int sms = sm_count();
   if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
-  const int bn = lik1_bn(a.S);
-  const int cg = gemm_cg(bn);
+  const int nt = gemm_nt(a);
+  const int bn = lik1_bn(a.S, nt);
+  const int cg = nt == 3 ? 1 : gemm_cg(bn);
   const int groups = sms / cg;  // CTAs, or CTA pairs
   const int bmc = 128 * cg;
   const int64_t tiles1 = ((a.N + bmc - 1) / bmc) * ((a.S + bn - 1) / bn);
@@ -623,13 +635,14 @@ int gemm_plan(const BjxElboArgs& a, Plan& p) {
   const int64_t tiles2 = ((a.Dw + bmc - 1) / bmc) * ((a.S + bn - 1) / bn);
   const int64_t kb_total = (a.N + 63) / 64;
   int64_t splits = tiles2 >= groups ? 1 : groups / tiles2;
-  const int64_t max_splits = (kb_total + 15) / 16;  // at least one full virtual tile per split
+  const int64_t max_splits = (kb_total + 15) / 16;  // at least one full (2-term) virtual tile per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.gm_splits = (int)splits;
   int64_t units = tiles2 * splits;
   p.gm_grid2 = cg * (int)(units < groups ? units : groups);
   p.gm_cg = cg;
+  p.gm_nt = nt;
   p.gm_Dp = gemm::pad64(a.Dw);
   p.gm_Sp = gemm::pad64(a.S);
   return BJX_OK;
@@ -641,38 +654,51 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
   float* Gpart = (float*)(ws + p.o_Gpart);
   float* statpart = (float*)(ws + p.o_statpart);
   const int64_t Dp = p.gm_Dp, Sp = p.gm_Sp;
-  const bool prepared = a.x_planes != nullptr;  // bjx_prepare_x_planes output for exactly this X (caller's promise)
-  __nv_bfloat16* x1 = prepared ? (__nv_bfloat16*)a.x_planes : (__nv_bfloat16*)(ws + p.o_gm_x);
-  __nv_bfloat16* x2 = x1 + (size_t)a.N * Dp;
-  __nv_bfloat16* t1 = (__nv_bfloat16*)(ws + p.o_gm_t);
-  __nv_bfloat16* t2 = t1 + (size_t)a.S * Dp;
-  __nv_bfloat16* g1 = (__nv_bfloat16*)(ws + p.o_gm_g);
-  __nv_bfloat16* g2 = g1 + (size_t)a.N * Sp;
+  const int nt = p.gm_nt;  // split terms per operand: 2 (BJX_PREC_BF16X2 / auto) or 3 (BJX_PREC_BF16X3, fp32-accurate)
+  // prepared planes hold two terms: the three-term mode always splits inside the step
+  const bool prepared = a.x_planes != nullptr && nt == 2;
+  __nv_bfloat16* xp[3];
+  __nv_bfloat16* tp[3];
+  __nv_bfloat16* gp[3];
+  for (int t = 0; t < 3; ++t) {
+    xp[t] = (prepared ? (__nv_bfloat16*)a.x_planes : (__nv_bfloat16*)(ws + p.o_gm_x)) + (size_t)t * a.N * Dp;
+    tp[t] = (__nv_bfloat16*)(ws + p.o_gm_t) + (size_t)t * a.S * Dp;
+    gp[t] = (__nv_bfloat16*)(ws + p.o_gm_g) + (size_t)t * a.N * Sp;
+  }
 
   // operand planes
   if (!prepared) {
-    int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, x1, st);
-    if (rc) return rc;
+    if (nt == 2) {
+      int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, xp[0], st);
+      if (rc) return rc;
+    } else {
+      const int64_t total = a.N * (Dp / 8);
+      k_split_planes<3, SrcPlain><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(SrcPlain{a.X, a.ldx}, a.N, a.Dw, Dp, xp[0], xp[1], xp[2]);
+      BJX_LAUNCH_CHECK("k_split_planes(X)");
+    }
   }
   {
     const int64_t tt = a.S * (Dp / 8);
-    k_split_planes<2, SrcPlain><<<(unsigned)((tt + 255) / 256), 256, 0, st>>>(SrcPlain{theta + a.w_offset, a.D}, a.S, a.Dw, Dp, t1, t2, nullptr);
+    if (nt == 2)
+      k_split_planes<2, SrcPlain><<<(unsigned)((tt + 255) / 256), 256, 0, st>>>(SrcPlain{theta + a.w_offset, a.D}, a.S, a.Dw, Dp, tp[0], tp[1], nullptr);
+    else
+      k_split_planes<3, SrcPlain><<<(unsigned)((tt + 255) / 256), 256, 0, st>>>(SrcPlain{theta + a.w_offset, a.D}, a.S, a.Dw, Dp, tp[0], tp[1], tp[2]);
     BJX_LAUNCH_CHECK("k_split_planes(theta)");
   }
   BJX_CUDA_TRY(cudaMemsetAsync(statpart, 0, (size_t)p.PS * a.S * sizeof(float), st));
   BJX_CUDA_TRY(cudaMemsetAsync(Gpart, 0, (size_t)p.PG * a.S * a.Dw * sizeof(float), st));
+  const int bn = lik1_bn(a.S, nt);
+  const int cg = p.gm_cg, bmc = 128 * cg;
 
   // ---- pass 1: eta, link, g planes, stat
   {
-    const int bn = lik1_bn(a.S);
     Params P;
     memset(&P, 0, sizeof(P));
     int rc;
-    if ((rc = make_map(&P.mapA[0], x1, a.N, a.Dw, Dp, 64, 128))) return rc;
-    if ((rc = make_map(&P.mapA[1], x2, a.N, a.Dw, Dp, 64, 128))) return rc;
-    const int cg = p.gm_cg, bmc = 128 * cg;
-    if ((rc = make_map(&P.mapB[0], t1, a.S, a.Dw, Dp, 64, bn / cg))) return rc;  // a pair loads half of the B tile per CTA
-    if ((rc = make_map(&P.mapB[1], t2, a.S, a.Dw, Dp, 64, bn / cg))) return rc;
+    for (int t = 0; t < nt; ++t) {
+      if ((rc = make_map(&P.mapA[t], xp[t], a.N, a.Dw, Dp, 64, 128))) return rc;
+      if ((rc = make_map(&P.mapB[t], tp[t], a.S, a.Dw, Dp, 64, bn / cg))) return rc;  // a pair loads half of the B tile per CTA
+    }
     P.sched.tiles_m = (int)((a.N + bmc - 1) / bmc);
     P.sched.tiles_n = (int)((a.S + bn - 1) / bn);
     P.sched.splits = 1;
@@ -684,11 +710,13 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     P.epi.n_rows = a.N;
     P.epi.S = (int)a.S;
     P.epi.family = a.likelihood;
-    P.epi.g1 = g1;
-    P.epi.g2 = g2;
+    P.epi.g1 = gp[0];
+    P.epi.g2 = gp[1];
+    P.epi.g3 = nt == 3 ? gp[2] : nullptr;
     P.epi.g_pitch = Sp;
     P.epi.statpart = statpart;
-    if (bn == 64) rc = launch<64, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
+    if (nt == 3) rc = launch<128, 3, false, false, EPI_LIK1>(P, p.gm_grid1, st);
+    else if (bn == 64) rc = launch<64, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
     else if (bn == 128) rc = launch<128, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
     else if (cg == 2) rc = launch<256, 2, false, false, EPI_LIK1, 2>(P, p.gm_grid1, st);
     else rc = launch<256, 2, false, false, EPI_LIK1>(P, p.gm_grid1, st);
@@ -696,26 +724,27 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
   }
   // ---- pass 2: G^T[d, s] = sum_n X[n, d] g[n, s]   (A = X planes, B = g planes, both MN-major; K = data rows)
   {
-    const int bn = lik1_bn(a.S);
     Params P;
     memset(&P, 0, sizeof(P));
     int rc;
-    if ((rc = make_map(&P.mapA[0], x1, a.N, a.Dw, Dp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapA[1], x2, a.N, a.Dw, Dp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[0], g1, a.N, a.S, Sp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[1], g2, a.N, a.S, Sp, 64, 64))) return rc;
-    const int cg = p.gm_cg, bmc = 128 * cg;
+    for (int t = 0; t < nt; ++t) {
+      if ((rc = make_map(&P.mapA[t], xp[t], a.N, a.Dw, Dp, 64, 64))) return rc;
+      if ((rc = make_map(&P.mapB[t], gp[t], a.N, a.S, Sp, 64, 64))) return rc;
+    }
     P.sched.tiles_m = (int)((a.Dw + bmc - 1) / bmc);
     P.sched.tiles_n = (int)((a.S + bn - 1) / bn);
     P.sched.splits = p.gm_splits;
     P.sched.kb_total = (int)((a.N + 63) / 64);
     P.sched.kb_per_split = (P.sched.kb_total + p.gm_splits - 1) / p.gm_splits;
-    P.sched.kb_per_vtile = 16;
+    // the accumulation chain in TMEM truncates (about 1.4e-7 relative per 64-row k-block and product triple): the
+    // fp32-accurate mode hands the accumulator to the epilogue four times as often
+    P.sched.kb_per_vtile = nt == 3 ? 4 : 16;
     P.sched.tril = 0;
     P.epi.S = (int)a.S;
     P.epi.Gpart = Gpart;
     P.epi.Dw = a.Dw;
-    if (bn == 64) rc = launch<64, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
+    if (nt == 3) rc = launch<128, 3, true, true, EPI_LIK2>(P, p.gm_grid2, st);
+    else if (bn == 64) rc = launch<64, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     else if (bn == 128) rc = launch<128, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);
     else if (cg == 2) rc = launch<256, 2, true, true, EPI_LIK2, 2>(P, p.gm_grid2, st);
     else rc = launch<256, 2, true, true, EPI_LIK2>(P, p.gm_grid2, st);

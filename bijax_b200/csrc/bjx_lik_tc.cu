@@ -841,7 +841,7 @@ bool tc_eligible(const BjxElboArgs& a) {
   if (a.Dw < 128 || a.Dw > 512 || a.Dw % 128 != 0) return false;
   if (a.S < 1 || a.S > tc::NS) return false;
   if (a.ldx % 4 != 0 || ((uintptr_t)a.X & 15) != 0) return false;  // 128-bit row loads
-  if (a.precision == BJX_PREC_BF16X3) return false;                // three-term split not built yet
+  if (a.precision == BJX_PREC_BF16X3) return false;                // the three-term split runs on the two-pass GEMM path
   return true;
 }
 

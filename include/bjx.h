@@ -97,7 +97,8 @@ typedef struct BjxCoord {
 /* ---- precision of the streaming contraction ----------------------------- */
 #define BJX_PREC_AUTO 0   /* tensor-core split path when the shape allows, else fp32 CUDA cores */
 #define BJX_PREC_FP32 1   /* fp32 FFMA on CUDA cores only */
-#define BJX_PREC_BF16X3 2 /* tcgen05, X/theta/dlogit each split in 3 bf16 terms (fp32-accurate) */
+#define BJX_PREC_BF16X3 2 /* tcgen05, X/theta/dlogit each split in 3 bf16 terms, 6 products (fp32-accurate);
+                             runs on the two-pass GEMM path with 128-wide tiles */
 #define BJX_PREC_BF16X2 3 /* tcgen05, 2-term split (about 2^-17 relative per product) */
 
 typedef struct BjxElboArgs {

@@ -28,7 +28,7 @@ def engine(precision):
     e.prepare_dataset = bool(prepare)
     return e
 
-eng = engine("auto")
+eng = engine(os.environ.get("C4_PRECISION", "auto"))
 out = torch.empty(1 + D + D * D + 1, device=dev)
 for i in range(3): eng.step(keys[i], loc, M, lns, X, y, 1.0, S, out=out)
 torch.cuda.synchronize()

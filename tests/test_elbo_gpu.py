@@ -253,6 +253,28 @@ def test_two_pass_tensor_core_gemm_path(N, D, S, lik):
     _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_gemm_two_pass")
 
 
+@pytest.mark.parametrize("N,D,S,lik", [(3000, 256, 48, "logit"), (1500, 200, 130, "gauss")])
+def test_three_term_split_is_fp32_accurate(N, D, S, lik):
+    """precision="bf16x3": every operand split in three bf16 terms, six products per useful product -- the fp32-accurate
+    tensor-core mode (north_star: "3xTF32 / fp32-accurate").  Held to a 4x tighter tolerance than the 2-term default."""
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if lik == "logit":
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="bf16x3")
+        kwargs = {}
+    else:
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), precision="bf16x3")
+        kwargs = {"log_noise_scale": np.float32(math.log(0.5))}
+    loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    loss, grads = _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, 11, S, 0, expect_kernel="tcgen05_gemm_two_pass")
+    (wl, wgl, wgr, _), _ = C.oracle_step(ref, loc, raw, kwargs, y, X, 4 * N, tf.prng_key(11), S, 0)
+    C.assert_close(loss.item(), wl.item(), rtol=2.5e-6, atol_scale=2.5e-6, what="loss (3-term)")
+    C.assert_close(grads["posterior"]["loc"].cpu().numpy(), wgl.numpy(), rtol=2.5e-6, atol_scale=2.5e-6, what="d loc (3-term)")
+    C.assert_close(grads["posterior"]["scale_diag"].cpu().numpy(), wgr.numpy(), rtol=2.5e-6, atol_scale=2.5e-6, what="d rho (3-term)")
+
+
 @pytest.mark.parametrize("D,S,lik", [(128, 10, "gauss"), (200, 130, "logit"), (384, 64, "gauss")])
 def test_full_rank_contractions_on_the_tensor_cores(D, S, lik):
     """z = loc + tril(M) eps and dM = tril(sum_s gz eps^T) as TMA-fed tcgen05 GEMMs with a 3-term bf16 split (fp32-accurate);
