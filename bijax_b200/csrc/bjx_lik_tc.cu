@@ -729,61 +729,36 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
       // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
       const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
+      // Only g is on the critical path (GEMM2 waits for it): the loss bookkeeping (stat, prod) is done after the hand-over.
+      float ope[8];
       if (ablate & 4) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
       } else if (logit) {
         // one exponential per datum: e = exp(-|x|); sigmoid = (x >= 0 ? 1 : e) / (1 + e); softplus = max(x, 0) + log(1 + e),
         // the logs taken of a running product (every 32 tiles)
-        float e[8], ope[8], rc[8];
+        float e[8], rc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] = __expf(-fabsf(eta[j]));
 #pragma unroll
         for (int j = 0; j < 8; ++j) ope[j] = 1.0f + e[j];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rc[j] = __fdividef(1.0f, ope[j]);
-        if (all_ok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            stat[j] += ycur * eta[j] - fmaxf(eta[j], 0.0f);
-            prod[j] *= ope[j];
-            g[j] = ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const bool ok = row_ok && (s0 + j) < S;
-            stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
-            prod[j] *= ok ? ope[j] : 1.0f;
-            g[j] = ok ? (ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j])) : 0.0f;
-          }
-        }
-      } else if (all_ok) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float rr = ycur - eta[j];
-          stat[j] = fmaf(rr, rr, stat[j]);
-          g[j] = rr;
+          const float gj = ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j]);
+          g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? gj : 0.0f;
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool ok = row_ok && (s0 + j) < S;
           const float rr = ycur - eta[j];
-          stat[j] += ok ? rr * rr : 0.0f;
-          g[j] = ok ? rr : 0.0f;
+          g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? rr : 0.0f;
         }
       }
       uint32_t e1[4], e2[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
-      if ((it & 31) == 31) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          stat[j] -= logf(prod[j]);
-          prod[j] = 1.0f;
-        }
-      }
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 34);
       mbar_wait(&bars->dl_empty, ph ^ 1);
       {
@@ -796,6 +771,27 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dl_full);
+      // ---- off the critical path: log-likelihood bookkeeping
+      if (!(ablate & 4)) {
+        if (logit) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = all_ok || (row_ok && (s0 + j) < S);
+            stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
+            prod[j] *= ok ? ope[j] : 1.0f;
+          }
+          if ((it & 31) == 31) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              stat[j] -= logf(prod[j]);
+              prod[j] = 1.0f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) stat[j] = fmaf(g[j], g[j], stat[j]);  // g = y - eta, already masked
+        }
+      }
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 35);
     }
 #pragma unroll
