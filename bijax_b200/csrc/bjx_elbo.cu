@@ -77,6 +77,9 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
               a.scale_bijector);
   BJX_REQUIRE(a.threefry_layout == BJX_LAYOUT_LEGACY || a.threefry_layout == BJX_LAYOUT_PARTITIONABLE,
               "unknown threefry layout %d", a.threefry_layout);
+  BJX_REQUIRE(a.point_mode >= BJX_POINT_OFF && a.point_mode <= BJX_POINT_MAP, "unknown point_mode %d", a.point_mode);
+  BJX_REQUIRE(a.point_mode == BJX_POINT_OFF || (a.S == 1 && a.S_total == 0 && a.vi_type == BJX_VI_MEAN_FIELD),
+              "point evaluation needs S == 1, no sample sharding and vi_type = mean field (raw_scale is ignored)");
   BJX_REQUIRE(a.S_total == 0 || (a.s_offset >= 0 && a.s_offset + a.S <= a.S_total), "sample shard [s_offset, s_offset+S) must lie in [0, S_total)");
   BJX_REQUIRE((a.S_total ? a.S_total : a.S) * a.D <= 0xFFFFFFFFll, "S*D must fit the 32-bit legacy counter");
   const int sms = sm_count();
@@ -224,7 +227,8 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
                                                   float* __restrict__ theta, float* __restrict__ bprime,
                                                   float* __restrict__ gprior, float* __restrict__ qp_part,
                                                   float* __restrict__ eps_out, int64_t probs_coord,
-                                                  float4* __restrict__ probs_aux, int64_t s_offset, int64_t S_total) {
+                                                  float4* __restrict__ probs_aux, int64_t s_offset, int64_t S_total,
+                                                  int point_mode) {
   __shared__ float red[32];
   const int64_t total = S * D;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -241,21 +245,23 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
       const uint32_t* k = key_index ? key + 2 * (*key_index) : key;  // device-resident loop: key = keys[step counter]
       // sample sharding: the flat index and the stream length are those of the unsharded (S_total, D) draw
       const uint32_t bits = random_bits_at(k[0], k[1], (uint64_t)(i + s_offset * D), (uint64_t)(S_total * D), layout);
-      eps = bits_to_normal(bits);
+      eps = point_mode ? 0.0f : bits_to_normal(bits);
       eps_buf[i] = eps;
       const float rho = raw[d];
       const ScaleEval sc = eval_scale(rho, scale_bij);
-      z = loc[d] + sc.sigma * eps;
+      z = point_mode ? loc[d] : loc[d] + sc.sigma * eps;
       logsig = scale_bij == BJX_SCALE_EXP ? rho : logf(sc.sigma);
     }
     if (eps_out) eps_out[i] = eps;
     const CoordEval ce = eval_coord(z, coords[d]);
     theta[i] = ce.theta;
     bprime[i] = ce.dtheta;
-    gprior[i] = -ce.dlogp;
+    gprior[i] = point_mode == BJX_POINT_MAP ? -(ce.dlogp - ce.dldj) : -ce.dlogp;
     if (d == probs_coord) probs_aux[i / D] = make_float4(ce.lt, ce.l1t, ce.dlt, ce.dl1t);
     // q.log_prob per coordinate (z - loc)/sigma == eps, minus the unconstrained prior's log density
     term = (-0.5f * eps * eps - logsig - BJX_HALF_LOG_2PI) - ce.logp;
+    if (point_mode == BJX_POINT_LOG_JOINT) term = -ce.logp;               // no variational term
+    if (point_mode == BJX_POINT_MAP) term = -(ce.logp - ce.ldj);          // prior density of theta = b(z), map.py:30
   }
   const float t = block_sum(term, red);
   if (threadIdx.x == 0) qp_part[blockIdx.x] = t;
@@ -414,6 +420,7 @@ struct TailArgs {
   int64_t S, D, Dw, w_off, N;
   int vi_type, scale_bij, likelihood, noise_src, noise_index;
   float noise_value, ll_scale, prior_weight;
+  int point_mode;        // BJX_POINT_*: d raw_scale is zero
   float entropy_weight;  // weight of the per-step constant -d log sigma / d raw (once per step across sample shards)
   int64_t S_total;       // samples of the whole step (means divide by this)
 };
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
     out[1 + d] = acc_mu;
     if (t.vi_type == BJX_VI_MEAN_FIELD) {
       const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
-      out[1 + t.D + d] = acc_rho * sc.dsigma - t.entropy_weight * sc.dlogsigma;
+      out[1 + t.D + d] = t.point_mode ? 0.0f : acc_rho * sc.dsigma - t.entropy_weight * sc.dlogsigma;
     }
   }
 }
@@ -527,11 +534,11 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
     }
     k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                     a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
-                                                    probs_coord, aux, s_offset, S_total);
+                                                    probs_coord, aux, s_offset, S_total, a.point_mode);
   } else {
     k_prologue<false><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, a.S, a.D, a.scale_bijector,
                                                      a.threefry_layout, eps, nullptr, theta, bprime, gprior, qp, a.eps_out,
-                                                     probs_coord, aux, s_offset, S_total);
+                                                     probs_coord, aux, s_offset, S_total, a.point_mode);
   }
   BJX_LAUNCH_CHECK("k_prologue");
   return BJX_OK;
@@ -589,7 +596,8 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   t.vi_type = a.vi_type; t.scale_bij = a.scale_bijector; t.likelihood = a.likelihood;
   t.noise_src = a.noise_src; t.noise_index = a.noise_index; t.noise_value = a.noise_value;
   t.ll_scale = a.ll_scale; t.prior_weight = a.prior_weight;
-  t.entropy_weight = a.S_total ? a.entropy_weight : a.prior_weight;
+  t.entropy_weight = a.point_mode ? 0.0f : (a.S_total ? a.entropy_weight : a.prior_weight);
+  t.point_mode = a.point_mode;
   t.S_total = a.S_total ? a.S_total : a.S;
   float* gz = a.vi_type == BJX_VI_FULL_RANK ? (float*)(ws + p.o_gz) : nullptr;
   k_tail<<<(unsigned)((a.D + 7) / 8), 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),

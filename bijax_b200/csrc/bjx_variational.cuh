@@ -36,6 +36,8 @@ struct CoordEval {
   float dtheta;   // d theta / d z
   float logp;     // log p(b(z)) + fldj_b(z)   (density of z under the unconstrained prior, core.py:117)
   float dlogp;    // d logp / d z
+  float ldj;      // fldj_b(z) alone and its z-derivative (MAP.neg_log_joint uses the prior density WITHOUT it, map.py:30)
+  float dldj;
   // log(theta), log(1 - theta) and their z-derivatives, free of the saturation of sigmoid in fp32 (used when theta
   // feeds tfd.Bernoulli(probs=theta): the coin-toss likelihood)
   float lt, l1t, dlt, dl1t;
@@ -110,6 +112,8 @@ __device__ __forceinline__ CoordEval eval_coord(float z, const BjxCoord c) {
   }
   r.logp = lp + ldj;
   r.dlogp = dlp_dz + dldj;
+  r.ldj = ldj;
+  r.dldj = dldj;
   if (last_op == BJX_BIJ_SIGMOID) {
     r.lt = -softplus_f(-x_in_last);
     r.l1t = -softplus_f(x_in_last);

@@ -60,6 +60,7 @@ class ElboEngine:
         self._planes_key = None
         self._planes_misses = 0
         self._last_raw_key = None
+        self._point_key: Optional[torch.Tensor] = None
         self._resolve_likelihood()
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -238,6 +239,43 @@ class ElboEngine:
                 self.lib.bjx_elbo_step_host(C.byref(a), key_host.ctypes.data, params_host.data_ptr(), out_host.data_ptr(), nv.current_stream_ptr())
             )
         return out_host
+
+    def point_step(self, z, X, y, ll_scale, mode, out=None) -> torch.Tensor:
+        """Point evaluation at the unconstrained value z [D] (BjxElboArgs.point_mode): packed [value | d value / d z | 0...],
+        value = -(log prior + ll_scale * log likelihood) with or without the bijectors' log-det-Jacobian
+        (MCMC.log_joint, mcmc.py:30-34 / MAP.neg_log_joint, map.py:27-33)."""
+        if self.vi_type != nv.VI_MEAN_FIELD or self.K:
+            raise NotImplementedError("point evaluation runs on a mean-field engine without trainable kwargs")
+        dev = self.device
+        z = self._f32(z, dev).reshape(-1)
+        if z.numel() != self.D:
+            raise ValueError(f"z must have {self.D} elements")
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(1, N, ldx if ldx else max(self.Dw, 1), ll_scale, 1.0, nv.LAYOUT_LEGACY)
+        a.point_mode = int(mode)
+        if self._point_key is None:
+            self._point_key = torch.zeros(2, dtype=torch.uint32, device=dev)
+        a.key, a.loc, a.raw_scale = self._point_key.data_ptr(), z.data_ptr(), z.data_ptr()  # raw_scale is ignored
+        a.X = X.data_ptr() if X is not None else None
+        a.y = y.data_ptr()
+        if out is None:
+            out = torch.empty(1 + 2 * self.D, dtype=torch.float32, device=dev)
+        a.out = out.data_ptr()
+        a.x_planes = self._x_planes(a, X)
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(dev):
+            nv.check(self.lib.bjx_elbo_step(C.byref(a), nv.current_stream_ptr()))
+        return out
+
+    def point_transform(self, z) -> torch.Tensor:
+        """theta = bijector(z) for one unconstrained vector (transform_tree, core.py:154-155): the fused prologue with a zero scale."""
+        dev = self.device
+        z = self._f32(z, dev).reshape(-1)
+        zero_scale = torch.full((self.D,), float("-inf") if self.scale_bijector == nv.SCALE_EXP else 0.0, device=dev)
+        if self._point_key is None:
+            self._point_key = torch.zeros(2, dtype=torch.uint32, device=dev)
+        return self.posterior_sample(self._point_key, z, zero_scale, 1).reshape(-1)
 
     def posterior_log_prob(self, theta: torch.Tensor, loc, raw_scale) -> torch.Tensor:
         """log q(theta_i) for constrained samples theta [n, D] in the flat latent layout (Posterior.log_prob, core.py:57-71)."""

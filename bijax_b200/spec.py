@@ -148,7 +148,7 @@ class LatentSpec:
             node = out
             for k in p[:-1]:
                 node = node.setdefault(k, {})
-            node[p[-1]] = flat[..., o : o + n].reshape(*flat.shape[:-1], *shp)
+            node[p[-1]] = flat[..., o : o + n].reshape(tuple(flat.shape[:-1]) + tuple(shp))
         return out
 
 

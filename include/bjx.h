@@ -163,8 +163,20 @@ typedef struct BjxElboArgs {
   int64_t S_total;
   int64_t s_offset;
   float entropy_weight;
-  float reserved2;
+
+  /* optional (ABI 2): POINT evaluation at z = loc (no sampling, no variational term) -- the sibling inference classes on
+   * the same likelihood kernels.  S must be 1; raw_scale is ignored and its gradient block is zero.
+   *   BJX_POINT_LOG_JOINT : out = -(log p~(z) + ll_scale * ll(b(z)))   = -MCMC.log_joint    (mcmc.py:30-34)
+   *   BJX_POINT_MAP       : out = -(log p(b(z)) + ll_scale * ll(b(z))) = MAP.neg_log_joint  (map.py:27-33; prior density
+   *                         of the constrained value, no log-det-Jacobian)
+   * and d out / d z in the `d loc` block. */
+  int32_t point_mode;
 } BjxElboArgs;
+
+#define BJX_POINT_OFF 0
+#define BJX_POINT_LOG_JOINT 1
+#define BJX_POINT_MAP 2
+
 
 /* ---- library ------------------------------------------------------------ */
 BJX_API int bjx_abi_version(void);

@@ -295,6 +295,22 @@ class ADVIRef:
             q = -0.5 * (zz * zz).sum() - torch.log(torch.abs(torch.diagonal(tril))).sum() - 0.5 * D * LOG_2PI
         return q + ildj
 
+    def map_neg_log_joint(self, z, outputs, inputs):
+        """MAP.neg_log_joint (map.py:27-33) at the flat unconstrained vector z: transform_tree, log_prob_dist of the PRIOR at
+        the constrained value (no log-det-Jacobian), likelihood.log_prob(outputs).sum(); returns -(log_prior + log_lik)."""
+        tree = self.unravel(z)
+        theta = {k: self.bijector[k].forward(tree[k]) for k in self.names}
+        log_prior = sum(self.prior[k].log_prob(theta[k]).sum() for k in self.names)
+        return -(log_prior + self.log_likelihood_fn(theta, outputs, inputs))
+
+    def mcmc_log_joint(self, z, outputs, inputs):
+        """MCMC.log_joint (mcmc.py:30-34): log_prob_dist(approx_normal_prior, z) (prior at b(z) plus fldj, core.py:114-121)
+        plus the log-likelihood at the constrained value."""
+        tree = self.unravel(z)
+        theta = {k: self.bijector[k].forward(tree[k]) for k in self.names}
+        p = sum(self.prior[k].log_prob(theta[k]).sum() + self.bijector[k].fldj(tree[k]).sum() for k in self.names)
+        return p + self.log_likelihood_fn(theta, outputs, inputs)
+
     def value_and_grad(self, loc, raw_scale, kwargs, outputs, inputs, full_data_size, eps):
         """jax.value_and_grad(loss_fn) (utils.py:7): returns loss, dloc, draw_scale, {dkwargs}."""
         loc = loc.detach().clone().requires_grad_(True)

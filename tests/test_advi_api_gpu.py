@@ -170,3 +170,70 @@ def test_posterior_log_prob_kernel_against_the_oracle(vi):
     # batch of shape (2, 3): same numbers, reshaped
     s6 = {k: v[:6].reshape(2, 3, *v.shape[1:]) for k, v in samples.items()}
     assert np.allclose(post.log_prob(s6, (2, 3)).cpu().numpy().ravel(), got[:6])
+
+
+@pytest.mark.parametrize("D,kernel", [(6, None), (192, "tcgen05_gemm_two_pass"), (128, "tcgen05_bf16_split")])
+def test_map_and_mcmc_log_joint_on_the_likelihood_kernels(D, kernel):
+    """bijax/map.py:27-33 and bijax/mcmc.py:30-34 as point evaluations of the fused step (S = 1, eps = 0, point_mode):
+    value and gradient with respect to the unconstrained tree against the float64 restatement, constrained latents
+    included; MAP uses the prior density of the constrained value, MCMC the density of z (with the log-det-Jacobian)."""
+    from tests import cases as C
+
+    N = 700
+    X, y = C.synth_linear(N, D, noise=0.5)
+    prior = {
+        "weights": tfd.Normal(np.zeros(D, np.float32), 1.5),
+        "noise": tfd.Gamma(2.0, 3.0),
+        "aux_beta": tfd.Beta(np.array([2.0, 0.5], np.float32), np.array([3.0, 1.0], np.float32)),
+        "aux_chain": tfd.Normal(1.0, 0.7),
+    }
+    bij = {"noise": tfb.Exp(), "aux_beta": tfb.Sigmoid(), "aux_chain": tfb.Chain([tfb.Softplus(), tfb.Exp()])}
+    lik = lk.GaussianLinear(noise_latent="noise")
+    _, ref = C.build_pair(prior, bij, lik)
+    dev = torch.device("cuda")
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    zflat = (0.3 * tf.normal(tf.prng_key(31), (ref.size,), 1)).astype(np.float32)
+    tree64 = ref.unravel(torch.tensor(zflat, dtype=torch.float64))
+    for cls, mode in ((bj.MAP, "map"), (bj.MCMC, "mcmc")):
+        model = cls(prior, lik, bij, kernel=kernel) if cls is bj.MAP else cls(prior, bij, lik, kernel=kernel)
+        ztree = {k: v.to(torch.float32).to(dev).clone().requires_grad_(True) for k, v in tree64.items()}
+        if mode == "map":
+            val = model.neg_log_joint({"params": ztree}, yd, {"X": Xd})
+        else:
+            val = model.log_joint(ztree, yd, {"X": Xd})
+        val.backward()
+        z64 = torch.tensor(zflat, dtype=torch.float64, requires_grad=True)
+        t64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+        want = ref.map_neg_log_joint(z64, t64(y), {"X": t64(X)}) if mode == "map" else ref.mcmc_log_joint(z64, t64(y), {"X": t64(X)})
+        (gw,) = torch.autograd.grad(want, z64)
+        C.assert_close(val.item(), want.item(), what=f"{mode} value")
+        got = torch.cat([ztree[k].grad.reshape(-1) for k in ref.names]).cpu().numpy()
+        C.assert_close(got, gw.numpy(), what=f"{mode} gradient")
+    # transform_tree
+    th = model.transform({k: v.detach() for k, v in ztree.items()})
+    assert torch.allclose(th["noise"].cpu().double(), torch.exp(tree64["noise"]), rtol=1e-6)
+    assert torch.allclose(th["aux_beta"].cpu().double(), torch.sigmoid(tree64["aux_beta"]), rtol=1e-6)
+
+
+def test_map_training_recovers_the_ridge_solution():
+    """MAP for Gaussian linear regression with a Normal(0, s) prior is ridge regression: train_fn in its seed=None form
+    (utils.py:10-19) on MAP.neg_log_joint converges to the closed-form solution."""
+    from bijax_b200 import random as br
+    from functools import partial
+    from tests import cases as C
+
+    N, D, tau, s0 = 5000, 8, 0.3, 2.0
+    X, y = C.synth_linear(N, D, noise=tau)
+    dev = torch.device("cuda")
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    model = bj.MAP({"weights": tfd.Normal(np.zeros(D, np.float32), s0)}, lk.GaussianLinear(noise_scale=tau), None)
+    params = model.init(br.PRNGKey(0))
+    assert params["params"]["weights"].shape == (D,)
+    loss_fn = partial(model.neg_log_joint, outputs=yd, inputs={"X": Xd})
+    res = bj.train(loss_fn, params, optim.adam(0.05), n_epochs=800)
+    w = res["params"]["params"]["weights"].cpu().numpy().astype(np.float64)
+    X64, y64 = X.astype(np.float64), y.astype(np.float64)
+    ridge = np.linalg.solve(X64.T @ X64 / tau**2 + np.eye(D) / s0**2, X64.T @ y64 / tau**2)
+    assert np.allclose(w, ridge, atol=2e-3), np.abs(w - ridge).max()
+    assert res["losses"][-1] < res["losses"][0]
+    assert torch.equal(model.apply(res["params"])["weights"].cpu(), res["params"]["params"]["weights"].cpu())

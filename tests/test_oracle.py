@@ -147,3 +147,34 @@ def test_oracle_posterior_log_prob_is_the_logit_normal_density():
         z = math.log(p / (1 - p))
         want = -0.5 * ((z - m) / s) ** 2 - math.log(s) - 0.5 * math.log(2 * math.pi) - math.log(p * (1 - p))
         assert abs(got - want) < 1e-12
+
+
+def test_oracle_map_and_mcmc_joints_differ_by_the_log_det_jacobian():
+    """map.py:27-33 evaluates the prior density at the constrained value; mcmc.py:30-34 the density of z (core.py:117):
+    for one Gamma latent under Exp they differ by fldj(z) = z, and both equal the hand-written formula."""
+    import math
+
+    import torch
+
+    from oracle import advi_ref as R
+
+    ref = R.ADVIRef({"noise": R.Gamma(2.0, 3.0), "weights": R.Normal(torch.zeros(2, dtype=torch.float64), 1.0)},
+                    {"noise": R.Exp()}, R.gaussian_linear_loglik("weights", "log_noise_scale"))
+    # replace the likelihood by one that reads the latent noise, as tests/cases.py does
+    def lik(latent, outputs, inputs, **kw):
+        loc = inputs["X"] @ latent["weights"]
+        zz = (outputs - loc) / latent["noise"]
+        return (-0.5 * zz * zz - 0.5 * R.LOG_2PI - torch.log(latent["noise"])).sum()
+    ref.log_likelihood_fn = lik
+    X = torch.tensor([[1.0, 2.0], [0.5, -1.0], [2.0, 0.0]], dtype=torch.float64)
+    y = torch.tensor([0.3, -0.2, 1.1], dtype=torch.float64)
+    z = torch.tensor([0.4, 0.7, -0.3], dtype=torch.float64)  # layout: noise, weights (sorted keys)
+    tau, w = math.exp(0.4), z[1:]
+    log_gamma = 2.0 * math.log(3.0) - math.lgamma(2.0) + (2.0 - 1.0) * math.log(tau) - 3.0 * tau
+    log_norm = float((-0.5 * w * w - 0.5 * R.LOG_2PI).sum())
+    r = (y - X @ w) / tau
+    ll = float((-0.5 * r * r - 0.5 * R.LOG_2PI - math.log(tau)).sum())
+    m = ref.map_neg_log_joint(z, y, {"X": X}).item()
+    j = ref.mcmc_log_joint(z, y, {"X": X}).item()
+    assert abs(m + (log_gamma + log_norm + ll)) < 1e-12
+    assert abs(j - (log_gamma + 0.4 + log_norm + ll)) < 1e-12
