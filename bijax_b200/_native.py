@@ -16,7 +16,7 @@ _LIB_PATH = _HERE / "_lib" / "libbjx.so"
 ABI_VERSION = 2
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 LAYOUT_LEGACY, LAYOUT_PARTITIONABLE = 0, 1
-VI_MEAN_FIELD, VI_FULL_RANK = 0, 1
+VI_MEAN_FIELD, VI_FULL_RANK, VI_LOW_RANK = 0, 1, 2
 SCALE_EXP, SCALE_SOFTPLUS, SCALE_IDENTITY = 0, 1, 2
 BIJ_IDENTITY, BIJ_EXP, BIJ_SOFTPLUS, BIJ_SIGMOID = 0, 1, 2, 3
 PRIOR_NORMAL, PRIOR_BETA, PRIOR_GAMMA = 0, 1, 2
@@ -96,6 +96,8 @@ class BjxElboArgs(C.Structure):
         ("s_offset", C.c_int64),
         ("entropy_weight", C.c_float),
         ("point_mode", C.c_int32),
+        ("reserved3", C.c_int32),
+        ("rank", C.c_int64),
     ]
 
 

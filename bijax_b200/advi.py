@@ -119,9 +119,7 @@ class ADVI:
             "The keys in `prior` and `prior_constraints` must be the same."
         )
         assert (vi_type == "low_rank") == (rank is not None), "`rank` must be specified only if `vi_type` is `low_rank`."
-        if vi_type == "low_rank":
-            raise NotImplementedError("low_rank is outside the fused hot path (SURVEY.md section 2, row 2); use mean_field or full_rank")
-        if vi_type not in ("mean_field", "full_rank"):
+        if vi_type not in ("mean_field", "full_rank", "low_rank"):
             raise ValueError(f"unknown vi_type {vi_type!r}")
         if not isinstance(likelihood, lk.Likelihood):
             raise NotImplementedError(
@@ -133,7 +131,12 @@ class ADVI:
         self.rank = rank
         # default parameter bijectors: [Identity, Exp] mean field (core.py:180-181), [Identity, Identity] full rank (core.py:205-206)
         if ordered_posterior_bijectors is None:
-            ordered_posterior_bijectors = [tfb.Identity(), tfb.Exp() if vi_type == "mean_field" else tfb.Identity()]
+            # core.py:180-181 (mean field), 191-192 (low rank: [Identity, Exp, Identity]), 205-206 (full rank)
+            ordered_posterior_bijectors = [tfb.Identity(), tfb.Identity() if vi_type == "full_rank" else tfb.Exp()]
+            if vi_type == "low_rank":
+                ordered_posterior_bijectors.append(tfb.Identity())
+        if vi_type == "low_rank" and len(ordered_posterior_bijectors) > 2 and type(ordered_posterior_bijectors[2]).__name__ != "Identity":
+            raise NotImplementedError("only Identity is supported on scale_perturb_factor")
         if type(ordered_posterior_bijectors[0]).__name__ != "Identity":
             raise NotImplementedError("only Identity is supported on the location parameter")
         self.posterior_params_bijector = ordered_posterior_bijectors
@@ -157,6 +160,12 @@ class ADVI:
     def init(self, seed, initializer: Optional[Callable] = None):
         """advi.py:77-78: raw params = initializer(seed, (P,)), default normal(stddev=1), unraveled in (loc, scale) order."""
         D = self.size
+        if self.vi_type == "low_rank":
+            # leaves in constructor-argument order: loc [D], scale_diag [D], scale_perturb_factor [D, rank]  (utils.py:53-55)
+            r = int(self.rank)
+            flat = brandom.normal(seed, (2 * D + D * r,)) if initializer is None else initializer(seed, (2 * D + D * r,))
+            return {"posterior": {"loc": flat[:D].clone(), "scale_diag": flat[D : 2 * D].clone(),
+                                  "scale_perturb_factor": flat[2 * D :].reshape(D, r).clone()}}
         P = D if self.vi_type == "mean_field" else (D * (D + 1) // 2 if self.packed_tril else D * D)
         flat = brandom.normal(seed, (D + P,)) if initializer is None else initializer(seed, (D + P,))
         scale = flat[D:].reshape((P,) if (self.vi_type == "mean_field" or self.packed_tril) else (D, D))
@@ -177,6 +186,10 @@ class ADVI:
             if raw is None:
                 raw = getattr(post, "scale_tril")
         kwargs = {k: v for k, v in params.items() if k != key}
+        if self.vi_type == "low_rank":
+            U = post["scale_perturb_factor"] if isinstance(post, dict) else post.scale_perturb_factor
+            # the engine takes [raw scale_diag | scale_perturb_factor] as one vector; torch.cat keeps both differentiable
+            raw = torch.cat([raw.reshape(-1).to(torch.float32), U.reshape(-1).to(torch.float32)])
         if self.packed_tril:
             raw = fill_triangular(raw)  # differentiable: gradients come back in the packed layout
         return loc, raw, kwargs
@@ -194,7 +207,7 @@ class ADVI:
         if sig not in self._engines:
             self._engines[sig] = ElboEngine(self.latents, self.likelihood_fn, self.vi_type, self.posterior_params_bijector[1],
                                             layout, device=self.device, precision=self.precision, kernel=self.kernel,
-                                            prepare_dataset=self.prepare_dataset)
+                                            prepare_dataset=self.prepare_dataset, rank=self.rank)
         return self._engines[sig], leaves
 
     def distributed(self, group=None, global_len: Optional[int] = None, shard: str = "rows"):
@@ -273,7 +286,12 @@ class ADVI:
             with torch.cuda.device(out.device):
                 nv.check(nv.load().bjx_fill_triangular_vjp(d_raw.contiguous().data_ptr(), D, packed.data_ptr(), nv.current_stream_ptr()))
             d_raw = packed
-        grads: Dict[str, Any] = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), _scale_key(self.vi_type): d_raw}}
+        if self.vi_type == "low_rank":
+            r = int(self.rank)
+            grads: Dict[str, Any] = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), "scale_diag": d_raw[:D].clone(),
+                                           "scale_perturb_factor": d_raw[D:].reshape(D, r).clone()}}
+        else:
+            grads = {key: {"loc": out[1 : 1 + D].reshape(loc.shape), _scale_key(self.vi_type): d_raw}}
         o = 1 + D + P
         for n in sorted(kwargs):
             ls, td = tree_flatten(kwargs[n])

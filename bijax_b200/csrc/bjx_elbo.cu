@@ -72,7 +72,9 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   BJX_REQUIRE(a.D >= 1, "D must be >= 1");
   BJX_REQUIRE(a.N >= 0, "N must be >= 0");
   BJX_REQUIRE(a.K >= 0, "K must be >= 0");
-  BJX_REQUIRE(a.vi_type == BJX_VI_MEAN_FIELD || a.vi_type == BJX_VI_FULL_RANK, "unknown vi_type %d", a.vi_type);
+  BJX_REQUIRE(a.vi_type == BJX_VI_MEAN_FIELD || a.vi_type == BJX_VI_FULL_RANK || a.vi_type == BJX_VI_LOW_RANK,
+              "unknown vi_type %d", a.vi_type);
+  BJX_REQUIRE(a.vi_type != BJX_VI_LOW_RANK || (a.rank >= 1 && a.rank <= 64), "low rank needs 1 <= rank <= 64 (got %lld)", (long long)a.rank);
   BJX_REQUIRE(a.scale_bijector >= BJX_SCALE_EXP && a.scale_bijector <= BJX_SCALE_IDENTITY, "unknown scale bijector %d",
               a.scale_bijector);
   BJX_REQUIRE(a.threefry_layout == BJX_LAYOUT_LEGACY || a.threefry_layout == BJX_LAYOUT_PARTITIONABLE,
@@ -125,7 +127,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
     return fail(BJX_ERR_INVALID_ARGUMENT, "unknown likelihood family %d", a.likelihood);
   }
 
-  p.Pn = a.vi_type == BJX_VI_MEAN_FIELD ? a.D : a.D * a.D;
+  p.Pn = a.vi_type == BJX_VI_MEAN_FIELD ? a.D : (a.vi_type == BJX_VI_FULL_RANK ? a.D * a.D : a.D + a.D * a.rank);
   p.n_qp_blocks = (int)((a.S * a.D + 255) / 256);
   const int64_t Dw = a.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : a.Dw;
 
@@ -190,11 +192,11 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   };
   const size_t SD = (size_t)a.S * a.D * sizeof(float);
   p.o_eps = take(SD);
-  p.o_z = take(a.vi_type == BJX_VI_FULL_RANK ? SD : 0);
+  p.o_z = take(a.vi_type != BJX_VI_MEAN_FIELD ? SD : 0);
   p.o_theta = take(SD);
   p.o_bprime = take(SD);
   p.o_gprior = take(SD);
-  p.o_gz = take(a.vi_type == BJX_VI_FULL_RANK ? SD : 0);
+  p.o_gz = take(a.vi_type != BJX_VI_MEAN_FIELD ? SD : 0);
   p.o_qp = take((size_t)p.n_qp_blocks * sizeof(float));
   p.o_aux = take((size_t)a.S * sizeof(float4));
   p.o_G = take((size_t)a.S * Dw * sizeof(float));
@@ -208,6 +210,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   p.o_gm_t = take(gm ? (size_t)p.gm_nt * a.S * p.gm_Dp * 2 : 0);
   p.o_gm_g = take(gm ? (size_t)p.gm_nt * a.N * p.gm_Sp * 2 : 0);
   p.o_fr_tc = take(p.fr_tc ? fullrank_tc_bytes(a) : 0);
+  p.o_lr = take(a.vi_type == BJX_VI_LOW_RANK ? lowrank_bytes(a) : 0);
   p.o_stage_key = take(16);
   p.o_stage_params = take((size_t)(a.D + p.Pn + a.K) * sizeof(float));
   p.o_stage_out = take((size_t)(1 + a.D + p.Pn + a.K) * sizeof(float));
@@ -239,8 +242,12 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
     if (FULL) {
       eps = eps_buf[i];
       z = z_buf[i];
-      const ScaleEval sc = eval_scale(raw[d * D + d], scale_bij);
-      logsig = logf(fabsf(sc.sigma));
+      if (raw != nullptr) {
+        const ScaleEval sc = eval_scale(raw[d * D + d], scale_bij);
+        logsig = logf(fabsf(sc.sigma));
+      } else {
+        logsig = 0.0f;  // low rank: log|det(diag(d) + U U^T)| is not a sum over coordinates; k_scalars adds it per sample
+      }
     } else {
       const uint32_t* k = key_index ? key + 2 * (*key_index) : key;  // device-resident loop: key = keys[step counter]
       // sample sharding: the flat index and the stream length are those of the unsharded (S_total, D) draw
@@ -482,7 +489,8 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
 // loss = prior_weight * mean_s(q_s - p~_s) - ll_scale * mean_s ll_s ;  d kwargs
 __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t Pn, const float* __restrict__ kwargs,
                                                  const float* __restrict__ theta, const float* __restrict__ qp_part,
-                                                 int n_qp, const float* __restrict__ stat, float* __restrict__ out) {
+                                                 int n_qp, const float* __restrict__ stat, const float* __restrict__ logdet,
+                                                 float* __restrict__ out) {
   __shared__ float red[32];
   float qp = 0.0f;
   for (int i = threadIdx.x; i < n_qp; i += 256) qp += qp_part[i];
@@ -502,7 +510,9 @@ __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t 
   dk = block_sum(dk, red);
   if (threadIdx.x == 0) {
     const float invS = 1.0f / (float)t.S_total;
-    out[0] = t.prior_weight * qp * invS - t.ll_scale * ll * invS;
+    // low rank: q.log_prob carries -log|det A| once per sample of this call
+    const float qextra = logdet ? -logdet[0] * (float)t.S : 0.0f;
+    out[0] = t.prior_weight * (qp + qextra) * invS - t.ll_scale * ll * invS;
     float* dkw = out + 1 + t.D + Pn;
     for (int64_t k = 0; k < K; ++k) dkw[k] = 0.0f;
     if (t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_KWARG) dkw[t.noise_index] = -t.ll_scale * dk * invS;
@@ -521,7 +531,15 @@ static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStrea
   const int64_t probs_coord = (a.likelihood == BJX_LIK_BERNOULLI_PROBS && a.N > 0) ? a.w_offset : -1;
   const int64_t total = a.S * a.D;
   const int64_t S_total = a.S_total ? a.S_total : a.S, s_offset = a.S_total ? a.s_offset : 0;
-  if (a.vi_type == BJX_VI_FULL_RANK) {
+  if (a.vi_type == BJX_VI_LOW_RANK) {
+    k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, total, s_offset * a.D, S_total * a.D, a.threefry_layout, eps);
+    BJX_LAUNCH_CHECK("k_eps");
+    int rc = launch_lowrank_sample(a, eps, z, ws + p.o_lr, st);
+    if (rc) return rc;
+    k_prologue<true><<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, a.loc, nullptr, a.coords, a.S, a.D, a.scale_bijector,
+                                                    a.threefry_layout, eps, z, theta, bprime, gprior, qp, a.eps_out,
+                                                    probs_coord, aux, s_offset, S_total, a.point_mode);
+  } else if (a.vi_type == BJX_VI_FULL_RANK) {
     k_eps<<<p.n_qp_blocks, 256, 0, st>>>(a.key, a.key_index, total, s_offset * a.D, S_total * a.D, a.threefry_layout, eps);
     BJX_LAUNCH_CHECK("k_eps");
     if (p.fr_tc) {
@@ -599,7 +617,7 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   t.entropy_weight = a.point_mode ? 0.0f : (a.S_total ? a.entropy_weight : a.prior_weight);
   t.point_mode = a.point_mode;
   t.S_total = a.S_total ? a.S_total : a.S;
-  float* gz = a.vi_type == BJX_VI_FULL_RANK ? (float*)(ws + p.o_gz) : nullptr;
+  float* gz = a.vi_type != BJX_VI_MEAN_FIELD ? (float*)(ws + p.o_gz) : nullptr;
   k_tail<<<(unsigned)((a.D + 7) / 8), 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
                                                        (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
                                                        (const float*)(ws + p.o_gprior), G, stat, gz, a.out);
@@ -615,8 +633,13 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
       BJX_LAUNCH_CHECK("k_fullrank_dM");
     }
   }
+  if (a.vi_type == BJX_VI_LOW_RANK) {
+    rc = launch_lowrank_grads(a, gz, (const float*)(ws + p.o_eps), ws + p.o_lr, t.entropy_weight, a.out + 1 + a.D, st);
+    if (rc) return rc;
+  }
   k_scalars<<<1, 256, 0, st>>>(t, a.K, p.Pn, a.kwargs, (const float*)(ws + p.o_theta), (const float*)(ws + p.o_qp),
-                               p.n_qp_blocks, stat, a.out);
+                               p.n_qp_blocks, stat, a.vi_type == BJX_VI_LOW_RANK ? lowrank_logdet_ptr(a, ws + p.o_lr) : nullptr,
+                               a.out);
   BJX_LAUNCH_CHECK("k_scalars");
   return BJX_OK;
 }
@@ -749,7 +772,7 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
   const size_t SD = (size_t)a.S * a.D * sizeof(float);
   BJX_CUDA_TRY(cudaMemcpyAsync(theta_out, ws + p.o_theta, SD, cudaMemcpyDeviceToDevice, st));
   if (z_out) {
-    if (a.vi_type == BJX_VI_FULL_RANK) {
+    if (a.vi_type != BJX_VI_MEAN_FIELD) {
       BJX_CUDA_TRY(cudaMemcpyAsync(z_out, ws + p.o_z, SD, cudaMemcpyDeviceToDevice, st));
     } else {
       return fail(BJX_ERR_UNSUPPORTED, "z_out is only materialised for the full-rank family; invert the bijector instead");

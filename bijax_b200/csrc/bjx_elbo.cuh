@@ -25,7 +25,7 @@ struct Plan {
   int64_t gm_Dp, gm_Sp;  // padded plane pitches (elements)
   int fr_tc;             // full-rank contractions on the tensor cores
   // byte offsets into the workspace
-  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta, o_gm_x, o_gm_t, o_gm_g, o_fr_tc,
+  size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta, o_gm_x, o_gm_t, o_gm_g, o_fr_tc, o_lr,
       o_stage_key, o_stage_params, o_stage_out, total;
 };
 
@@ -49,6 +49,13 @@ bool fullrank_tc_eligible(const BjxElboArgs& a);
 size_t fullrank_tc_bytes(const BjxElboArgs& a);
 int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);
 int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char* scratch, float entropy_weight, cudaStream_t st);
+
+// low-rank variational family (bjx_lowrank.cu)
+size_t lowrank_bytes(const BjxElboArgs& a);
+int launch_lowrank_sample(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);
+const float* lowrank_logdet_ptr(const BjxElboArgs& a, const char* scratch);
+int launch_lowrank_grads(const BjxElboArgs& a, const float* gz, const float* eps, char* scratch, float entropy_weight,
+                         float* d_raw, cudaStream_t st);
 
 // per-datum link functions (the elementwise part of advi.py:91 for the recognised families)
 //   Bernoulli(logits=eta): f = y*eta - softplus(eta)   (== -(1-y) softplus(eta) - y softplus(-eta)),  g = y - sigmoid(eta)

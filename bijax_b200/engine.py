@@ -29,23 +29,26 @@ class ElboEngine:
         precision: str = "auto",
         kernel: Optional[str] = None,
         prepare_dataset: bool = True,
+        rank: Optional[int] = None,
     ):
         nv.require_cuda()
         self.lib = nv.load()
         self.latents = latents
         self.likelihood = likelihood
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        if vi_type not in ("mean_field", "full_rank"):
-            raise NotImplementedError(
-                f"vi_type={vi_type!r}: only mean_field and full_rank are fused; low_rank stays out of scope (SURVEY.md section 2)"
-            )
-        self.vi_type = nv.VI_MEAN_FIELD if vi_type == "mean_field" else nv.VI_FULL_RANK
-        sb = type(scale_bijector).__name__ if scale_bijector is not None else ("Exp" if vi_type == "mean_field" else "Identity")
+        if vi_type not in ("mean_field", "full_rank", "low_rank"):
+            raise ValueError(f"unknown vi_type {vi_type!r}")
+        self.vi_type = {"mean_field": nv.VI_MEAN_FIELD, "full_rank": nv.VI_FULL_RANK, "low_rank": nv.VI_LOW_RANK}[vi_type]
+        self.rank = int(rank) if vi_type == "low_rank" else 0
+        if vi_type == "low_rank" and not 1 <= self.rank <= 64:
+            raise NotImplementedError("the fused low-rank family supports 1 <= rank <= 64")
+        # default scale bijectors: Exp on scale_diag (core.py:180-181, 191-192), Identity on scale_tril (core.py:205-206)
+        sb = type(scale_bijector).__name__ if scale_bijector is not None else ("Identity" if vi_type == "full_rank" else "Exp")
         if sb not in _SCALE_IDS:
             raise NotImplementedError(f"scale bijector {sb} is not one of Exp / Softplus / Identity")
         self.scale_bijector = _SCALE_IDS[sb]
         self.D = latents.size
-        self.P = self.D if self.vi_type == nv.VI_MEAN_FIELD else self.D * self.D
+        self.P = {nv.VI_MEAN_FIELD: self.D, nv.VI_FULL_RANK: self.D * self.D, nv.VI_LOW_RANK: self.D * (1 + self.rank)}[self.vi_type]
         self.kwarg_layout = list(kwarg_layout)  # [(name, numel)] in sorted-key order
         self.K = sum(n for _, n in self.kwarg_layout)
         self.precision = _PRECISIONS[precision] if isinstance(precision, str) else int(precision)
@@ -108,6 +111,7 @@ class ElboEngine:
         a.noise_src, a.noise_index, a.noise_value = self.noise_src, self.noise_index, self.noise_value
         a.threefry_layout = layout
         a.precision = self.precision
+        a.rank = self.rank
         a.kernel_override = self.kernel_override
         a.ll_scale, a.prior_weight = float(ll_scale), float(prior_weight)
         a.coords = self.coords.data_ptr()

@@ -45,7 +45,7 @@ def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
     kw = dict(loss_fn.keywords)
     if not {"outputs", "inputs", "full_data_size"} <= set(kw) or set(kw) - {"outputs", "inputs", "full_data_size", "n_samples"}:
         return None
-    if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False):
+    if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False) or getattr(model, "vi_type", "") == "low_rank":
         return None
     return model, kw
 

@@ -55,6 +55,7 @@ extern "C" {
 /* ---- variational family: core.py:179-187 (mean field), 204-212 (full rank) */
 #define BJX_VI_MEAN_FIELD 0
 #define BJX_VI_FULL_RANK 1
+#define BJX_VI_LOW_RANK 2 /* core.py:190-201: MultivariateNormalDiagPlusLowRank, scale = diag(d) + U U^T, rank <= 64 */
 
 /* ---- bijector on the raw scale parameter (ordered_posterior_bijectors[1],
  *      advi.py:33,45,65-67; default Exp, core.py:180-181) ------------------ */
@@ -130,14 +131,15 @@ typedef struct BjxElboArgs {
   /* inputs (device) */
   const uint32_t* key;     /* [2]   per-step PRNG key (advi.py:83 seed) */
   const float* loc;        /* [D]   params["posterior"].loc */
-  const float* raw_scale;  /* [D] raw scale_diag  |  [D*D] row-major raw scale_tril (upper part ignored) */
+  const float* raw_scale;  /* [D] raw scale_diag  |  [D*D] row-major raw scale_tril (upper part ignored)  |
+                              low rank: [D] raw scale_diag followed by [D, rank] row-major scale_perturb_factor */
   const float* kwargs;     /* [K]   or NULL */
   const float* X;          /* [N, ldx] row-major, or NULL */
   const float* y;          /* [N] */
   const BjxCoord* coords;  /* [D]   prior + bijector table */
 
   /* outputs (device) */
-  float* out;      /* packed [1 + D + P + K]: loss, d loc, d raw_scale (P = D or D*D), d kwargs.
+  float* out;      /* packed [1 + D + P + K]: loss, d loc, d raw_scale (P = D, D*D or D + D*rank), d kwargs.
                       This buffer is the all-reduce message under data sharding. */
   float* eps_out;  /* optional [S*D]: the standard-normal draws used (NULL to skip) */
 
@@ -171,6 +173,10 @@ typedef struct BjxElboArgs {
    *                         of the constrained value, no log-det-Jacobian)
    * and d out / d z in the `d loc` block. */
   int32_t point_mode;
+  int32_t reserved3;
+
+  /* optional (ABI 2): rank of the low-rank family (BJX_VI_LOW_RANK), 1..64 */
+  int64_t rank;
 } BjxElboArgs;
 
 #define BJX_POINT_OFF 0

@@ -295,6 +295,46 @@ class ADVIRef:
             q = -0.5 * (zz * zz).sum() - torch.log(torch.abs(torch.diagonal(tril))).sum() - 0.5 * D * LOG_2PI
         return q + ildj
 
+    def loss_low_rank(self, loc, raw_diag, U, kwargs, outputs, inputs, full_data_size, eps):
+        """advi.py:80-95 for vi_type="low_rank" (core.py:190-201): q = MultivariateNormalDiagPlusLowRank(loc, d, U) with
+        d = scale_bijector(raw_diag) (default Exp), i.e. scale operator A = diag(d) + U U^T; sample = loc + A eps;
+        q.log_prob(z) = -1/2 |A^-1 (z - loc)|^2 - log|det A| - D/2 log 2 pi (dense solve / slogdet here, float64)."""
+        dt = loc.dtype
+        eps = eps.to(dt)
+        D = self.size
+        d = self.scale_bijector.forward(raw_diag)
+        A = torch.diag(d) + U @ U.T
+        samples = loc + eps @ A.T
+        logdet = torch.linalg.slogdet(A)[1]
+
+        def loss_no_batch(sample):
+            zz = torch.linalg.solve(A, sample - loc)
+            q_log_prob = -0.5 * (zz * zz).sum() - logdet - 0.5 * D * LOG_2PI
+            tree = self.unravel(sample)
+            p_log_prob = 0.0
+            theta = {}
+            for k in self.names:
+                b = self.bijector[k]
+                th = b.forward(tree[k])
+                p_log_prob = p_log_prob + (self.prior[k].log_prob(th).sum() + b.fldj(tree[k]).sum())
+                theta[k] = th
+            ll = self.log_likelihood_fn(theta, outputs, inputs, **kwargs)
+            ll = (ll / len(outputs)) * full_data_size
+            return q_log_prob - p_log_prob - ll
+
+        return torch.stack([loss_no_batch(samples[s]) for s in range(samples.shape[0])]).mean()
+
+    def value_and_grad_low_rank(self, loc, raw_diag, U, kwargs, outputs, inputs, full_data_size, eps):
+        loc = loc.detach().clone().requires_grad_(True)
+        raw_diag = raw_diag.detach().clone().requires_grad_(True)
+        U = U.detach().clone().requires_grad_(True)
+        kw = {k: v.detach().clone().requires_grad_(True) for k, v in kwargs.items()}
+        loss = self.loss_low_rank(loc, raw_diag, U, kw, outputs, inputs, full_data_size, eps)
+        leaves = [loc, raw_diag, U] + list(kw.values())
+        grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+        gk = {k: (g if g is not None else torch.zeros_like(v)) for (k, v), g in zip(kw.items(), grads[3:])}
+        return loss.detach(), grads[0], grads[1], grads[2], gk
+
     def map_neg_log_joint(self, z, outputs, inputs):
         """MAP.neg_log_joint (map.py:27-33) at the flat unconstrained vector z: transform_tree, log_prob_dist of the PRIOR at
         the constrained value (no log-det-Jacobian), likelihood.log_prob(outputs).sum(); returns -(log_prior + log_lik)."""

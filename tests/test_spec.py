@@ -53,8 +53,12 @@ def test_constructor_forms_and_errors():
         bj.ADVI(prior, {"p": tfb.Sigmoid()}, lk.BernoulliProbs("p"), vi_type="mean_field", rank=2)
     with pytest.raises(NotImplementedError):
         bj.ADVI(prior, {"p": tfb.Sigmoid()}, lambda *a, **k: 0.0)
-    with pytest.raises(NotImplementedError):
-        bj.ADVI(prior, {"p": tfb.Sigmoid()}, lk.BernoulliProbs("p"), vi_type="low_rank", rank=2)
+    m3 = bj.ADVI(prior, {"p": tfb.Sigmoid()}, lk.BernoulliProbs("p"), vi_type="low_rank", rank=2)  # core.py:190-201
+    assert m3.vi_type == "low_rank" and m3.rank == 2 and len(m3.posterior_params_bijector) == 3
+    with pytest.raises(AssertionError):
+        bj.ADVI(prior, {"p": tfb.Sigmoid()}, lk.BernoulliProbs("p"), vi_type="low_rank")  # rank is required (advi.py:55-57)
+    with pytest.raises(ValueError):
+        bj.ADVI(prior, {"p": tfb.Sigmoid()}, lk.BernoulliProbs("p"), vi_type="banded")
 
 
 def test_duck_typed_foreign_distribution_objects():
