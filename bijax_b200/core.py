@@ -34,8 +34,6 @@ class Posterior:
     def log_prob(self, sample: Dict, sample_shape=()):
         """core.py:57-71: q(z = b^{-1}(theta)) + sum inverse_log_det_jacobian(theta), one fused kernel over the flattened
         samples (bjx_posterior_log_prob: inverse bijector chains, triangular solve for the full-rank family)."""
-        if self.model.vi_type == "low_rank":
-            raise NotImplementedError("Posterior.log_prob of the low-rank family (a Woodbury solve per sample) is not built; sample() is")
         lat = self.model.latents
         dev = self.engine.device
         leaves = dict(flatten_tree(sample, lambda x: isinstance(x, torch.Tensor)))

@@ -57,6 +57,9 @@ const float* lowrank_logdet_ptr(const BjxElboArgs& a, const char* scratch);
 int launch_lowrank_grads(const BjxElboArgs& a, const float* gz, const float* eps, char* scratch, float entropy_weight,
                          float* d_raw, cudaStream_t st);
 
+size_t lowrank_posterior_bytes(const BjxElboArgs& a);
+int launch_lowrank_posterior_log_prob(const BjxElboArgs& a, const float* theta, int64_t n, float* out, cudaStream_t st);
+
 // per-datum link functions (the elementwise part of advi.py:91 for the recognised families)
 //   Bernoulli(logits=eta): f = y*eta - softplus(eta)   (== -(1-y) softplus(eta) - y softplus(-eta)),  g = y - sigmoid(eta)
 //   Normal(eta, tau):      f = (y - eta)^2 (tau applied in the tail),                                   g = y - eta

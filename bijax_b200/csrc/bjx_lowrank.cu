@@ -128,6 +128,89 @@ __global__ void __launch_bounds__(256) k_lr_grads(const float* __restrict__ gz, 
   }
 }
 
+// Posterior.log_prob for the low-rank family: one block per sample, Woodbury solve
+//   A^-1 v = v / d - W (U^T (v / d)),   v = b^-1(theta) - loc,   W = diag(1/d) U C^-1  (k_lr_logdet)
+__device__ __forceinline__ void lr_inverse_coord(float theta, uint32_t chain, float& z_out, float& fldj_out);
+
+__global__ void __launch_bounds__(256) k_post_logprob_lr(const float* __restrict__ theta, int64_t D, int r,
+                                                         const float* __restrict__ loc, const float* __restrict__ raw_d,
+                                                         const float* __restrict__ U, const float* __restrict__ W,
+                                                         const float* __restrict__ scal, const BjxCoord* __restrict__ coords,
+                                                         int scale_bij, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* vd = sm;        // [D]  (z - loc) / d
+  float* t = sm + D;     // [r]  U^T vd
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t s = blockIdx.x;
+  float part = 0.0f;  // - sum fldj
+  for (int64_t i = tid; i < D; i += 256) {
+    float z, fldj;
+    lr_inverse_coord(theta[s * D + i], coords[i].chain, z, fldj);
+    vd[i] = (z - loc[i]) / eval_scale(raw_d[i], scale_bij).sigma;
+    part -= fldj;
+  }
+  __syncthreads();
+  for (int k = w; k < r; k += 8) {
+    float acc = 0.0f;
+    for (int64_t i = lane; i < D; i += 32) acc = fmaf(U[i * r + k], vd[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) t[k] = acc;
+  }
+  __syncthreads();
+  for (int64_t i = tid; i < D; i += 256) {
+    float zz = vd[i];
+    for (int k = 0; k < r; ++k) zz = fmaf(-W[i * r + k], t[k], zz);
+    part += -0.5f * zz * zz - BJX_HALF_LOG_2PI;
+  }
+  const float tot = block_sum(part, red);
+  if (tid == 0) out[s] = tot - scal[0];
+}
+
+// the inverse of a packed bijector chain and the forward log-det-Jacobian at the pre-image (same as bjx_posterior.cu)
+__device__ __forceinline__ void lr_inverse_coord(float theta, uint32_t chain, float& z_out, float& fldj_out) {
+  uint32_t ops[8];
+  int n = 0;
+  while ((chain & 0xFu) && n < 8) {
+    ops[n++] = chain & 0xFu;
+    chain >>= 4;
+  }
+  float x = theta;
+  for (int i = n - 1; i >= 0; --i) {
+    const uint32_t op = ops[i];
+    if (op == BJX_BIJ_EXP) x = logf(x);
+    else if (op == BJX_BIJ_SOFTPLUS) x = x + logf(-expm1f(-x));
+    else x = logf(x) - log1pf(-x);
+  }
+  z_out = x;
+  float ldj = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t op = ops[i];
+    if (op == BJX_BIJ_EXP) { ldj += x; x = expf(x); }
+    else if (op == BJX_BIJ_SOFTPLUS) { ldj += -softplus_f(-x); x = softplus_f(x); }
+    else { ldj += -softplus_f(-x) - softplus_f(x); x = sigmoid_f(x); }
+  }
+  fldj_out = ldj;
+}
+
+size_t lowrank_posterior_bytes(const BjxElboArgs& a) { return align_up(((size_t)a.D * a.rank + a.D + 4) * sizeof(float), 256); }
+
+int launch_lowrank_posterior_log_prob(const BjxElboArgs& a, const float* theta, int64_t n, float* out, cudaStream_t st) {
+  const int r = (int)a.rank;
+  const float* raw_d = a.raw_scale;
+  const float* U = a.raw_scale + a.D;
+  float* W = (float*)a.workspace;
+  float* ddiag = W + a.D * r;
+  float* scal = ddiag + a.D;
+  k_lr_logdet<<<1, 256, (size_t)2 * r * (r + 1) * sizeof(float), st>>>(raw_d, U, a.D, r, a.scale_bijector, scal, W, ddiag);
+  BJX_LAUNCH_CHECK("k_lr_logdet");
+  const size_t smem = ((size_t)a.D + r) * sizeof(float);
+  if (smem > 48 * 1024) BJX_CUDA_TRY(cudaFuncSetAttribute(k_post_logprob_lr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_post_logprob_lr<<<(unsigned)n, 256, smem, st>>>(theta, a.D, r, a.loc, raw_d, U, W, scal, a.coords, a.scale_bijector, out);
+  BJX_LAUNCH_CHECK("k_post_logprob_lr");
+  return BJX_OK;
+}
+
 size_t lowrank_bytes(const BjxElboArgs& a) {
   const size_t S = (size_t)a.S, D = (size_t)a.D, r = (size_t)a.rank;
   return align_up((2 * S * r + D * r + D + 4) * sizeof(float), 256);

@@ -164,10 +164,17 @@ extern "C" int bjx_posterior_log_prob(const BjxElboArgs* args, const float* thet
   const BjxElboArgs& a = *args;
   BJX_REQUIRE(a.D >= 1 && n >= 0, "need D >= 1 and n >= 0");
   BJX_REQUIRE(a.loc && a.raw_scale && a.coords, "null loc / raw_scale / coords pointer");
-  BJX_REQUIRE(a.vi_type == BJX_VI_MEAN_FIELD || a.vi_type == BJX_VI_FULL_RANK, "unknown vi_type %d", a.vi_type);
+  BJX_REQUIRE(a.vi_type == BJX_VI_MEAN_FIELD || a.vi_type == BJX_VI_FULL_RANK || a.vi_type == BJX_VI_LOW_RANK, "unknown vi_type %d", a.vi_type);
   BJX_REQUIRE(a.scale_bijector >= BJX_SCALE_EXP && a.scale_bijector <= BJX_SCALE_IDENTITY, "unknown scale bijector %d", a.scale_bijector);
   if (n == 0) return BJX_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a.vi_type == BJX_VI_LOW_RANK) {
+    BJX_REQUIRE(a.rank >= 1 && a.rank <= 64, "low rank needs 1 <= rank <= 64");
+    BJX_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= lowrank_posterior_bytes(a),
+                "low-rank Posterior.log_prob needs a workspace of (D * rank + D + 4) floats");
+    BJX_REQUIRE(((size_t)a.D + a.rank) * sizeof(float) <= 200 * 1024 && n <= 0x7FFFFFFFll, "D too large for the low-rank log_prob kernel");
+    return launch_lowrank_posterior_log_prob(a, theta, n, out, st);
+  }
   if (a.vi_type == BJX_VI_MEAN_FIELD) {
     k_post_logprob_mf<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(theta, n, a.D, a.loc, a.raw_scale, a.coords, a.scale_bijector, out);
     BJX_LAUNCH_CHECK("k_post_logprob_mf");

@@ -289,6 +289,9 @@ class ElboEngine:
         raw = self._f32(raw_scale, dev).reshape(-1)
         a = self._args(1, 0, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
         a.loc, a.raw_scale = loc.data_ptr(), raw.data_ptr()
+        if self.vi_type == nv.VI_LOW_RANK:  # Woodbury factors
+            scratch = torch.empty(self.D * self.rank + self.D + 64, dtype=torch.float32, device=dev)
+            a.workspace, a.workspace_bytes = scratch.data_ptr(), scratch.numel() * 4
         out = torch.empty(theta.shape[0], dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             nv.check(self.lib.bjx_posterior_log_prob(C.byref(a), theta.data_ptr(), theta.shape[0], out.data_ptr(), nv.current_stream_ptr()))

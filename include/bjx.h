@@ -223,7 +223,8 @@ BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
 /* theta[S, D] = bijector(loc + scale * eps) for eps = normal(key, (S, D)); z_out optional */
 BJX_API int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out, void* stream);
 /* out[i] = log q(theta_i) = q.log_prob(b^{-1}(theta_i)) + sum inverse_log_det_jacobian(theta_i)   (core.py:57-71) for n
- * constrained samples theta [n, D] in the flat latent layout; uses args->D, vi_type, scale_bijector, loc, raw_scale, coords */
+ * constrained samples theta [n, D] in the flat latent layout; uses args->D, vi_type, scale_bijector, loc, raw_scale, coords
+ * (low rank: also args->rank and a workspace of (D * rank + D + 4) floats for the Woodbury factors) */
 BJX_API int bjx_posterior_log_prob(const BjxElboArgs* args, const float* theta, int64_t n, float* out, void* stream);
 
 /* ---- packed full-rank parameterisation (north_star item 2: "L built by fill-triangular") ------------------------------

@@ -224,7 +224,8 @@ class ADVIRef:
         self.log_likelihood_fn = log_likelihood_fn
         self.vi_type = vi_type
         # get_mean_field default [Identity, Exp] (core.py:180-181); full rank [Identity, Identity] (core.py:205-206)
-        self.scale_bijector = scale_bijector if scale_bijector is not None else (Exp() if vi_type == "mean_field" else Identity())
+        # (low rank: [Identity, Exp, Identity], core.py:191-192)
+        self.scale_bijector = scale_bijector if scale_bijector is not None else (Identity() if vi_type == "full_rank" else Exp())
         # flat layout: sorted keys, row-major ravel (core.py:168-176, jax dict pytrees flatten in sorted-key order)
         self.names = sorted(self.prior)
         self.shapes = {k: self.prior[k].event_like_shape() for k in self.names}
@@ -289,6 +290,11 @@ class ADVIRef:
             sigma = self.scale_bijector.forward(raw_scale)
             zz = (z - loc) / sigma
             q = (-0.5 * zz * zz - torch.log(sigma)).sum() - 0.5 * D * LOG_2PI
+        elif self.vi_type == "low_rank":  # raw_scale = (raw scale_diag, scale_perturb_factor)
+            raw_d, U = raw_scale
+            A = torch.diag(self.scale_bijector.forward(raw_d)) + U @ U.T
+            zz = torch.linalg.solve(A, z - loc)
+            q = -0.5 * (zz * zz).sum() - torch.linalg.slogdet(A)[1] - 0.5 * D * LOG_2PI
         else:
             tril = torch.tril(self.scale_bijector.forward(raw_scale))
             zz = torch.linalg.solve_triangular(tril, (z - loc)[:, None], upper=False)[:, 0]

@@ -130,14 +130,14 @@ def test_device_resident_training_loop_matches_the_host_driven_loop():
     assert torch.equal(eager["params"]["posterior"]["loc"], fused["params"]["posterior"]["loc"])
 
 
-@pytest.mark.parametrize("vi", ["mean_field", "full_rank"])
+@pytest.mark.parametrize("vi", ["mean_field", "full_rank", "low_rank"])
 def test_posterior_log_prob_kernel_against_the_oracle(vi):
     """Posterior.log_prob (core.py:57-71) as one fused kernel: inverse bijector chains + log-det-Jacobians + diagonal /
     triangular-solve Gaussian density, against the float64 restatement, for constrained latents of every supported kind."""
     from bijax_b200 import random as br
     from tests import cases as C
 
-    Dw = 70 if vi == "full_rank" else 6
+    Dw = 70 if vi != "mean_field" else 6
     prior = {
         "weights": tfd.Normal(np.zeros(Dw, np.float32), 1.5),
         "noise": tfd.Gamma(2.0, 3.0),
@@ -146,16 +146,29 @@ def test_posterior_log_prob_kernel_against_the_oracle(vi):
         "aux_chain": tfd.Normal(1.0, 0.7),
     }
     bij = {"noise": tfb.Exp(), "aux_beta": tfb.Sigmoid(), "aux_pos": tfb.Softplus(), "aux_chain": tfb.Chain([tfb.Softplus(), tfb.Exp()])}
-    model, ref = C.build_pair(prior, bij, lk.GaussianLinear(noise_latent="noise"), vi_type=vi)
+    if vi == "low_rank":
+        model = bj.ADVI(prior, bij, lk.GaussianLinear(noise_latent="noise"), vi_type=vi, rank=4)
+        _, ref = C.build_pair(prior, bij, lk.GaussianLinear(noise_latent="noise"))
+        ref.vi_type = "low_rank"
+    else:
+        model, ref = C.build_pair(prior, bij, lk.GaussianLinear(noise_latent="noise"), vi_type=vi)
     D = model.size
     loc = (0.3 * tf.normal(tf.prng_key(31), (D,), 1)).astype(np.float32)
-    if vi == "mean_field":
+    raw64 = None
+    if vi == "low_rank":
+        raw = (-1.0 + 0.2 * tf.normal(tf.prng_key(32), (D,), 1)).astype(np.float32)
+        Uf = (0.2 * tf.normal(tf.prng_key(33), (D, 4), 1)).astype(np.float32)
+        skey = "scale_diag"
+        raw64 = (torch.tensor(raw, dtype=torch.float64), torch.tensor(Uf, dtype=torch.float64))
+    elif vi == "mean_field":
         raw = (-1.0 + 0.2 * tf.normal(tf.prng_key(32), (D,), 1)).astype(np.float32)
         skey = "scale_diag"
     else:
         raw = (0.3 * np.eye(D) + 0.02 * tf.normal(tf.prng_key(32), (D, D), 1)).astype(np.float32)
         skey = "scale_tril"
     params = {"posterior": {"loc": torch.tensor(loc, device="cuda"), skey: torch.tensor(raw, device="cuda")}}
+    if vi == "low_rank":
+        params["posterior"]["scale_perturb_factor"] = torch.tensor(Uf, device="cuda")
     post = model.apply(params)
     n = 37
     samples = post.sample(br.PRNGKey(9), (n,))
@@ -163,7 +176,8 @@ def test_posterior_log_prob_kernel_against_the_oracle(vi):
     assert got.shape == (n,)
     t64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
     cpu = {k: v.cpu().double() for k, v in samples.items()}
-    want = np.array([ref.posterior_log_prob(t64(loc), t64(raw), {k: v[i] for k, v in cpu.items()}).item() for i in range(n)])
+    want = np.array([ref.posterior_log_prob(t64(loc), raw64 if raw64 is not None else t64(raw), {k: v[i] for k, v in cpu.items()}).item()
+                     for i in range(n)])
     assert np.allclose(got, want, rtol=2e-5, atol=2e-4), np.abs(got - want).max()
     p = post.prob(samples, (n,)).cpu().numpy()
     assert np.allclose(p, np.exp(want), rtol=1e-3)
