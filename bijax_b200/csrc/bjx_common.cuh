@@ -30,6 +30,18 @@ int fail(int code, const char* fmt, ...);
 
 int sm_count();
 
+// per-device "this function's attribute has been set" flags (function attributes are per device)
+struct DeviceOnce {
+  bool done[64] = {};
+  bool test_and_set() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;  // unknown device: set the attribute every time
+    const bool was = done[dev];
+    done[dev] = true;
+    return was;
+  }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- Threefry-2x32-20 (Salmon et al. SC'11; the generator under jax.random) ---------------------------------------

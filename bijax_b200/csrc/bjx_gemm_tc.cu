@@ -545,11 +545,9 @@ namespace gemm {
 template <int BN, int NT, bool A_MN, bool B_MN, int EPI, int CG = 1>
 static int launch(const Params& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, NT, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.test_and_set())
     BJX_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
   if (CG == 1) {
     k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG><<<grid, THREADS, C::SMEM_BYTES, st>>>(P);
   } else {

@@ -896,10 +896,9 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * a.Dw, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
 #define BJX_TCP_LAUNCH(NBLK)                                                                                              \
   do {                                                                                                                    \
-    static bool attr_set = false;                                                                                         \
-    if (!attr_set) {                                                                                                      \
+    static DeviceOnce attr_set;                                                                                         \
+    if (!attr_set.test_and_set()) {                                                                                                      \
       BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-      attr_set = true;                                                                                                    \
     }                                                                                                                     \
     k_lik_tc_tma<NBLK><<<p.tc_ctas, tcp::THREADS, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,    \
                                                               a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace); \
@@ -917,10 +916,9 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   }
 #define BJX_TC_LAUNCH(NBLK)                                                                                           \
   do {                                                                                                                \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
+    static DeviceOnce attr_set;                                                                                     \
+    if (!attr_set.test_and_set()) {                                                                                                  \
       BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-      attr_set = true;                                                                                                \
     }                                                                                                                 \
     k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
                                                          a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush, g_pf_mode);                     \
