@@ -459,8 +459,8 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 };
 }  // namespace tcp
 
-template <int NBLK>  // D / 64
-__global__ void __launch_bounds__(tcp::THREADS, 1)
+template <int NBLK, int EW>  // D / 64; epilogue warps (8 or 16)
+__global__ void __launch_bounds__((tcp::EPI_WARP0 + EW) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int S, int family,
              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
@@ -470,6 +470,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
   } while (0)
   using namespace tc;
+  constexpr int NTHREADS = (tcp::EPI_WARP0 + EW) * 32;
+  constexpr int HG = EW / 4;    // groups of samples among the epilogue warps of one TMEM sub-partition
+  constexpr int SG = NS / HG;   // samples whose partial logits a thread loads (16 or 8)
+  constexpr int VPT = SG / 2;   // (row, sample) pairs a thread finishes after the swap with its partner (8 or 4)
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   constexpr int D = NBLK * BLK_COLS;
   constexpr int NCH = NBLK / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -498,7 +503,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       mbar_init(&bars->x_empty[b], 1);
     }
     mbar_init(&bars->acc1_full, 1);
-    mbar_init(&bars->dl_full, tcp::EPI_WARPS);
+    mbar_init(&bars->dl_full, EW);
     mbar_init(&bars->dl_empty, 1);
     mbar_init(&bars->done, 1);
     fence_mbar_init();
@@ -507,7 +512,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   }
   if (tid < 4 * NS) sred[tid] = 0.0f;
   if (warp == tcp::MMA_WARP) tmem_alloc(&bars->tmem_base, TMEM_COLS);
-  for (int idx = tid; idx < NS * (D / 8); idx += tcp::THREADS) {
+  for (int idx = tid; idx < NS * (D / 8); idx += NTHREADS) {
     const int s = idx / (D / 8), d8 = idx % (D / 8);
     float v[8];
 #pragma unroll
@@ -650,13 +655,13 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const int h = (warp - tcp::EPI_WARP0) >> 2;
     const int part = q >> 1;
     const int r = 32 * (q & 1) + lane;
-    const int s0 = h * 16 + part * 8;
-    float* xch_mine = xch + (size_t)(warp - tcp::EPI_WARP0) * 256;                   // what the partner wrote for me
-    float* xch_peer = xch + (size_t)((warp - tcp::EPI_WARP0) ^ 2) * 256;             // (warp index ^ 2 flips q's high bit)
-    const int pair_bar = 2 + 2 * (q & 1) + h;                                        // named barriers 2..5, 64 threads each
-    float stat[8], prod[8];
+    const int s0 = h * SG + part * VPT;
+    float* xch_mine = xch + (size_t)(warp - tcp::EPI_WARP0) * (VPT * 32);             // what the partner wrote for me
+    float* xch_peer = xch + (size_t)((warp - tcp::EPI_WARP0) ^ 2) * (VPT * 32);       // (warp index ^ 2 flips q's high bit)
+    const int pair_bar = 2 + HG * (q & 1) + h;                                        // named barriers 2.., 64 threads each
+    float stat[VPT], prod[VPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < VPT; ++j) {
       stat[j] = 0.0f;
       prod[j] = 1.0f;
     }
@@ -669,8 +674,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     constexpr int PART_COL = 384;
     auto drain_chunk = [&](int ch, bool first, bool final) {
 #pragma unroll 1
-      for (int part = 0; part < 2; ++part) {
-        const int sb = h * 16 + part * 8;
+      for (int part = 0; part < SG / 8; ++part) {
+        const int sb = h * SG + part * 8;
         uint32_t fa[8], fb[8], fp[8];
         tmem_ld8(t_lane + ACC2_COL + ch * NB + sb, fa);
         tmem_ld8(t_lane + ACC2_COL + ch * NB + NS + sb, fb);
@@ -717,64 +722,75 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       mbar_wait(&bars->acc1_full, ph);
       tc_fence_after();
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
-      uint32_t va[16], vb[16];
+      uint32_t va[SG], vb[SG];
       const uint32_t acc1 = t_lane + ACC1_COL + ((it & 1) ? NB : 0);  // the logits accumulator of this tile's parity
-      tmem_ld16(acc1 + h * 16, va);
-      tmem_ld16(acc1 + NS + h * 16, vb);
+      if constexpr (SG == 16) {
+        tmem_ld16(acc1 + h * SG, va);
+        tmem_ld16(acc1 + NS + h * SG, vb);
+      } else {
+        tmem_ld8(acc1 + h * SG, va);
+        tmem_ld8(acc1 + NS + h * SG, vb);
+      }
       tmem_ld_wait();
-      float eta[8], g[8];
+      float eta[VPT], g[VPT];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // samples [8 * (1 - part), +8) of my 16 go to the partner, [8 * part, +8) stay
+      for (int j = 0; j < VPT; ++j) {
+        // samples [VPT * (1 - part), +VPT) of my SG go to the partner, [VPT * part, +VPT) stay
         const float lo = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
-        const float up = __uint_as_float(va[8 + j]) + __uint_as_float(vb[8 + j]);
+        const float up = __uint_as_float(va[VPT + j]) + __uint_as_float(vb[VPT + j]);
         xch_peer[j * 32 + lane] = part ? lo : up;
         eta[j] = part ? up : lo;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
 #pragma unroll
-      for (int j = 0; j < 8; ++j) eta[j] += xch_mine[j * 32 + lane];
+      for (int j = 0; j < VPT; ++j) eta[j] += xch_mine[j * 32 + lane];
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
       // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
       // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
       const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
       // Only g is on the critical path (GEMM2 waits for it): the loss bookkeeping (stat, prod) is done after the hand-over.
-      float ope[8];
+      float ope[VPT];
       if (ablate & 4) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
+        for (int j = 0; j < VPT; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
       } else if (logit) {
         // one exponential per datum: e = exp(-|x|); sigmoid = (x >= 0 ? 1 : e) / (1 + e); softplus = max(x, 0) + log(1 + e),
         // the logs taken of a running product (every 32 tiles)
-        float e[8], rc[8];
+        float e[VPT], rc[VPT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = __expf(-fabsf(eta[j]));
+        for (int j = 0; j < VPT; ++j) e[j] = __expf(-fabsf(eta[j]));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ope[j] = 1.0f + e[j];
+        for (int j = 0; j < VPT; ++j) ope[j] = 1.0f + e[j];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rc[j] = __fdividef(1.0f, ope[j]);
+        for (int j = 0; j < VPT; ++j) rc[j] = __fdividef(1.0f, ope[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < VPT; ++j) {
           const float gj = ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j]);
           g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? gj : 0.0f;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < VPT; ++j) {
           const float rr = ycur - eta[j];
           g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? rr : 0.0f;
         }
       }
-      uint32_t e1[4], e2[4];
+      uint32_t e1[VPT / 2], e2[VPT / 2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
+      for (int j = 0; j < VPT / 2; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 34);
       mbar_wait(&bars->dl_empty, ph ^ 1);
       {
         uint8_t* rowp = sdl + r * 128;
         const int sw = r & 7;
-        *reinterpret_cast<uint4*>(rowp + (((2 * h + part) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
-        *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + part) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+        // row layout: [e1: 32 samples x 2 B | e2: 32 x 2 B], 16-byte chunks XOR-swizzled by the row
+        if constexpr (VPT == 8) {
+          *reinterpret_cast<uint4*>(rowp + (((2 * h + part) ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+          *reinterpret_cast<uint4*>(rowp + (((4 + 2 * h + part) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+        } else {
+          *reinterpret_cast<uint2*>(rowp + ((h ^ sw) << 4) + 8 * part) = make_uint2(e1[0], e1[1]);
+          *reinterpret_cast<uint2*>(rowp + (((4 + h) ^ sw) << 4) + 8 * part) = make_uint2(e2[0], e2[1]);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -784,33 +800,33 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if (!(ablate & 4)) {
         if (logit) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < VPT; ++j) {
             const bool ok = all_ok || (row_ok && (s0 + j) < S);
             stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
             prod[j] *= ok ? ope[j] : 1.0f;
           }
           if ((it & 31) == 31) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < VPT; ++j) {
               stat[j] -= logf(prod[j]);
               prod[j] = 1.0f;
             }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) stat[j] = fmaf(g[j], g[j], stat[j]);  // g = y - eta, already masked
+          for (int j = 0; j < VPT; ++j) stat[j] = fmaf(g[j], g[j], stat[j]);  // g = y - eta, already masked
         }
       }
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 35);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < VPT; ++j) {
       float v = stat[j] - logf(prod[j]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) sred[q * NS + s0 + j] = v;  // the other (q, sample) slots stay zero
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(tcp::EPI_WARPS * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
     if (warp == tcp::EPI_WARP0 && lane < S) {
       statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
     }
@@ -819,7 +835,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     if (my_tiles > 0) {
       for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, !((flushed >> ch) & 1u), true);
     } else {
-      for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * D; i += tcp::EPI_WARPS * 32) gp[i] = 0.0f;
+      for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * D; i += EW * 32) gp[i] = 0.0f;
     }
   }
 
@@ -894,22 +910,33 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     int rc;
     if ((rc = make_bf16_tensor_map(&maps.x1, planes, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
     if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * a.Dw, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
-#define BJX_TCP_LAUNCH(NBLK)                                                                                              \
+#define BJX_TCP_LAUNCH(NBLK, EW)                                                                                              \
   do {                                                                                                                    \
     static DeviceOnce attr_set;                                                                                         \
     if (!attr_set.test_and_set()) {                                                                                                      \
-      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK><<<p.tc_ctas, tcp::THREADS, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,    \
+    k_lik_tc_tma<NBLK, EW><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S, \
                                                               a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace); \
   } while (0)
+    static int epi_warps = -1;  // BJX_TC_EPI_WARPS = 8 | 16
+    if (epi_warps < 0) {
+      const char* e = getenv("BJX_TC_EPI_WARPS");
+      epi_warps = (e && atoi(e) == 16) ? 16 : 8;
+    }
+#define BJX_TCP_LAUNCH_EW(NBLK)                 \
+  do {                                          \
+    if (epi_warps == 16) BJX_TCP_LAUNCH(NBLK, 16); \
+    else BJX_TCP_LAUNCH(NBLK, 8);               \
+  } while (0)
     switch (nblk) {
-      case 2: BJX_TCP_LAUNCH(2); break;
-      case 4: BJX_TCP_LAUNCH(4); break;
-      case 6: BJX_TCP_LAUNCH(6); break;
-      case 8: BJX_TCP_LAUNCH(8); break;
+      case 2: BJX_TCP_LAUNCH_EW(2); break;
+      case 4: BJX_TCP_LAUNCH_EW(4); break;
+      case 6: BJX_TCP_LAUNCH_EW(6); break;
+      case 8: BJX_TCP_LAUNCH_EW(8); break;
       default: return fail(BJX_ERR_UNSUPPORTED, "tcgen05 kernel needs D in {128, 256, 384, 512}");
     }
+#undef BJX_TCP_LAUNCH_EW
 #undef BJX_TCP_LAUNCH
     BJX_LAUNCH_CHECK("k_lik_tc_tma");
     return BJX_OK;
