@@ -8,6 +8,7 @@
 //   EPI_LIK2  G^T[d, s] = sum_n X[n, d] g[n, s]       -> the transposed contraction of the VJP             (utils.py:7)
 //   EPI_Z     z[s, i]   = loc[i] + sum_{j<=i} L[i, j] eps[s, j]   full-rank sample, tfd.MultivariateNormalTriL (advi.py:83)
 //   EPI_DM    dM[i, j]  = [j<=i] scale'(M_ij) sum_s gz[s, i] eps[s, j] - [i==j] prior_weight dlog|L_ii|     its VJP
+//             (computed as the transposed tile sum_s eps[s, j] gz[s, i] so that the stores are coalesced)
 //
 // fp32 operands are pre-split into NT bf16 planes (x = x1 + x2 (+ x3), bjx_split_planes) so that every operand tile is a
 // plain TMA box; the products a_i * b_j with i + j <= NT + 1 accumulate in fp32 in TMEM (NT = 2: 3 products, 2^-17 relative;
@@ -42,7 +43,7 @@ struct Sched {
   int kb_total;          // k-blocks in the whole K extent
   int kb_per_split;
   int kb_per_vtile;      // k-blocks accumulated in TMEM before the epilogue takes the accumulator
-  int tril;              // 0 none; 1 EPI_Z: k <= last column index of the tile; 2 EPI_DM: tiles above the diagonal are empty
+  int tril;              // 0 none; 1 EPI_Z: k <= last column index of the tile; 2 EPI_DM (transposed tiles: rows j, columns i): tiles with all j > i are empty
 };
 
 struct EpiArgs {
@@ -107,7 +108,7 @@ __device__ __forceinline__ void for_each_vtile(const Sched& sc, F&& f) {
       const int lim = ((n_blk + 1) * BN + BK - 1) / BK;
       if (kb_hi > lim) kb_hi = lim;
     } else if (sc.tril == 2) {
-      if (n_blk * BN > m_blk * BMC + BMC - 1) kb_hi = kb_lo;
+      if (m_blk * BMC > n_blk * BN + BN - 1) kb_hi = kb_lo;  // every j of the tile is above every i: strictly upper triangle
     }
     if (kb_hi < kb_lo) kb_hi = kb_lo;
     int kb0 = kb_lo;
@@ -380,29 +381,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           }
         }
       } else {
-        // dM[i, j]: rows = i, columns = j
+        // transposed tile of dM: accumulator rows = j (column of dM), columns = i (row of dM), so that for a fixed i the 32
+        // lanes write -- and read M at -- consecutive addresses
         {
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
-            const int64_t j0 = (int64_t)n_blk * BN + c * 32;
-            if (j0 >= e.D) break;
+            const int64_t i0 = (int64_t)n_blk * BN + c * 32;
+            if (i0 >= e.D) break;
             uint32_t v[32];
             if (!empty) {  // warp-uniform
               tmem_ld32(t_acc + c * 32, v);
               tmem_ld_wait();
             }
-            if (r < e.D)
+            if (r < e.D) {
+              // all 32 loads of M first (independent, in flight together): the stores below may alias them for the compiler
+              float mv[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = j0 + j;
-              if (col < e.D) {
-                float val = 0.0f;
-                if (col <= r) {
-                  const ScaleEval se = eval_scale(e.M[r * e.D + col], e.scale_bij);
-                  val = (empty ? 0.0f : __uint_as_float(v[j])) * se.dsigma;
-                  if (col == r) val -= e.prior_weight * se.dlogsigma;
+              for (int j = 0; j < 32; ++j) {
+                const int64_t i = i0 + j;
+                mv[j] = (i < e.D && r <= i) ? __ldg(e.M + i * e.D + r) : 0.0f;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t i = i0 + j;
+                if (i < e.D) {
+                  float val = 0.0f;
+                  if (r <= i) {
+                    const ScaleEval se = eval_scale(mv[j], e.scale_bij);
+                    val = (empty ? 0.0f : __uint_as_float(v[j])) * se.dsigma;
+                    if (r == i) val -= e.prior_weight * se.dlogsigma;
+                  }
+                  e.out[i * e.D + r] = val;
                 }
-                e.out[r * e.D + col] = val;
               }
             }
           }
@@ -811,9 +821,9 @@ int launch_fullrank_dM_tc(const BjxElboArgs& a, const float* gz, float* dM, char
   Params P;
   memset(&P, 0, sizeof(P));
   int rc;
-  for (int t = 0; t < 3; ++t) {
-    if ((rc = make_map(&P.mapA[t], g0 + t * plane, a.S, a.D, Dp, 64, 64))) return rc;
-    if ((rc = make_map(&P.mapB[t], e0 + t * plane, a.S, a.D, Dp, 64, 64))) return rc;
+  for (int t = 0; t < 3; ++t) {  // A = eps (rows of the tile = j), B = gz (columns = i): the transposed tile of dM
+    if ((rc = make_map(&P.mapA[t], e0 + t * plane, a.S, a.D, Dp, 64, 64))) return rc;
+    if ((rc = make_map(&P.mapB[t], g0 + t * plane, a.S, a.D, Dp, 64, 64))) return rc;
   }
   P.sched.tiles_m = (int)((a.D + 127) / 128);
   P.sched.tiles_n = (int)((a.D + 127) / 128);
