@@ -167,7 +167,13 @@ class ElboEngine:
                 return None
             self._planes = None  # release the old planes before allocating new ones
             n = int(self.lib.bjx_x_planes_bytes(int(a.N), int(a.Dw)))
-            self._planes = torch.empty(n, dtype=torch.uint8, device=self.device)
+            try:
+                self._planes = torch.empty(n, dtype=torch.uint8, device=self.device)
+            except torch.cuda.OutOfMemoryError:
+                # no room for a second copy of the dataset: stay on the kernels that read raw fp32 X
+                self.prepare_dataset = False
+                self._planes, self._planes_key = None, None
+                return None
             with torch.cuda.device(self.device):
                 nv.check(self.lib.bjx_prepare_x_planes(X.data_ptr(), int(a.N), int(a.Dw), int(a.ldx), self._planes.data_ptr(),
                                                        nv.current_stream_ptr()))
