@@ -45,7 +45,7 @@ def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
     kw = dict(loss_fn.keywords)
     if not {"outputs", "inputs", "full_data_size"} <= set(kw) or set(kw) - {"outputs", "inputs", "full_data_size", "n_samples"}:
         return None
-    if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False) or getattr(model, "vi_type", "") == "low_rank":
+    if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False):
         return None
     return model, kw
 
@@ -99,7 +99,11 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
     post = params[key]
     from .advi import _scale_key
 
-    new_post = {"loc": flat[:D].reshape(loc.shape), _scale_key(model.vi_type): flat[D : D + P].reshape(raw.shape)}
+    if model.vi_type == "low_rank":
+        new_post = {"loc": flat[:D].reshape(loc.shape), "scale_diag": flat[D : 2 * D],
+                    "scale_perturb_factor": flat[2 * D : D + P].reshape(D, int(model.rank))}
+    else:
+        new_post = {"loc": flat[:D].reshape(loc.shape), _scale_key(model.vi_type): flat[D : D + P].reshape(raw.shape)}
     new_params = {key: new_post}
     o = D + P
     for name in sorted(kwargs):

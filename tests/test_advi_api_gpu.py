@@ -251,3 +251,24 @@ def test_map_training_recovers_the_ridge_solution():
     assert np.allclose(w, ridge, atol=2e-3), np.abs(w - ridge).max()
     assert res["losses"][-1] < res["losses"][0]
     assert torch.equal(model.apply(res["params"])["weights"].cpu(), res["params"]["params"]["weights"].cpu())
+
+
+def test_device_resident_loop_with_the_low_rank_family():
+    """The fused training loop carries [loc | raw scale_diag | scale_perturb_factor | kwargs] as one flat vector."""
+    from bijax_b200 import random as br
+    from functools import partial
+    from tests import cases as C
+
+    N, D, r = 2048, 12, 3
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D), scale_diag=np.ones(D))}, {}, lk.BernoulliLogits(),
+                    vi_type="low_rank", rank=r)
+    fresh = lambda: model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.05 * br.normal(k, shape))
+    loss_fn = partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=8)
+    fused = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=40, seed=br.PRNGKey(3))
+    host = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=40, seed=br.PRNGKey(3), fused=False)
+    assert fused["params"]["posterior"]["scale_perturb_factor"].shape == (D, r)
+    assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-4)
+    for k in ("loc", "scale_diag", "scale_perturb_factor"):
+        assert torch.allclose(fused["params"]["posterior"][k], host["params"]["posterior"][k], rtol=1e-4, atol=2e-5), k
