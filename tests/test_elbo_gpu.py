@@ -446,6 +446,21 @@ def test_low_rank_family(D, r, S, lik, kernel):
         assert np.abs(smp.mean(0) - loc).max() < 0.02
 
 
+def test_c4_shape_family_full_rank_wide():
+    """config c4's shape family at reduced N: full-rank Gaussian linear regression with D = 1024 and S = 256 -- CTA-pair
+    (cta_group::2) GEMM passes with 256-wide tiles, the tensor-core L.eps and dM contractions -- against the float64 oracle."""
+    D, S, N = 1024, 256, 1500
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    X, y = C.synth_linear(N, D)
+    model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), vi_type="full_rank", kernel="tcgen05_gemm_two_pass")
+    kwargs = {"log_noise_scale": np.float32(math.log(0.2))}
+    loc = 0.1 * tf.normal(tf.prng_key(6), (D,), 1)
+    M = (0.1 * np.eye(D) + 0.002 * tf.normal(tf.prng_key(8), (D, D), 1)).astype(np.float32)  # conditioning stated: 0.1 I + 0.002 noise
+    loss, grads = _run_case(model, ref, loc, M, kwargs, y, X, N, 17, S, 0, expect_kernel="tcgen05_gemm_two_pass")
+    g = grads["posterior"]["scale_tril"].cpu().numpy()
+    assert np.all(np.triu(g, 1) == 0.0)
+
+
 def _np_fill_triangular(x):
     """tfp.math.fill_triangular(x, upper=False) restated in NumPy (documented example: [1..6] -> [[4,0,0],[6,5,0],[3,2,1]])."""
     m = x.shape[-1]
