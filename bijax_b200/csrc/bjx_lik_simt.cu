@@ -16,7 +16,7 @@ namespace bjx {
 // =====================================================================================================================
 constexpr int SD_CHUNK = SD_CHUNK_ROWS;
 
-template <int REC4>
+template <int REC4, int DWT>  // DWT = the column count as a compile-time constant: the padding slots cost no FMAs
 __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y,
                                                     int64_t N, int Dw, const float* __restrict__ theta, int64_t D,
                                                     int64_t w_off, int S, int family, int SB, int64_t rows_per_cta,
@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
 #pragma unroll
       for (int u = 0; u < ROWS; ++u) eta[u] = 0.0f;
 #pragma unroll
-      for (int d = 1; d < REC; ++d)
+      for (int d = 1; d <= DWT; ++d)
 #pragma unroll
-        for (int u = 0; u < ROWS; ++u) eta[u] = fmaf(rec[u][d], th[d], eta[u]);  // th[d > Dw] == 0: padding drops out
+        for (int u = 0; u < ROWS; ++u) eta[u] = fmaf(rec[u][d], th[d], eta[u]);
 #pragma unroll
       for (int u = 0; u < ROWS; ++u) {
         float f, g;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X,
         stat += ok ? f : 0.0f;
         g = ok ? g : 0.0f;
 #pragma unroll
-        for (int d = 1; d < REC; ++d) G[d] = fmaf(g, rec[u][d], G[d]);
+        for (int d = 1; d <= DWT; ++d) G[d] = fmaf(g, rec[u][d], G[d]);
       }
     }
   }
@@ -119,10 +119,11 @@ int smalld_occupancy(int rec4) {
   int occ = 0;
   cudaError_t e = cudaErrorInvalidValue;
   switch (rec4) {
-    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<1>, 256, 0); break;
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<2>, 256, 0); break;
-    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<3>, 256, 0); break;
-    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<4>, 256, 0); break;
+    // (the widest column count of each record width: the most registers, a safe lower bound for the others)
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<1, 3>, 256, 0); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<2, 7>, 256, 0); break;
+    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<3, 11>, 256, 0); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<4, 15>, 256, 0); break;
     default: break;
   }
   return (e == cudaSuccess && occ > 0) ? occ : 1;
@@ -134,14 +135,25 @@ int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_
   float* statpart = (float*)(ws + p.o_statpart);
   const int64_t rows_per_cta = (a.N + p.sd_grid_x - 1) / p.sd_grid_x;
   dim3 grid(p.sd_grid_x, p.sd_grid_y);
-#define BJX_SD_LAUNCH(R4)                                                                                          \
-  k_lik_smalld<R4><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,       \
-                                         a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart)
-  switch (p.sd_rec4) {
-    case 1: BJX_SD_LAUNCH(1); break;
-    case 2: BJX_SD_LAUNCH(2); break;
-    case 3: BJX_SD_LAUNCH(3); break;
-    case 4: BJX_SD_LAUNCH(4); break;
+#define BJX_SD_LAUNCH(R4, DW)                                                                                      \
+  k_lik_smalld<R4, DW><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,   \
+                                             a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart)
+  switch ((int)a.Dw) {
+    case 1: BJX_SD_LAUNCH(1, 1); break;
+    case 2: BJX_SD_LAUNCH(1, 2); break;
+    case 3: BJX_SD_LAUNCH(1, 3); break;
+    case 4: BJX_SD_LAUNCH(2, 4); break;
+    case 5: BJX_SD_LAUNCH(2, 5); break;
+    case 6: BJX_SD_LAUNCH(2, 6); break;
+    case 7: BJX_SD_LAUNCH(2, 7); break;
+    case 8: BJX_SD_LAUNCH(3, 8); break;
+    case 9: BJX_SD_LAUNCH(3, 9); break;
+    case 10: BJX_SD_LAUNCH(3, 10); break;
+    case 11: BJX_SD_LAUNCH(3, 11); break;
+    case 12: BJX_SD_LAUNCH(4, 12); break;
+    case 13: BJX_SD_LAUNCH(4, 13); break;
+    case 14: BJX_SD_LAUNCH(4, 14); break;
+    case 15: BJX_SD_LAUNCH(4, 15); break;
     default: return fail(BJX_ERR_UNSUPPORTED, "small-D kernel supports Dw <= 15 (got %lld)", (long long)a.Dw);
   }
 #undef BJX_SD_LAUNCH
