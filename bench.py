@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--p2p-allreduce", action="store_true",
+                    help="N > 1: the exchange step as one kernel over NVLink peer memory (bjx_allreduce_packed_p2p) instead of NCCL")
     ap.add_argument("--raw-fp32", action="store_true",
                     help="do not keep the dataset as prepared split-bf16 planes: the kernel converts raw fp32 X in registers every step")
     return ap.parse_args()
@@ -225,10 +227,22 @@ def run_ours(args):
     keys = br.split(br.PRNGKey(0), W + K)  # per-step key = split(seed, n)[i]  (utils.py:30)
     out = torch.empty(1 + 2 * D, device=dev)
 
+    p2p = None
+    if world > 1 and args.p2p_allreduce:
+        from bijax_b200.parallel import P2PAllReduce
+
+        p2p = P2PAllReduce(out.numel(), None, dev)
+
+    def allreduce(t):
+        if p2p is not None:
+            p2p(t)
+        else:
+            dist.all_reduce(t)
+
     def step(i):
         engine.step(keys[i], loc, raw, None, X, y, ll_scale, S, prior_weight, out=out, partitionable=False)
         if world > 1:
-            dist.all_reduce(out)
+            allreduce(out)
 
     def barrier():
         if world > 1:
@@ -289,7 +303,7 @@ def run_ours(args):
                 p = params_host.to(dev, non_blocking=True)
                 k = torch.from_numpy(keys_host[i].astype(np.int64)).to(torch.uint32).to(dev, non_blocking=True)
                 engine.step(k, p[:D], p[D:], None, X, y, ll_scale, S, prior_weight, out=stage, partitionable=False)
-                dist.all_reduce(stage)
+                allreduce(stage)
                 out_host.copy_(stage, non_blocking=False)
 
         for i in range(min(W, 3)):
@@ -340,6 +354,8 @@ def run_ours(args):
                              f"c5 shard: Bayesian logistic regression, mean-field, D=512, S=32, {rows} rows per GPU x {world} GPUs, NCCL all-reduce of [loss|grads]"),
                 "rows_per_gpu": rows, "rows_total": n_total, "D": D, "S": S, "precision": args.precision, "kernel": kernel,
                 "l2": "inputs_larger_than_l2 (X shard is >= 20 GB, read once per step)", "threefry_layout": "legacy",
+                "exchange": ("none (one GPU)" if world == 1 else
+                             "one-shot all-reduce kernel over NVLink peer memory (bjx_allreduce_packed_p2p)" if p2p is not None else "NCCL all-reduce"),
                 "dataset_layout": ("split-bf16 planes x1+x2 (4 B/element, prepared once per dataset in %.1f ms, TMA-fed kernel)" % prepare_ms
                                    if prepared else "raw fp32 X (converted in registers every step)"),
             },
@@ -348,6 +364,8 @@ def run_ours(args):
             "steps_per_s_actual": steps_per_s, "snd_per_s": steps_per_s * S * n_total * D, "loss_last_step": loss_value,
         }
         print(json.dumps(line), flush=True)
+    if p2p is not None:
+        p2p.close()
     if world > 1:
         dist.destroy_process_group()
 

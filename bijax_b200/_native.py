@@ -40,6 +40,12 @@ EXPORTED_SYMBOLS = (
     "bjx_elbo_step_host",
     "bjx_elbo_kernel_choice",
     "bjx_train_steps",
+    "bjx_p2p_buffer_bytes",
+    "bjx_p2p_alloc",
+    "bjx_p2p_open",
+    "bjx_p2p_close",
+    "bjx_p2p_free",
+    "bjx_allreduce_packed_p2p",
     "bjx_x_planes_bytes",
     "bjx_prepare_x_planes",
     "bjx_posterior_sample",
@@ -140,6 +146,13 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
     lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
+    lib.bjx_p2p_buffer_bytes.argtypes = [i64, i32]
+    lib.bjx_p2p_buffer_bytes.restype = C.c_size_t
+    lib.bjx_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+    lib.bjx_p2p_open.argtypes = [vp, C.POINTER(vp)]
+    lib.bjx_p2p_close.argtypes = [vp]
+    lib.bjx_p2p_free.argtypes = [vp]
+    lib.bjx_allreduce_packed_p2p.argtypes = [vp, i64, C.POINTER(vp), i32, i32, C.c_uint64, vp]
     lib.bjx_x_planes_bytes.argtypes = [i64, i64]
     lib.bjx_x_planes_bytes.restype = C.c_size_t
     lib.bjx_prepare_x_planes.argtypes = [vp, i64, i64, i64, vp, vp]
@@ -154,7 +167,7 @@ def load() -> C.CDLL:
     lib.bjx_debug_set_trace_buffer.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what bjx.h declares
-        if name not in ("bjx_last_error", "bjx_elbo_workspace_bytes", "bjx_abi_version", "bjx_device_sm_count", "bjx_x_planes_bytes"):
+        if name not in ("bjx_last_error", "bjx_elbo_workspace_bytes", "bjx_abi_version", "bjx_device_sm_count", "bjx_x_planes_bytes", "bjx_p2p_buffer_bytes"):
             fn.restype = C.c_int
     if lib.bjx_abi_version() != ABI_VERSION:
         raise ImportError(f"libbjx ABI {lib.bjx_abi_version()} != expected {ABI_VERSION}; rebuild with `python -m bijax_b200.build --force`")

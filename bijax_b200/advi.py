@@ -210,7 +210,7 @@ class ADVI:
                                             prepare_dataset=self.prepare_dataset, rank=self.rank)
         return self._engines[sig], leaves
 
-    def distributed(self, group=None, global_len: Optional[int] = None, shard: str = "rows"):
+    def distributed(self, group=None, global_len: Optional[int] = None, shard: str = "rows", p2p: bool = False):
         """Data parallelism with one all-reduce of the packed [loss | grads] buffer per step.
         ``shard="rows"``: ``outputs`` / ``inputs`` passed to loss_fn are this rank's row shard.  ``shard="samples"`` (for
         small N): every rank passes the full data and evaluates its block of the ``n_samples`` Monte-Carlo samples."""
@@ -221,6 +221,9 @@ class ADVI:
         self._group = group if group is not None else dist.group.WORLD
         self._global_len = global_len
         self._shard = shard
+        # p2p=True: the all-reduce is one kernel over NVLink peer memory (parallel.P2PAllReduce) instead of an NCCL call
+        self._p2p = bool(p2p)
+        self._p2p_op = None
         return self
 
     def _run(self, engine, seed, outputs, inputs, full_data_size, n_samples):
@@ -259,7 +262,14 @@ class ADVI:
             if self._group is not None:
                 import torch.distributed as dist
 
-                dist.all_reduce(out, group=self._group)
+                if getattr(self, "_p2p", False):
+                    if self._p2p_op is None or self._p2p_op.n != out.numel():
+                        from .parallel import P2PAllReduce
+
+                        self._p2p_op = P2PAllReduce(out.numel(), self._group, engine.device)
+                    self._p2p_op(out)
+                else:
+                    dist.all_reduce(out, group=self._group)
             return out
 
         return run

@@ -55,3 +55,68 @@ def allreduce_packed(out: torch.Tensor, group=None) -> torch.Tensor:
     """The single exchange step of the path: in-place sum of the packed loss+gradient buffer."""
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+class P2PAllReduce:
+    """The exchange step as ONE kernel over NVLink peer memory (bjx_allreduce_packed_p2p) instead of an NCCL call: every
+    rank stores its packed [loss | grads] vector into a slot of every peer's buffer, raises a flag, waits for the peers'
+    flags and sums the slots in rank order.  One process per GPU of ONE box (CUDA IPC); at most 8 ranks.  The process
+    group is used once, to exchange the 64-byte IPC handles."""
+
+    def __init__(self, n: int, group=None, device=None):
+        import ctypes as C
+
+        from . import _native as nv
+
+        self.lib = nv.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("the peer-memory all-reduce covers the <= 8 GPUs of one box")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n = int(n)
+        nbytes = int(self.lib.bjx_p2p_buffer_bytes(self.n, self.world))
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.bjx_p2p_alloc(nbytes, C.byref(own), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        self._own = own
+        self._ptrs = (C.c_void_p * self.world)()
+        self._opened = []
+        with torch.cuda.device(self.device):
+            for p in range(self.world):
+                if p == self.rank:
+                    self._ptrs[p] = own.value
+                else:
+                    q = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+                    nv.check(self.lib.bjx_p2p_open(hb, C.byref(q)))
+                    self._ptrs[p] = q.value
+                    self._opened.append(q)
+        dist.barrier(group=self.group)  # every buffer is mapped everywhere before the first epoch
+        self.epoch = 0
+
+    def __call__(self, out: torch.Tensor) -> torch.Tensor:
+        from . import _native as nv
+
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == self.n
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.bjx_allreduce_packed_p2p(out.data_ptr(), self.n, self._ptrs, self.rank, self.world, self.epoch,
+                                                       nv.current_stream_ptr()))
+        return out
+
+    def close(self):
+        from . import _native as nv
+
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody is still pushing into a buffer that is about to be unmapped
+        with torch.cuda.device(self.device):
+            for q in self._opened:
+                nv.check(self.lib.bjx_p2p_close(q))
+            self._opened = []
+            if self._own is not None:
+                nv.check(self.lib.bjx_p2p_free(self._own))
+                self._own = None

@@ -249,6 +249,21 @@ BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grad
 BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, float lr,
                     float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream);
 
+/* ---- the exchange step over NVLink peer memory (one kernel instead of an NCCL call) ---------------------------------
+ * One-shot all-reduce (sum, in place) of the packed [loss | grads] buffer across the <= 8 GPUs of a box: every rank
+ * stores its vector into a slot of every peer's buffer over NVLink, raises a flag, waits for the peers' flags and sums
+ * the slots in rank order (deterministic).  Set-up, once: bjx_p2p_alloc (cudaMalloc + cudaIpcGetMemHandle), exchange the
+ * 64-byte handles between the processes, bjx_p2p_open the peers'.  Per step: bjx_allreduce_packed_p2p with epoch = 1, 2,
+ * 3, ... in lockstep on every rank, on the stream that ran bjx_elbo_step.  The replaced call is the psum / ncclAllReduce of
+ * SURVEY.md section 8e (the reference itself is single-device). */
+BJX_API size_t bjx_p2p_buffer_bytes(int64_t n, int32_t world);
+BJX_API int bjx_p2p_alloc(size_t bytes, void** ptr_out, void* handle_out_64_bytes);
+BJX_API int bjx_p2p_open(const void* handle_64_bytes, void** ptr_out);
+BJX_API int bjx_p2p_close(void* peer_ptr);
+BJX_API int bjx_p2p_free(void* own_ptr);
+BJX_API int bjx_allreduce_packed_p2p(float* out, int64_t n, void* const* bufs_host, int32_t rank, int32_t world, uint64_t epoch,
+                             void* stream);
+
 /* ---- in-library timing of the dominant (streaming likelihood) kernel -------
  * bjx_profile_begin(capacity): from now on every bjx_elbo_step on this thread records a CUDA event pair around its
  * streaming-likelihood launch(es) on the caller's stream (no synchronisation); bjx_profile_collect synchronises on the
