@@ -51,8 +51,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline time budget at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--p2p-allreduce", action="store_true",
-                    help="N > 1: the exchange step as one kernel over NVLink peer memory (bjx_allreduce_packed_p2p) instead of NCCL")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: use NCCL for the exchange step instead of the one-kernel all-reduce over NVLink peer memory "
+                         "(bjx_allreduce_packed_p2p, the default)")
     ap.add_argument("--raw-fp32", action="store_true",
                     help="do not keep the dataset as prepared split-bf16 planes: the kernel converts raw fp32 X in registers every step")
     return ap.parse_args()
@@ -228,10 +229,15 @@ def run_ours(args):
     out = torch.empty(1 + 2 * D, device=dev)
 
     p2p = None
-    if world > 1 and args.p2p_allreduce:
+    if world > 1 and not args.nccl_allreduce:
         from bijax_b200.parallel import P2PAllReduce
 
-        p2p = P2PAllReduce(out.numel(), None, dev)
+        try:
+            p2p = P2PAllReduce(out.numel(), None, dev)  # raises on every rank together if any rank cannot map its peers
+        except RuntimeError as exc:
+            if rank == 0:
+                print(f"[bench] peer-memory all-reduce unavailable ({exc}); using NCCL", file=sys.stderr, flush=True)
+            p2p = None
 
     def allreduce(t):
         if p2p is not None:

@@ -78,24 +78,37 @@ class P2PAllReduce:
         nbytes = int(self.lib.bjx_p2p_buffer_bytes(self.n, self.world))
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        with torch.cuda.device(self.device):
-            nv.check(self.lib.bjx_p2p_alloc(nbytes, C.byref(own), handle))
+        error = None
+        try:
+            with torch.cuda.device(self.device):
+                nv.check(self.lib.bjx_p2p_alloc(nbytes, C.byref(own), handle))
+        except Exception as exc:  # keep going: every rank must take part in the collectives below
+            error = exc
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=self.group)
-        self._own = own
+        self._own = own if error is None else None
         self._ptrs = (C.c_void_p * self.world)()
         self._opened = []
-        with torch.cuda.device(self.device):
-            for p in range(self.world):
-                if p == self.rank:
-                    self._ptrs[p] = own.value
-                else:
-                    q = C.c_void_p()
-                    hb = (C.c_ubyte * 64).from_buffer_copy(handles[p])
-                    nv.check(self.lib.bjx_p2p_open(hb, C.byref(q)))
-                    self._ptrs[p] = q.value
-                    self._opened.append(q)
-        dist.barrier(group=self.group)  # every buffer is mapped everywhere before the first epoch
+        if error is None:
+            try:
+                with torch.cuda.device(self.device):
+                    for p in range(self.world):
+                        if p == self.rank:
+                            self._ptrs[p] = own.value
+                        else:
+                            q = C.c_void_p()
+                            hb = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+                            nv.check(self.lib.bjx_p2p_open(hb, C.byref(q)))
+                            self._ptrs[p] = q.value
+                            self._opened.append(q)
+            except Exception as exc:
+                error = exc
+        # agreement (also the barrier: every buffer is mapped everywhere before the first epoch): all ranks succeed or all raise
+        ok = torch.tensor([0.0 if error is not None else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0.0:
+            self._release()
+            raise RuntimeError(f"peer-memory all-reduce could not be set up on every rank (this rank: {error})")
         self.epoch = 0
 
     def __call__(self, out: torch.Tensor) -> torch.Tensor:
@@ -108,15 +121,16 @@ class P2PAllReduce:
                                                        nv.current_stream_ptr()))
         return out
 
-    def close(self):
-        from . import _native as nv
-
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)  # nobody is still pushing into a buffer that is about to be unmapped
+    def _release(self):
         with torch.cuda.device(self.device):
             for q in self._opened:
-                nv.check(self.lib.bjx_p2p_close(q))
+                self.lib.bjx_p2p_close(q)
             self._opened = []
             if self._own is not None:
-                nv.check(self.lib.bjx_p2p_free(self._own))
+                self.lib.bjx_p2p_free(self._own)
                 self._own = None
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody is still pushing into a buffer that is about to be unmapped
+        self._release()
