@@ -272,3 +272,25 @@ def test_device_resident_loop_with_the_low_rank_family():
     assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-4)
     for k in ("loc", "scale_diag", "scale_perturb_factor"):
         assert torch.allclose(fused["params"]["posterior"][k], host["params"]["posterior"][k], rtol=1e-4, atol=2e-5), k
+
+
+def test_peer_memory_allreduce_kernel_single_rank(tmp_path):
+    """The one-kernel exchange step (bjx_allreduce_packed_p2p) on a world of one: slot push, epoch flag, rank-order sum and
+    the alternation of the two slot sets over many epochs leave the vector unchanged.  (Worlds of 2 and 8 are exercised by
+    scripts/p2p_check.py under torchrun: bit-equal to the rank-order sum, profiles/ and DESIGN.md section 6.)"""
+    import torch.distributed as dist
+
+    from bijax_b200.parallel import P2PAllReduce
+
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        op = P2PAllReduce(1025, None, torch.device("cuda"))
+        for i in range(5):
+            v = torch.randn(1025, device="cuda")
+            w = v.clone()
+            op(w)
+            assert torch.equal(v, w)
+        assert op.epoch == 5
+        op.close()
+    finally:
+        dist.destroy_process_group()
