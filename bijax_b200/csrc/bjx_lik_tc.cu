@@ -141,7 +141,6 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     // unit = quarter of a block: rows 16*qd .. 16*qd+15, 64 columns.  lane -> (row 4*i + lane/8, 16-byte chunk lane%8).
     const int qd = warp & 3, bl = warp >> 2;
     const int rl = lane >> 3, c = lane & 7;
-    const int64_t total_blocks = my_tiles * NBLK;
     // De-phase the CTAs: with identical work per tile all SMs would issue their 64 KB load bursts in lockstep (a 9.5 MB
     // burst every tile period, ~3500-cycle load latency measured); a one-off start-up skew spreads the HBM demand.
     if (stagger_cycles > 0 && my_tiles > 4) {
@@ -150,9 +149,14 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       while (clock64() - t_start < delay) {
       }
     }
-    for (int64_t g = bl; g < total_blocks; g += 4) {
-      const int64_t it = g / NBLK;
-      const int b = (int)(g % NBLK);
+    // A warp set owns FIXED block indices (bl, bl + 4, ...) in every tile: the parity waits on x_empty[b] below are only
+    // unambiguous if the same waiter meets every phase of the barrier.  (A flat round-robin over blocks made a set meet a
+    // block only every other tile for D = 128 and 384, two phases apart: the wait could pass on a stale phase.)  For
+    // D = 128 the sets 2 and 3 therefore idle.
+    for (int64_t u = 0; u < my_tiles * 2; ++u) {
+      const int64_t it = u >> 1;
+      const int b = bl + 4 * (int)(u & 1);
+      if (b >= NBLK) continue;
       const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS + 16 * qd + rl;
       float4 v[8];
 #pragma unroll
@@ -170,10 +174,10 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       // fire-and-forget L2 prefetch of the SAME unit of the next tile (16 rows x 256 B = 32 lines, one per lane): HBM keeps
       // streaming into the 126 MB L2 while this warp's registers are tied up waiting for the shared-memory slot
       if (pf_dist > 0 && pf_mode < 2) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
-        const int64_t gp = g + pf_dist;
-        const int64_t prow = (blockIdx.x + (gp / NBLK) * gridDim.x) * TILE_ROWS + 16 * qd + (lane >> 1);
-        if (gp < total_blocks && prow < N) {
-          const float* pp = X + prow * ldx + (gp % NBLK) * BLK_COLS + (lane & 1) * 32;
+        const int64_t itp = it + (pf_dist >= 8 ? pf_dist / 8 : 1);  // the same unit, pf_dist / 8 tiles ahead
+        const int64_t prow = (blockIdx.x + itp * gridDim.x) * TILE_ROWS + 16 * qd + (lane >> 1);
+        if (itp < my_tiles && prow < N) {
+          const float* pp = X + prow * ldx + b * BLK_COLS + (lane & 1) * 32;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
           if (pf_mode == 1) {  // touch every 32-byte sector of the 128-byte line
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 8));
@@ -447,8 +451,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 // the swizzled UMMA image.  No loader warps, no registers in flight, no conversion and no generic-proxy stores or fences
 // on the shared-memory port: one producer thread, one MMA warp, eight epilogue warps (320 threads).
 namespace tcp {
-constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2;  // then EW (8 or 16) epilogue warps
 struct Maps {
   CUtensorMap x1, x2;
 };

@@ -211,7 +211,8 @@ def test_error_paths():
 @pytest.mark.parametrize(
     "N,D,S,lik",
     [(64, 128, 32, "logit"), (1, 128, 32, "logit"), (65, 256, 16, "logit"), (1000, 512, 32, "logit"),
-     (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss")],
+     (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss"),
+     (40000, 128, 32, "logit"), (30000, 384, 20, "gauss")],  # several tiles per CTA for every block count
 )
 @pytest.mark.parametrize("prepared", [True, False])
 def test_tensor_core_path(N, D, S, lik, prepared):
