@@ -212,7 +212,7 @@ def test_error_paths():
     "N,D,S,lik",
     [(64, 128, 32, "logit"), (1, 128, 32, "logit"), (65, 256, 16, "logit"), (1000, 512, 32, "logit"),
      (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss"),
-     (40000, 128, 32, "logit"), (30000, 384, 20, "gauss")],  # several tiles per CTA for every block count
+     (40000, 128, 32, "logit"), (30000, 384, 20, "gauss"), (50000, 256, 32, "logit")],  # several tiles per CTA for every block count
 )
 @pytest.mark.parametrize("prepared", [True, False])
 def test_tensor_core_path(N, D, S, lik, prepared):
@@ -235,7 +235,7 @@ def test_tensor_core_path(N, D, S, lik, prepared):
 @pytest.mark.parametrize(
     "N,D,S,lik",
     [(300, 64, 40, "gauss"), (1000, 200, 64, "logit"), (4097, 512, 130, "gauss"), (2500, 1000, 256, "logit"),
-     (129, 2048, 256, "gauss"), (70000, 128, 33, "logit"), (1, 64, 1, "gauss")],
+     (129, 2048, 256, "gauss"), (70000, 128, 33, "logit"), (1, 64, 1, "gauss"), (45000, 192, 100, "gauss")],
 )
 def test_two_pass_tensor_core_gemm_path(N, D, S, lik):
     """config c4 shape family (S up to 256, D up to 2048): TMA-fed tcgen05 GEMMs with split-bf16 operand planes,
