@@ -607,6 +607,32 @@ def test_large_shape_properties_of_the_tensor_core_path():
     C.assert_close(full[1 + D :].cpu().numpy(), other[1 + D :].cpu().numpy(), what="d rho vs fp32 kernel")
 
 
+@pytest.mark.parametrize("D,prepared", [(128, True), (384, True), (256, True), (128, False), (384, False)])
+def test_accumulator_folding_with_few_blocks_per_tile(D, prepared):
+    """Enough tiles per CTA (21+) that the periodic folding of the GEMM2 accumulators runs for every block count
+    (D = 128, 256, 384 have 1, 2, 3 chunks, so a different folding rotation than D = 512): the fused tensor-core kernels
+    against the independent fp32 CUDA-core kernel on the same device data, plus bit-reproducibility."""
+    from bijax_b200 import random as br
+
+    N, S = 200_000, 32
+    X, y = _device_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), prepare_dataset=prepared)
+    eng = model._engine_for({})[0]
+    assert eng.kernel_choice(S, N) == "tcgen05_bf16_split"
+    loc = 0.02 * br.normal(br.PRNGKey(5), (D,), partitionable=True)
+    raw = torch.full((D,), math.log(0.1), device=X.device)
+    key = br.PRNGKey(77)
+    a = eng.step(key, loc, raw, None, X, y, 1.0, S).clone()
+    b = eng.step(key, loc, raw, None, X, y, 1.0, S).clone()
+    assert torch.equal(a, b)
+    ref_eng = _tc_engine(D, precision="fp32")
+    other = ref_eng.step(key, loc, raw, None, X, y, 1.0, S)
+    C.assert_close(a[:1].cpu().numpy(), other[:1].cpu().numpy(), what="loss vs fp32 kernel")
+    C.assert_close(a[1 : 1 + D].cpu().numpy(), other[1 : 1 + D].cpu().numpy(), what="d loc vs fp32 kernel")
+    C.assert_close(a[1 + D :].cpu().numpy(), other[1 + D :].cpu().numpy(), what="d rho vs fp32 kernel")
+
+
 def test_sample_count_invariance_of_eps_layout():
     """eps for (S, D) is the flat stream reshaped, so the first S' < S samples of a partitionable draw are the S'-sample
     draw: sharding the Monte-Carlo samples (small-N case) reproduces the same noise."""
