@@ -235,7 +235,8 @@ def test_tensor_core_path(N, D, S, lik, prepared):
 @pytest.mark.parametrize(
     "N,D,S,lik",
     [(300, 64, 40, "gauss"), (1000, 200, 64, "logit"), (4097, 512, 130, "gauss"), (2500, 1000, 256, "logit"),
-     (129, 2048, 256, "gauss"), (70000, 128, 33, "logit"), (1, 64, 1, "gauss"), (45000, 192, 100, "gauss")],
+     (129, 2048, 256, "gauss"), (70000, 128, 33, "logit"), (1, 64, 1, "gauss"), (45000, 192, 100, "gauss"),
+     (700, 64, 300, "logit"), (900, 128, 520, "gauss")],  # more samples than one 256-wide tile
 )
 def test_two_pass_tensor_core_gemm_path(N, D, S, lik):
     """config c4 shape family (S up to 256, D up to 2048): TMA-fed tcgen05 GEMMs with split-bf16 operand planes,
