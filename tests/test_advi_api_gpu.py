@@ -294,3 +294,23 @@ def test_peer_memory_allreduce_kernel_single_rank(tmp_path):
         op.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_device_resident_loop_captures_the_two_pass_tensor_core_path():
+    """CUDA-graph capture of bjx_train_steps over the TMA-fed two-pass path (tensor-map encodes on the host at capture time,
+    memset nodes, CTA-pair cluster launches): graph replay equals the host-driven loop."""
+    from bijax_b200 import random as br
+    from functools import partial
+    from tests import cases as C
+
+    N, D, S = 3000, 128, 160  # S > 128: 256-wide tiles, cta_group::2
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D), scale_diag=np.ones(D))}, {}, lk.BernoulliLogits(),
+                    kernel="tcgen05_gemm_two_pass")
+    fresh = lambda: model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.05 * br.normal(k, shape))
+    loss_fn = partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=S)
+    fused = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=36, seed=br.PRNGKey(3))
+    host = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=36, seed=br.PRNGKey(3), fused=False)
+    assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-4)
+    assert torch.allclose(fused["params"]["posterior"]["loc"], host["params"]["posterior"]["loc"], rtol=1e-4, atol=2e-5)
