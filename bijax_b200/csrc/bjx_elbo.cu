@@ -90,6 +90,10 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   if (a.likelihood == BJX_LIK_BERNOULLI_PROBS) {
     BJX_REQUIRE(a.w_offset >= 0 && a.w_offset < a.D, "w_offset out of range");
     p.kernel = KERNEL_COIN;
+    p.tiny = (a.vi_type == BJX_VI_MEAN_FIELD && a.point_mode == BJX_POINT_OFF && a.S * a.D <= TINY_SD && a.S <= TINY_S &&
+              a.N <= TINY_N && a.kernel_override == 0)
+                 ? 1
+                 : 0;
   } else if (a.likelihood == BJX_LIK_BERNOULLI_LOGITS || a.likelihood == BJX_LIK_GAUSSIAN) {
     BJX_REQUIRE(a.Dw >= 1 && a.w_offset >= 0 && a.w_offset + a.Dw <= a.D, "weights [w_offset, w_offset+Dw) must lie in [0, D)");
     BJX_REQUIRE(a.ldx >= a.Dw, "ldx must be >= Dw");
@@ -519,6 +523,92 @@ __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t 
   }
 }
 
+// ---- tiny problems: the whole step in ONE block ---------------------------------------------------------------------------
+// Config c1 (coin toss: D = 1, S = 16, N = 100) is pure launch latency -- four launches of a few hundred threads.  This
+// kernel runs the same four stages (k_prologue -> k_lik_coin -> k_tail -> k_scalars, same formulas) back to back in one
+// block with shared memory in place of the global workspace.  Mean field, tfd.Bernoulli(probs = theta) likelihood,
+// S * D <= 1024, S <= 256, N <= 4096.
+
+__global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restrict__ key, const int64_t* __restrict__ key_index,
+                                                        const float* __restrict__ loc, const float* __restrict__ raw,
+                                                        const BjxCoord* __restrict__ coords, int S, int D, int scale_bij,
+                                                        int layout, const float* __restrict__ y, int N, int probs_coord,
+                                                        float prior_weight, float entropy_weight, float ll_scale,
+                                                        int64_t s_offset, int64_t S_total, int64_t K,
+                                                        float* __restrict__ eps_out, float* __restrict__ out) {
+  __shared__ float s_eps[TINY_SD], s_gprior[TINY_SD];
+  __shared__ float4 s_aux[TINY_S];
+  __shared__ float s_G[TINY_S], s_stat[TINY_S];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = S * D;
+  const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
+  // ---- stage 1 (k_prologue): eps, z, bijector, prior and entropy terms
+  float term = 0.0f;
+  for (int i = tid; i < total; i += 256) {
+    const int d = i % D;
+    const uint32_t bits = random_bits_at(k[0], k[1], (uint64_t)(i + s_offset * D), (uint64_t)(S_total * D), layout);
+    const float eps = bits_to_normal(bits);
+    const float rho = raw[d];
+    const ScaleEval sc = eval_scale(rho, scale_bij);
+    const float z = loc[d] + sc.sigma * eps;
+    const float logsig = scale_bij == BJX_SCALE_EXP ? rho : logf(sc.sigma);
+    const CoordEval ce = eval_coord(z, coords[d]);
+    s_eps[i] = eps;
+    s_gprior[i] = -ce.dlogp;
+    if (eps_out) eps_out[i] = eps;
+    if (d == probs_coord) s_aux[i / D] = make_float4(ce.lt, ce.l1t, ce.dlt, ce.dl1t);
+    term += (-0.5f * eps * eps - logsig - BJX_HALF_LOG_2PI) - ce.logp;
+  }
+  const float qp_sum = block_sum(term, red);  // valid in thread 0
+  __syncthreads();
+  // ---- stage 2 (k_lik_coin): per sample, sums over the N tosses -- one warp per sample
+  for (int s = warp; s < S; s += 8) {
+    const float4 a = s_aux[s];
+    float f = 0.0f, g = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      const float kk = y[n];
+      f += (1.0f - kk) * a.y + kk * a.x;
+      g += (1.0f - kk) * a.w + kk * a.z;
+    }
+    f = warp_sum(f);
+    g = warp_sum(g);
+    if (lane == 0) {
+      s_stat[s] = N > 0 ? f : 0.0f;
+      s_G[s] = N > 0 ? g : 0.0f;
+    }
+  }
+  __syncthreads();
+  // ---- stage 3 (k_tail): reparameterisation gradient, one warp per latent coordinate
+  const float invS = 1.0f / (float)S_total;
+  const float cS = ll_scale * invS;
+  for (int d = warp; d < D; d += 8) {
+    float acc_mu = 0.0f, acc_rho = 0.0f;
+    for (int s2 = lane; s2 < S; s2 += 32) {
+      const int i = s2 * D + d;
+      const float dll = d == probs_coord ? s_G[s2] : 0.0f;  // already differentiated with respect to z
+      const float gz = prior_weight * s_gprior[i] * invS - cS * dll;
+      acc_mu += gz;
+      acc_rho = fmaf(gz, s_eps[i], acc_rho);
+    }
+    acc_mu = warp_sum(acc_mu);
+    acc_rho = warp_sum(acc_rho);
+    if (lane == 0) {
+      const ScaleEval sc = eval_scale(raw[d], scale_bij);
+      out[1 + d] = acc_mu;
+      out[1 + D + d] = acc_rho * sc.dsigma - entropy_weight * sc.dlogsigma;
+    }
+  }
+  // ---- stage 4 (k_scalars): loss and (zero) kwarg gradients
+  float ll = 0.0f;
+  for (int s2 = tid; s2 < S; s2 += 256) ll += s_stat[s2];
+  ll = block_sum(ll, red);
+  if (tid == 0) {
+    out[0] = prior_weight * qp_sum * invS - ll_scale * ll * invS;
+    for (int64_t kk = 0; kk < K; ++kk) out[1 + 2 * D + kk] = 0.0f;
+  }
+}
+
 // ---- orchestration ------------------------------------------------------------------------------------------------------
 static int run_prologue(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
   float* eps = (float*)(ws + p.o_eps);
@@ -575,6 +665,15 @@ static int check_ptrs(const BjxElboArgs& a, const Plan& p) {
 
 static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
   char* ws = (char*)a.workspace;
+  if (p.tiny) {  // the whole step in one block (launch latency is all there is at this size)
+    const int probs_coord = a.N > 0 ? (int)a.w_offset : -1;
+    k_tiny_coin_step<<<1, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, (int)a.S, (int)a.D, a.scale_bijector,
+                                        a.threefry_layout, a.y, (int)a.N, probs_coord, a.prior_weight,
+                                        a.S_total ? a.entropy_weight : a.prior_weight, a.ll_scale, a.S_total ? a.s_offset : 0,
+                                        a.S_total ? a.S_total : a.S, a.K, a.eps_out, a.out);
+    BJX_LAUNCH_CHECK("k_tiny_coin_step");
+    return BJX_OK;
+  }
   int rc = run_prologue(a, p, ws, st);
   if (rc) return rc;
 

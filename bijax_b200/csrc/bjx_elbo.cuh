@@ -8,6 +8,9 @@ enum { KERNEL_FP32_TILED = 0, KERNEL_FP32_SMALLD = 1, KERNEL_TC_BF16 = 2, KERNEL
 
 constexpr int SD_CHUNK_ROWS = 256;  // rows staged per shared-memory chunk by the small-D kernel
 
+// limits of the one-block step for tiny problems (k_tiny_coin_step): S * D, S, N
+constexpr int TINY_SD = 1024, TINY_S = 256, TINY_N = 4096;
+
 struct Plan {
   int kernel;        // KERNEL_*
   int n_qp_blocks;   // prologue blocks = partial sums of (q - p~)
@@ -24,6 +27,7 @@ struct Plan {
   int gm_grid1, gm_grid2, gm_splits, gm_cg, gm_nt;  // gm_cg = 2: CTA pairs (cta_group::2); gm_nt = split terms per operand
   int64_t gm_Dp, gm_Sp;  // padded plane pitches (elements)
   int fr_tc;             // full-rank contractions on the tensor cores
+  int tiny;              // the whole step in one block (k_tiny_coin_step)
   // byte offsets into the workspace
   size_t o_eps, o_z, o_theta, o_bprime, o_gprior, o_gz, o_qp, o_aux, o_G, o_stat, o_Gpart, o_statpart, o_gbuf, o_tc_theta, o_gm_x, o_gm_t, o_gm_g, o_fr_tc, o_lr,
       o_stage_key, o_stage_params, o_stage_out, total;

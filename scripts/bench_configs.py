@@ -49,7 +49,7 @@ ref = R.ADVIRef({"p": R.Beta(0.5, 0.5)}, {"p": R.Sigmoid()}, R.bernoulli_probs_l
 yc = y.cpu(); epsc = torch.tensor(tf.normal(tf.prng_key(1), (16, 1), 0))
 cpu = time_cpu(lambda: ref.value_and_grad(torch.zeros(1), torch.zeros(1), {}, yc, None, 100, epsc), 2.0)
 out.append({"config": "c1 coin toss D=1 N=100 S=16", "kernel": eng.kernel_choice(16, 100), "gpu_us_per_step": us, "gpu_us_per_step_cuda_graph": us_graph,
-            "cpu_us_per_step": cpu, "bound": "launch latency (4 launches)"})
+            "cpu_us_per_step": cpu, "bound": "launch latency (1 launch: k_tiny_coin_step)"})
 
 # ---- c2: linear regression D=5 + learnable log_noise_scale, N=1M, S=64
 N, D, S = 1_000_000, 5, 64
