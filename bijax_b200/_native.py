@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = (
     "bjx_elbo_step_host",
     "bjx_elbo_kernel_choice",
     "bjx_train_steps",
+    "bjx_minibatch_gather",
+    "bjx_train_steps_minibatch",
     "bjx_p2p_buffer_bytes",
     "bjx_p2p_alloc",
     "bjx_p2p_open",
@@ -107,6 +109,16 @@ class BjxElboArgs(C.Structure):
     ]
 
 
+class BjxMinibatch(C.Structure):
+    """include/bjx.h BjxMinibatch (the on-device minibatch sampler)."""
+
+    _fields_ = [
+        ("N_full", C.c_int64), ("B", C.c_int64), ("Dw", C.c_int64), ("ldx_full", C.c_int64),
+        ("X_full", C.c_void_p), ("y_full", C.c_void_p), ("x_planes_full", C.c_void_p),
+        ("Xb", C.c_void_p), ("yb", C.c_void_p), ("planes_b", C.c_void_p), ("idx_out", C.c_void_p), ("elbo_key", C.c_void_p),
+    ]
+
+
 class BjxError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libbjx error {code}: {message}")
@@ -146,6 +158,8 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
     lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
+    lib.bjx_minibatch_gather.argtypes = [C.POINTER(BjxMinibatch), vp, vp, i32, vp]
+    lib.bjx_train_steps_minibatch.argtypes = [C.POINTER(BjxElboArgs), C.POINTER(BjxMinibatch), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
     lib.bjx_p2p_buffer_bytes.argtypes = [i64, i32]
     lib.bjx_p2p_buffer_bytes.restype = C.c_size_t
     lib.bjx_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]

@@ -18,7 +18,7 @@ CSRC = ROOT / "csrc"
 INCLUDE = ROOT.parent / "include"
 OUT_DIR = ROOT / "_lib"
 LIB = OUT_DIR / "libbjx.so"
-SOURCES = ["bjx_random.cu", "bjx_elbo.cu", "bjx_lik_simt.cu", "bjx_lik_tc.cu", "bjx_gemm_tc.cu", "bjx_posterior.cu", "bjx_lowrank.cu", "bjx_p2p.cu"]
+SOURCES = ["bjx_random.cu", "bjx_elbo.cu", "bjx_lik_simt.cu", "bjx_lik_tc.cu", "bjx_gemm_tc.cu", "bjx_posterior.cu", "bjx_lowrank.cu", "bjx_p2p.cu", "bjx_minibatch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

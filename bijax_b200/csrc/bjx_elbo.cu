@@ -880,8 +880,9 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
   return BJX_OK;
 }
 
-int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
-                    float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream) {
+static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,
+                            float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses,
+                            void* stream) {
   using namespace bjx;
   BJX_REQUIRE(args != nullptr && params_flat && adam_m && adam_v && steps_done, "null pointer");
   BJX_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
@@ -893,11 +894,21 @@ int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat
   a.raw_scale = params_flat + a.D;
   a.kwargs = a.K ? params_flat + a.D + p.Pn : nullptr;
   a.key_index = steps_done;
+  if (mb) {  // the step's seed is the half of split(key[*steps_done]) that the gather kernel leaves in mb->elbo_key
+    BJX_REQUIRE(mb->elbo_key != nullptr, "minibatch training needs mb->elbo_key");
+    BJX_REQUIRE(mb->B == a.N, "minibatch: args->N (%lld) must equal the batch size (%lld)", (long long)a.N, (long long)mb->B);
+    a.key = mb->elbo_key;
+    a.key_index = nullptr;
+  }
   rc = check_ptrs(a, p);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = a.D + p.Pn + a.K;
   for (int64_t i = 0; i < n_steps; ++i) {
+    if (mb) {
+      rc = launch_minibatch_gather(*mb, args->key, steps_done, a.threefry_layout, st);
+      if (rc) return rc;
+    }
     rc = run_step(a, p, st);
     if (rc) return rc;
     k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params_flat, adam_m, adam_v, a.out + 1, n, lr, b1, b2, eps, steps_done);
@@ -906,6 +917,19 @@ int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat
     BJX_LAUNCH_CHECK("k_train_bump");
   }
   return BJX_OK;
+}
+
+int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
+                    float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream) {
+  return train_steps_impl(args, nullptr, n_steps, params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, stream);
+}
+
+int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,
+                              float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses,
+                              void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(mb != nullptr, "mb is null");
+  return train_steps_impl(args, mb, n_steps, params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, stream);
 }
 
 size_t bjx_x_planes_bytes(int64_t N, int64_t Dw) {

@@ -78,4 +78,7 @@ __device__ __forceinline__ void link_eval(int family, float y, float eta, float&
   }
 }
 
+// bjx_minibatch.cu
+int launch_minibatch_gather(const BjxMinibatch& mb, const uint32_t* key, const int64_t* key_index, int layout, cudaStream_t st);
+
 }  // namespace bjx

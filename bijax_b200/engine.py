@@ -148,12 +148,27 @@ class ElboEngine:
             raise ValueError(f"X must be [N={N}, D={self.Dw}] (rows = data, row-major); got {tuple(X.shape)}")
         return X, y, N, X.stride(0)
 
+    def wants_planes(self, S, N) -> bool:
+        """True if a step of this shape reads the dataset as prepared split-bf16 planes (TMA-fed tcgen05 kernels)."""
+        if not self.prepare_dataset or self.Dw < 1 or self.precision == nv.PREC_BF16X3:
+            return False
+        a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        return self.lib.bjx_elbo_kernel_choice(C.byref(a)) in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"])
+
+    def bind_planes(self, X: Optional[torch.Tensor], planes: Optional[torch.Tensor]) -> None:
+        """The caller maintains the operand planes of the tensor ``X`` itself (the minibatch sampler gathers plane rows
+        straight into ``planes``); (None, None) removes the binding."""
+        self._bound_planes = None if X is None or planes is None else (X.data_ptr(), planes)
+
     def _x_planes(self, a: nv.BjxElboArgs, X: torch.Tensor) -> Optional[int]:
         """Device pointer of the prepared operand planes of X if this step takes the GEMM path, else None."""
         if not self.prepare_dataset or X is None:
             return None
         if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
             return None
+        bound = getattr(self, "_bound_planes", None)
+        if bound is not None and bound[0] == X.data_ptr():
+            return bound[1].data_ptr()
         key = (X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()))
         if self._planes_misses > 2 and key == self._last_raw_key:
             self._planes_misses = 0  # the same tensor came back: it is a dataset after all
@@ -304,7 +319,7 @@ class ElboEngine:
         return out
 
     def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
-                    n_samples, partitionable=None):
+                    n_samples, partitionable=None, minibatch=None):
         """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip
         (bjx_train_steps; train_fn's scan body, utils.py:22-28).  ``keys`` is the [n, 2] uint32 array of per-step keys,
         ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place."""
@@ -317,10 +332,19 @@ class ElboEngine:
         a.y = y.data_ptr()
         a.out = out.data_ptr()
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
-        a.x_planes = self._x_planes(a, X)
+        if minibatch is not None:  # X / y are the sampler's batch buffers; it fills the planes itself (bjx_minibatch_gather)
+            a.x_planes = minibatch["planes_b"].data_ptr() if minibatch["planes_b"] is not None else None
+        else:
+            a.x_planes = self._x_planes(a, X)
         ws = self._workspace(a)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         lr, b1, b2, eps = hyper
+        if minibatch is not None:
+            with torch.cuda.device(self.device):
+                nv.check(self.lib.bjx_train_steps_minibatch(C.byref(a), C.byref(minibatch["mb"]), int(n_steps), params_flat.data_ptr(),
+                                                            adam_m.data_ptr(), adam_v.data_ptr(), lr, b1, b2, eps, steps_done.data_ptr(),
+                                                            losses.data_ptr() if losses is not None else None, nv.current_stream_ptr()))
+            return
         with torch.cuda.device(self.device):
             nv.check(self.lib.bjx_train_steps(C.byref(a), int(n_steps), params_flat.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),
                                               lr, b1, b2, eps, steps_done.data_ptr(), losses.data_ptr() if losses is not None else None,

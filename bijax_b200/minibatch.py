@@ -1,0 +1,103 @@
+"""On-device minibatch sampler for the ELBO step.
+
+The reference's only concession to large N is the ``ll / len(outputs) * full_data_size`` scaling of ``loss_fn``
+(bijax/advi.py:92); which rows make up ``outputs`` / ``inputs`` is left to the caller.  What a JAX user writes around it,
+
+    def loss(params, seed):
+        k_batch, k_elbo = jax.random.split(seed)
+        idx = jax.random.choice(k_batch, N, (B,))
+        return model.loss_fn(params, y[idx], {"X": X[idx]}, full_data_size=N, seed=k_elbo, n_samples=S)
+
+is ``MinibatchLoss(model, y, {"X": X}, batch_size=B, n_samples=S)`` here: one gather kernel (csrc/bjx_minibatch.cu) draws
+the indices from the key and copies those rows -- of the prepared split-bf16 planes when the step's kernel is TMA-fed,
+of raw fp32 X otherwise -- into batch buffers the step then reads.  ``train_fn(loss, params, optim.adam(...), n, seed)``
+recognises the object and keeps the whole loop on the device (bjx_train_steps_minibatch in replayed CUDA graphs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _native as nv
+from . import random as brandom
+
+
+class MinibatchLoss:
+    def __init__(self, model, outputs, inputs, batch_size: int, n_samples: int = 1, full_data_size: Optional[int] = None):
+        nv.require_cuda()
+        self.model = model
+        self.B = int(batch_size)
+        self.S = int(n_samples)
+        self.outputs = outputs
+        self.inputs = inputs
+        self.N = len(outputs)
+        if self.B < 1 or self.N < 1:
+            raise ValueError("need batch_size >= 1 and a non-empty dataset")
+        self.full_data_size = float(self.N if full_data_size is None else full_data_size)
+        self._state = None  # (engine, buffers) built on first use: the engine depends on the params' trainable kwargs
+
+    # ---- buffers ----------------------------------------------------------------------------------------------------
+    def _setup(self, engine):
+        if self._state is not None and self._state["engine"] is engine:
+            return self._state
+        dev = engine.device
+        X = None
+        if engine.lik_id != nv.LIK_BERNOULLI_PROBS:
+            X = self.inputs[engine.x_name] if isinstance(self.inputs, dict) else self.inputs
+        X, y, N, ldx = engine._data(X, self.outputs)
+        st = {"engine": engine, "X": X, "y": y, "ldx": ldx}
+        st["yb"] = torch.empty(self.B, dtype=torch.float32, device=dev)
+        st["idx"] = torch.empty(self.B, dtype=torch.int32, device=dev)
+        st["elbo_key"] = torch.zeros(2, dtype=torch.uint32, device=dev)
+        st["Xb"] = torch.zeros((self.B, engine.Dw), dtype=torch.float32, device=dev) if X is not None else None
+        st["planes_full"] = st["planes_b"] = None
+        if X is not None and engine.wants_planes(self.S, self.B):
+            # the batch step is TMA-fed: keep the FULL dataset as planes (made once) and gather plane rows
+            lib = engine.lib
+            full = torch.empty(int(lib.bjx_x_planes_bytes(N, engine.Dw)), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                nv.check(lib.bjx_prepare_x_planes(X.data_ptr(), N, engine.Dw, ldx, full.data_ptr(), nv.current_stream_ptr()))
+            st["planes_full"] = full
+            st["planes_b"] = torch.empty(int(lib.bjx_x_planes_bytes(self.B, engine.Dw)), dtype=torch.uint8, device=dev)
+        mb = nv.BjxMinibatch()
+        mb.N_full, mb.B, mb.Dw, mb.ldx_full = N, self.B, max(engine.Dw, 1), ldx if ldx else max(engine.Dw, 1)
+        mb.y_full, mb.yb = y.data_ptr(), st["yb"].data_ptr()
+        mb.idx_out, mb.elbo_key = st["idx"].data_ptr(), st["elbo_key"].data_ptr()
+        if st["planes_b"] is not None:
+            mb.x_planes_full, mb.planes_b = st["planes_full"].data_ptr(), st["planes_b"].data_ptr()
+        elif X is not None:
+            mb.X_full, mb.Xb = X.data_ptr(), st["Xb"].data_ptr()
+        st["mb"] = mb
+        self._state = st
+        return st
+
+    def _engine(self, params):
+        _, _, kwargs = self.model._split_params(params)
+        engine, _ = self.model._engine_for(kwargs)
+        return engine
+
+    # ---- one draw ---------------------------------------------------------------------------------------------------
+    def sample(self, params, seed):
+        """Draw the batch of ``seed``: returns (idx int32[B], y[idx], X[idx] or None, k_elbo).  The returned tensors are
+        the sampler's own buffers (overwritten by the next draw); X[idx] is None when the step reads gathered planes."""
+        st = self._setup(self._engine(params))
+        seed = brandom._check_key(seed)
+        with torch.cuda.device(st["engine"].device):
+            nv.check(st["engine"].lib.bjx_minibatch_gather(C.byref(st["mb"]), seed.data_ptr(), None, brandom._layout(None), nv.current_stream_ptr()))
+        return st["idx"], st["yb"], (st["Xb"] if st["planes_b"] is None else None), st["elbo_key"]
+
+    def __call__(self, params, seed):
+        """The loss of the docstring's ``loss(params, seed)``; differentiable like ``model.loss_fn``."""
+        st = self._setup(self._engine(params))
+        self.sample(params, seed)
+        engine = st["engine"]
+        inputs = None
+        if st["Xb"] is not None:
+            inputs = {engine.x_name: st["Xb"]} if isinstance(self.inputs, dict) else st["Xb"]
+        engine.bind_planes(st["Xb"], st["planes_b"])
+        try:
+            return self.model.loss_fn(params, st["yb"], inputs, self.full_data_size, st["elbo_key"], self.S)
+        finally:
+            engine.bind_planes(None, None)

@@ -100,3 +100,30 @@ def normal(key, shape=(), partitionable=None, offset: int = 0, total=None, out=N
     with torch.cuda.device(key.device):
         nv.check(nv.load().bjx_random_normal(key.data_ptr(), total, int(offset), n, _layout(partitionable), out.data_ptr(), nv.current_stream_ptr()))
     return out
+
+
+def randint(key, shape, minval: int, maxval: int, partitionable=None) -> torch.Tensor:
+    """jax.random.randint(key, shape, minval, maxval) for the default int32 dtype (the index draw of the on-device
+    minibatch sampler, csrc/bjx_minibatch.cu; restated in oracle/threefry.py::randint)."""
+    key = _check_key(key)
+    shape = _shape(shape)
+    n = math.prod(shape) if shape else 1
+    span = int(maxval) - int(minval)
+    if span < 1:
+        span = 1  # jax returns minval everywhere
+    if span >= 2**31 or not (-(2**31) <= int(minval) < 2**31):
+        raise ValueError("randint: int32 range only")
+    out = torch.empty(n, dtype=torch.int32, device=key.device)
+    if n:
+        mb = nv.BjxMinibatch()
+        mb.N_full, mb.B, mb.idx_out = span, n, out.data_ptr()
+        with torch.cuda.device(key.device):
+            nv.check(nv.load().bjx_minibatch_gather(mb, key.data_ptr(), None, _layout(partitionable), nv.current_stream_ptr()))
+    if minval:
+        out += int(minval)
+    return out.reshape(shape)
+
+
+def choice(key, a: int, shape=(), partitionable=None) -> torch.Tensor:
+    """jax.random.choice(key, a, shape) for an integer ``a`` with the defaults replace=True, p=None: randint(key, shape, 0, a)."""
+    return randint(key, shape, 0, int(a), partitionable)

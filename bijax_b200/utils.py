@@ -37,6 +37,13 @@ def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
 
     if seed is None or return_args or getattr(optimizer, "hyper", None) is None:
         return None
+    from .minibatch import MinibatchLoss
+
+    if isinstance(loss_fn, MinibatchLoss):  # loss(params, seed) with the batch drawn on the device from the seed
+        model = loss_fn.model
+        if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False):
+            return None
+        return model, {"minibatch": loss_fn, "full_data_size": loss_fn.full_data_size, "n_samples": loss_fn.S}
     if not isinstance(loss_fn, functools.partial) or loss_fn.args:
         return None
     model = getattr(loss_fn.func, "__self__", None)
@@ -60,10 +67,15 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
     flat = torch.cat([f32(loc), f32(raw)] + [f32(l) for l in kw_leaves]).contiguous()
     n_epochs = int(n_epochs)
     keys = brandom.split(seed, max(n_epochs, 1)).contiguous()
-    outputs, inputs = kw["outputs"], kw["inputs"]
-    X = None
-    if engine.x_name is not None and inputs is not None:
-        X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
+    mb_state = None
+    if "minibatch" in kw:  # batch buffers of the on-device sampler; every step gathers a fresh batch into them
+        mb_state = kw["minibatch"]._setup(engine)
+        outputs, X = mb_state["yb"], mb_state["Xb"]
+    else:
+        outputs, inputs = kw["outputs"], kw["inputs"]
+        X = None
+        if engine.x_name is not None and inputs is not None:
+            X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
     ll_scale = float(kw["full_data_size"]) / float(len(outputs))  # advi.py:92
     S = int(kw.get("n_samples", 1))
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
@@ -72,7 +84,7 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
     out = torch.empty(1 + flat.numel(), dtype=torch.float32, device=dev)
 
     def enqueue(n, flat_, m_, v_, done_, losses_):
-        engine.train_steps(keys, n, flat_, m_, v_, optimizer.hyper, done_, losses_, out, X, outputs, ll_scale, S)
+        engine.train_steps(keys, n, flat_, m_, v_, optimizer.hyper, done_, losses_, out, X, outputs, ll_scale, S, minibatch=mb_state)
 
     n_graphs, rest = divmod(n_epochs, GRAPH_STEPS)
     if n_graphs >= 2:

@@ -249,6 +249,40 @@ BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grad
 BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, float lr,
                     float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream);
 
+/* ---- on-device minibatch sampler (the scaling it feeds is advi.py:92) ----------------------
+ * What a JAX user writes around loss_fn,
+ *     k_batch, k_elbo = jax.random.split(key)
+ *     idx = jax.random.choice(k_batch, N_full, (B,))     (replace=True: == jax.random.randint(k_batch, (B,), 0, N_full))
+ *     loss_fn(params, y[idx], {"X": X[idx]}, full_data_size, seed=k_elbo, n_samples)
+ * as one gather kernel: idx[b] from the key (threefry; uint32 arithmetic of jax's _randint), then row idx[b] of X (raw
+ * fp32 and / or the prepared split-bf16 planes) and of y copied into contiguous batch buffers that bjx_elbo_step reads with
+ * N = B and ll_scale = full_data_size / B.  Every destination is optional (NULL = skip).  elbo_key != NULL: `key` is first
+ * split in two, the indices come from the first half and the second half is written to elbo_key[2]; elbo_key == NULL: the
+ * indices come from `key` itself.  key_index (optional) selects key[2 * *key_index] on the device, as in BjxElboArgs. */
+typedef struct BjxMinibatch {
+  int64_t N_full;            /* rows of the full dataset (< 2^31) */
+  int64_t B;                 /* rows per batch */
+  int64_t Dw;                /* columns of X (ignored when only y is gathered) */
+  int64_t ldx_full;          /* row pitch of X_full in floats */
+  const float* X_full;       /* [N_full, ldx_full] or NULL */
+  const float* y_full;       /* [N_full] or NULL */
+  const void* x_planes_full; /* bjx_prepare_x_planes(X_full, N_full, Dw) or NULL */
+  float* Xb;                 /* out [B, Dw] dense, or NULL */
+  float* yb;                 /* out [B], or NULL */
+  void* planes_b;            /* out bjx_x_planes_bytes(B, Dw) bytes in the layout bjx_prepare_x_planes(Xb, B, Dw) would give, or NULL */
+  int32_t* idx_out;          /* out [B] row indices, or NULL */
+  uint32_t* elbo_key;        /* out [2] second half of split(key), or NULL (see above) */
+} BjxMinibatch;
+BJX_API int bjx_minibatch_gather(const BjxMinibatch* mb, const uint32_t* key, const int64_t* key_index, int32_t layout, void* stream);
+
+/* bjx_train_steps on minibatches: per step { bjx_minibatch_gather at key[*steps_done] -> ELBO + gradients on the batch with
+ * seed mb->elbo_key -> Adam -> losses[*steps_done], ++*steps_done }.  `args` describes the BATCH problem (N = mb->B, X =
+ * mb->Xb, y = mb->yb, x_planes = mb->planes_b or NULL, ll_scale = full_data_size / B); args->key is the [n, 2] array of
+ * per-step keys; mb->elbo_key must be set.  Graph-capturable like bjx_train_steps. */
+BJX_API int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat,
+                                      float* adam_m, float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done,
+                                      float* losses, void* stream);
+
 /* ---- the exchange step over NVLink peer memory (one kernel instead of an NCCL call) ---------------------------------
  * One-shot all-reduce (sum, in place) of the packed [loss | grads] buffer across the <= 8 GPUs of a box: every rank
  * stores its vector into a slot of every peer's buffer over NVLink, raises a flag, waits for the peers' flags and sums

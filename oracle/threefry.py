@@ -181,3 +181,28 @@ def uniform(key, shape, layout: int = LAYOUT_LEGACY, minval=0.0, maxval=1.0, off
     shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
     n = int(np.prod(shape)) if shape else 1
     return uniform_from_bits(random_bits(key, n, layout, offset), minval, maxval).reshape(shape)
+
+
+def randint(key, n: int, minval: int, maxval: int, layout: int = LAYOUT_LEGACY) -> np.ndarray:
+    """``jax.random.randint(key, (n,), minval, maxval)`` for the default int32 dtype -> int32[n]; also what
+    ``jax.random.choice(key, N, (n,))`` (replace=True, p=None) returns for ``minval, maxval = 0, N``.
+
+    Restates ``jax._src.random._randint``: ``k1, k2 = split(key)``, 32 "higher" bits from k1 and 32 "lower" bits from
+    k2, ``multiplier = (2**16 % span)**2 % span`` and ``offset = ((higher % span) * multiplier + lower % span) % span``,
+    every operation in uint32 and wrapping exactly as XLA's integer ops do (for span > 2**16 the squared multiplier wraps
+    to 0 and the offset reduces to ``lower % span``).  Used by the on-device minibatch sampler (SURVEY.md section 8(f)
+    row 3); the reference itself never draws indices.
+
+    PARITY STATUS of this function: UNPINNED against JAX -- no JAX here and no published known-answer vector; it pins
+    the CUDA sampler (bijax_b200/csrc/bjx_minibatch.cu) against an independent NumPy restatement of the same published
+    algorithm, on top of the pinned threefry / split."""
+    k1, k2 = split(key, 2, layout)
+    hi = random_bits(k1, n, layout).astype(U32)
+    lo = random_bits(k2, n, layout).astype(U32)
+    span = np.array([maxval - minval if maxval > minval else 1], dtype=np.uint64).astype(U32)
+    with np.errstate(over="ignore"):
+        mult = np.array([1 << 16], dtype=U32) % span
+        mult = (mult * mult) % span
+        off = ((hi % span) * mult + lo % span) % span
+    return (np.int64(minval) + off.astype(np.int64)).astype(np.int32)
+

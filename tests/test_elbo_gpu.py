@@ -63,6 +63,27 @@ def test_c1_coin_toss(layout):
         assert abs(loss.item() - 200.757306865) < 200.76 * 1e-5
 
 
+@pytest.mark.parametrize("N,S", [(100, 256), (100, 257), (4096, 16), (4097, 16), (100_000, 33)])
+def test_coin_toss_on_either_side_of_the_one_block_limits(N, S):
+    """The one-block step (k_tiny_coin_step: S <= 256, N <= 4096) and the four-launch path give the oracle's numbers."""
+    model, ref = C.build_pair({"p_of_heads": tfd.Beta(2.0, 3.0)}, {"p_of_heads": tfb.Sigmoid()}, lk.BernoulliProbs("p_of_heads"))
+    init = tf.normal(tf.prng_key(5), (2,), 0)
+    y = np.array([1.0 if (n * 7) % 10 < 4 else 0.0 for n in range(N)], dtype=np.float32)
+    _run_case(model, ref, init[:1], 0.3 * init[1:] - 1.0, {}, y, None, max(N, 1), 11, S, 0, expect_kernel="coin")
+
+
+@pytest.mark.parametrize("S", [9, 300])
+def test_coin_toss_with_other_latents_beside_the_probability(S):
+    """D = 4: the toss probability is coordinate 3 of the flattened latent; the other coordinates only see their priors."""
+    prior = {"a_scale": tfd.Gamma(2.0, 1.5), "b_vec": tfd.MultivariateNormalDiag(loc=np.zeros(2, np.float32), scale_diag=np.full(2, 0.7, np.float32)),
+             "p_of_heads": tfd.Beta(1.5, 0.8)}
+    model, ref = C.build_pair(prior, {"a_scale": tfb.Softplus(), "p_of_heads": tfb.Sigmoid()}, lk.BernoulliProbs("p_of_heads"),
+                              scale_bijector=tfb.Softplus())
+    init = tf.normal(tf.prng_key(6), (8,), 0)
+    y = np.array([1.0 if n % 3 == 0 else 0.0 for n in range(250)], dtype=np.float32)
+    _run_case(model, ref, 0.5 * init[:4], 0.3 * init[4:], {}, y, None, 500, 12, S, 0, expect_kernel="coin")
+
+
 @pytest.mark.parametrize("N,S", [(4096, 64), (1000, 7), (1, 3), (300, 300)])
 def test_c2_linear_regression_learnable_noise_small_d(N, S):
     """config c2 shape family: D=5, Gaussian likelihood with trainable log_noise_scale (README.md:99-106)."""

@@ -43,6 +43,15 @@ def test_struct_layouts_match_the_header(tmp_path):
             nv.BjxElboArgs.ll_scale.offset, nv.BjxElboArgs.kernel_override.offset, nv.BjxElboArgs.x_planes.offset,
             nv.BjxElboArgs.key_index.offset, nv.BjxElboArgs.S_total.offset, nv.BjxElboArgs.point_mode.offset, nv.BjxElboArgs.rank.offset]
     assert got == want
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "bjx.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(BjxMinibatch), offsetof(BjxMinibatch, ldx_full), offsetof(BjxMinibatch, x_planes_full),'
+        " offsetof(BjxMinibatch, planes_b), offsetof(BjxMinibatch, elbo_key));return 0;}\n"
+    )
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    M = nv.BjxMinibatch
+    assert got == [C.sizeof(M), M.ldx_full.offset, M.x_planes_full.offset, M.planes_b.offset, M.elbo_key.offset]
 
 
 def test_header_is_plain_c():
@@ -59,3 +68,8 @@ def test_argument_validation_happens_before_any_cuda_work():
     assert lib.bjx_elbo_step(None, None) == nv.ERR_INVALID_ARGUMENT
     with pytest.raises(nv.BjxError):
         nv.check(lib.bjx_random_normal(None, 4, 0, 4, 0, None, None))
+    assert lib.bjx_minibatch_gather(None, None, None, 0, None) == nv.ERR_INVALID_ARGUMENT
+    mb = nv.BjxMinibatch()
+    mb.N_full, mb.B = 10, 4
+    assert lib.bjx_minibatch_gather(C.byref(mb), None, None, 0, None) == nv.ERR_INVALID_ARGUMENT  # no key
+    assert lib.bjx_train_steps_minibatch(None, None, 1, None, None, None, 0.1, 0.9, 0.999, 1e-8, None, None, None) == nv.ERR_INVALID_ARGUMENT

@@ -229,3 +229,28 @@ def test_oracle_distribution_and_bijector_formulas_against_scipy():
     want = np.sqrt(2.0) * sp.erfinv(u.astype(np.float64))
     rel = np.abs(nrm - want) / np.maximum(np.abs(want), 1e-3)
     assert rel.max() < 1e-5 and np.median(rel) < 2e-7
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_randint_restatement_properties(layout):
+    """oracle/threefry.py::randint (the index draw of the minibatch sampler): for span <= 2**16 the uint32 recipe equals
+    the exact (higher * 2**32 + lower) mod span; above that the wrapped multiplier is 0 and it reduces to lower mod span;
+    a degenerate range returns minval; draws are in range and reproducible."""
+    key = tf.prng_key(123)
+    k1, k2 = tf.split(key, 2, layout)
+    n = 500
+    hi = [int(v) for v in tf.random_bits(k1, n, layout)]
+    lo = [int(v) for v in tf.random_bits(k2, n, layout)]
+    for span in (1, 2, 10, 100, 4096, 65535, 65536):
+        got = tf.randint(key, n, 0, span, layout)
+        m = (65536 % span) ** 2 % span
+        assert [int(g) for g in got] == [(((h % span) * m) % 2**32 + l % span) % 2**32 % span for h, l in zip(hi, lo)]
+        if span <= 256:  # no intermediate overflow: the recipe is the exact double-width remainder
+            assert [int(g) for g in got] == [((h << 32) + l) % span for h, l in zip(hi, lo)]
+    for span in (65537, 10_000_000, 2**31 - 1):
+        assert [int(g) for g in tf.randint(key, n, 0, span, layout)] == [l % span for l in lo]
+    assert np.array_equal(tf.randint(key, 7, 5, 5, layout), np.full(7, 5, np.int32))
+    got = tf.randint(key, n, -3, 4, layout)
+    assert got.dtype == np.int32 and got.min() >= -3 and got.max() <= 3 and len(set(got.tolist())) == 7
+    assert np.array_equal(got, tf.randint(key, n, -3, 4, layout))
+
