@@ -523,6 +523,26 @@ __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t 
   }
 }
 
+// ---- optax.adam on one element (eps outside the square root, bias-corrected); t = 1-based step number ------------------------
+__device__ __forceinline__ void adam_one(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float gi, int64_t i,
+                                         float lr, float b1, float b2, float eps, float t) {
+  const float c1 = 1.0f - powf(b1, t), c2 = 1.0f - powf(b2, t);
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+// the rest of a training step (Adam, loss record, step counter) for kernels that can finish it themselves
+struct TrainTail {
+  float *params, *m, *v;  // params == nullptr: not a training step
+  float lr, b1, b2, eps;
+  int64_t* steps_done;
+  float* losses;
+  int64_t n;
+};
+
 // ---- tiny problems: the whole step in ONE block ---------------------------------------------------------------------------
 // Config c1 (coin toss: D = 1, S = 16, N = 100) is pure launch latency -- four launches of a few hundred threads.  This
 // kernel runs the same four stages (k_prologue -> k_lik_coin -> k_tail -> k_scalars, same formulas) back to back in one
@@ -535,7 +555,7 @@ __global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restri
                                                         int layout, const float* __restrict__ y, int N, int probs_coord,
                                                         float prior_weight, float entropy_weight, float ll_scale,
                                                         int64_t s_offset, int64_t S_total, int64_t K,
-                                                        float* __restrict__ eps_out, float* __restrict__ out) {
+                                                        float* __restrict__ eps_out, float* __restrict__ out, TrainTail tt) {
   __shared__ float s_eps[TINY_SD], s_gprior[TINY_SD];
   __shared__ float4 s_aux[TINY_S];
   __shared__ float s_G[TINY_S], s_stat[TINY_S];
@@ -607,6 +627,17 @@ __global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restri
     out[0] = prior_weight * qp_sum * invS - ll_scale * ll * invS;
     for (int64_t kk = 0; kk < K; ++kk) out[1 + 2 * D + kk] = 0.0f;
   }
+  // ---- training loop: Adam on [loc | raw | kwargs], loss record, ++step -- the whole epoch is this one launch
+  if (tt.params != nullptr) {
+    __syncthreads();  // out[] written above by this block
+    const int64_t t0 = *tt.steps_done;
+    for (int64_t i = tid; i < tt.n; i += 256) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.lr, tt.b1, tt.b2, tt.eps, (float)(t0 + 1));
+    __syncthreads();  // everybody has read the step number (and the key it selects)
+    if (tid == 0) {
+      if (tt.losses) tt.losses[t0] = out[0];
+      *tt.steps_done = t0 + 1;
+    }
+  }
 }
 
 // ---- orchestration ------------------------------------------------------------------------------------------------------
@@ -663,15 +694,17 @@ static int check_ptrs(const BjxElboArgs& a, const Plan& p) {
   return BJX_OK;
 }
 
-static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st) {
+// tt (training loops only): kernels that can finish the epoch themselves do so and set *tt_done
+static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const TrainTail* tt = nullptr, bool* tt_done = nullptr) {
   char* ws = (char*)a.workspace;
   if (p.tiny) {  // the whole step in one block (launch latency is all there is at this size)
     const int probs_coord = a.N > 0 ? (int)a.w_offset : -1;
     k_tiny_coin_step<<<1, 256, 0, st>>>(a.key, a.key_index, a.loc, a.raw_scale, a.coords, (int)a.S, (int)a.D, a.scale_bijector,
                                         a.threefry_layout, a.y, (int)a.N, probs_coord, a.prior_weight,
                                         a.S_total ? a.entropy_weight : a.prior_weight, a.ll_scale, a.S_total ? a.s_offset : 0,
-                                        a.S_total ? a.S_total : a.S, a.K, a.eps_out, a.out);
+                                        a.S_total ? a.S_total : a.S, a.K, a.eps_out, a.out, tt ? *tt : TrainTail{});
     BJX_LAUNCH_CHECK("k_tiny_coin_step");
+    if (tt && tt_done) *tt_done = true;
     return BJX_OK;
   }
   int rc = run_prologue(a, p, ws, st);
@@ -764,14 +797,19 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, float* 
                                                   float eps, const int64_t* __restrict__ steps_done) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  const float t = (float)(*steps_done + 1);
-  const float c1 = 1.0f - powf(b1, t), c2 = 1.0f - powf(b2, t);
-  const float gi = g[i];
-  const float mi = b1 * m[i] + (1.0f - b1) * gi;
-  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  adam_one(p, m, v, g[i], i, lr, b1, b2, eps, (float)(*steps_done + 1));
+}
+
+// few parameters (n <= 1024): Adam and the bookkeeping of k_train_bump in one block, one launch
+__global__ void __launch_bounds__(1024) k_adam_bump_small(TrainTail tt, const float* __restrict__ out) {
+  const int64_t t0 = *tt.steps_done;
+  const int64_t i = threadIdx.x;
+  if (i < tt.n) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.lr, tt.b1, tt.b2, tt.eps, (float)(t0 + 1));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (tt.losses) tt.losses[t0] = out[0];
+    *tt.steps_done = t0 + 1;
+  }
 }
 
 __global__ void k_train_bump(int64_t* __restrict__ steps_done, const float* __restrict__ out, float* __restrict__ losses) {
@@ -904,13 +942,21 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = a.D + p.Pn + a.K;
+  const TrainTail tt{params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, n};
   for (int64_t i = 0; i < n_steps; ++i) {
     if (mb) {
       rc = launch_minibatch_gather(*mb, args->key, steps_done, a.threefry_layout, st);
       if (rc) return rc;
     }
-    rc = run_step(a, p, st);
+    bool finished = false;
+    rc = run_step(a, p, st, &tt, &finished);
     if (rc) return rc;
+    if (finished) continue;  // the step kernel did Adam and the bookkeeping itself
+    if (n <= 1024) {
+      k_adam_bump_small<<<1, 1024, 0, st>>>(tt, a.out);
+      BJX_LAUNCH_CHECK("k_adam_bump_small");
+      continue;
+    }
     k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params_flat, adam_m, adam_v, a.out + 1, n, lr, b1, b2, eps, steps_done);
     BJX_LAUNCH_CHECK("k_adam_dev");
     k_train_bump<<<1, 1, 0, st>>>(steps_done, a.out, losses);
