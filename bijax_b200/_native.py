@@ -13,7 +13,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_lib" / "libbjx.so"
 
 # ---- constants mirrored from include/bjx.h ----------------------------------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 LAYOUT_LEGACY, LAYOUT_PARTITIONABLE = 0, 1
 VI_MEAN_FIELD, VI_FULL_RANK, VI_LOW_RANK = 0, 1, 2
@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "bjx_elbo_step",
     "bjx_elbo_step_host",
     "bjx_elbo_kernel_choice",
+    "bjx_elbo_supports_row_index",
     "bjx_train_steps",
     "bjx_minibatch_gather",
     "bjx_train_steps_minibatch",
@@ -106,6 +107,7 @@ class BjxElboArgs(C.Structure):
         ("point_mode", C.c_int32),
         ("reserved3", C.c_int32),
         ("rank", C.c_int64),
+        ("row_index", C.c_void_p),
     ]
 
 
@@ -157,6 +159,7 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step.argtypes = [C.POINTER(BjxElboArgs), vp]
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
+    lib.bjx_elbo_supports_row_index.argtypes = [C.POINTER(BjxElboArgs)]
     lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
     lib.bjx_minibatch_gather.argtypes = [C.POINTER(BjxMinibatch), vp, vp, i32, vp]
     lib.bjx_train_steps_minibatch.argtypes = [C.POINTER(BjxElboArgs), C.POINTER(BjxMinibatch), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]

@@ -282,12 +282,12 @@ class ADVI:
         run = self._run(engine, seed, outputs, inputs, full_data_size, n_samples)
         return _ElboFunction.apply(loc, raw, kw, run)
 
-    def minibatch_loss_fn(self, outputs, inputs, batch_size, n_samples=1, full_data_size=None):
+    def minibatch_loss_fn(self, outputs, inputs, batch_size, n_samples=1, full_data_size=None, copy_free=None):
         """``loss(params, seed)`` on a minibatch of ``batch_size`` rows drawn on the device from ``seed``
         (jax.random.choice semantics) with the full-data scaling of advi.py:92; see minibatch.MinibatchLoss."""
         from .minibatch import MinibatchLoss
 
-        return MinibatchLoss(self, outputs, inputs, batch_size, n_samples, full_data_size)
+        return MinibatchLoss(self, outputs, inputs, batch_size, n_samples, full_data_size, copy_free)
 
     def value_and_grad(self, params, outputs, inputs, full_data_size, seed, n_samples=1):
         """jax.value_and_grad(loss_fn)(params, ...) in one fused step: (loss, grads with the structure of params)."""

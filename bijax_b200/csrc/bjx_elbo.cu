@@ -131,6 +131,10 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
     return fail(BJX_ERR_INVALID_ARGUMENT, "unknown likelihood family %d", a.likelihood);
   }
 
+  if (a.row_index != nullptr) {
+    if (p.kernel != KERNEL_TC_BF16 || a.x_planes != nullptr || a.N < 1)
+      return fail(BJX_ERR_UNSUPPORTED, "row_index: only the fused tcgen05 kernel on raw fp32 X reads through an index; gather the rows instead");
+  }
   p.Pn = a.vi_type == BJX_VI_MEAN_FIELD ? a.D : (a.vi_type == BJX_VI_FULL_RANK ? a.D * a.D : a.D + a.D * a.rank);
   p.n_qp_blocks = (int)((a.S * a.D + 255) / 256);
   const int64_t Dw = a.likelihood == BJX_LIK_BERNOULLI_PROBS ? 1 : a.Dw;
@@ -843,6 +847,17 @@ int bjx_elbo_kernel_choice(const BjxElboArgs* args) {
   int rc = make_plan(*args, p);
   if (rc) return rc;
   return p.kernel;
+}
+
+int bjx_elbo_supports_row_index(const BjxElboArgs* args) {
+  using namespace bjx;
+  BJX_REQUIRE(args != nullptr, "args is null");
+  BjxElboArgs a = *args;
+  static const int32_t dummy = 0;
+  if (a.row_index == nullptr) a.row_index = &dummy;
+  a.x_planes = nullptr;
+  Plan p;
+  return make_plan(a, p) == BJX_OK ? 1 : 0;
 }
 
 int bjx_elbo_step(const BjxElboArgs* args, void* stream) {

@@ -74,11 +74,15 @@ __device__ __forceinline__ void link_fast(int family, float y, float eta, float&
 }  // namespace tc
 
 // =========================================================================================================================
-template <int NBLK>  // D / 64
+// IDX: row r of the problem is row ridx[r] of X (minibatches drawn on the device, BjxElboArgs.row_index): the loaders read
+// the dataset THROUGH the index, so a batch costs one pass over its own rows and nothing else.  y is already gathered.
+template <int NBLK, bool IDX>  // D / 64
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, int64_t N, const float* __restrict__ theta,
          int64_t Dtot, int64_t w_off, int S, int family, float* __restrict__ Gpart, float* __restrict__ statpart,
-         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist, int flush_tiles, int pf_mode) {
+         long long* __restrict__ trace, int stagger_cycles, int ablate, int pf_dist, int flush_tiles, int pf_mode,
+         const int32_t* __restrict__ ridx) {
+  if (IDX) pf_mode = 0;  // address-range prefetches make no sense through an index
   using namespace tc;
   // optional timeline of CTA 0, tiles [TRACE_T0, TRACE_T0 + 8): 64 clock64 slots per tile (bjx_debug_set_trace_buffer)
   constexpr int64_t TRACE_T0 = 16;
@@ -153,9 +157,26 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
     // unambiguous if the same waiter meets every phase of the barrier.  (A flat round-robin over blocks made a set meet a
     // block only every other tile for D = 128 and 384, two phases apart: the wait could pass on a stale phase.)  For
     // D = 128 the sets 2 and 3 therefore idle.
+    // IDX: source rows of this lane's four rows, for the current tile and (loaded one tile ahead) for the next one
+    int32_t cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
+    if (IDX && my_tiles > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = (int64_t)blockIdx.x * TILE_ROWS + 16 * qd + rl + 4 * i;
+        nxt[i] = row < N ? __ldg(ridx + row) : 0;
+      }
+    }
     for (int64_t u = 0; u < my_tiles * 2; ++u) {
       const int64_t it = u >> 1;
       const int b = bl + 4 * (int)(u & 1);
+      if (IDX && (u & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cur[i] = nxt[i];
+          const int64_t row = (blockIdx.x + (it + 1) * gridDim.x) * TILE_ROWS + 16 * qd + rl + 4 * i;
+          nxt[i] = (it + 1 < my_tiles && row < N) ? __ldg(ridx + row) : 0;
+        }
+      }
       if (b >= NBLK) continue;
       const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS + 16 * qd + rl;
       float4 v[8];
@@ -163,7 +184,8 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       for (int i = 0; i < 4; ++i) {
         const int64_t row = row0 + 4 * i;
         if (row < N) {
-          const float4* p = reinterpret_cast<const float4*>(X + row * ldx + b * BLK_COLS + c * 8);
+          const int64_t src = IDX ? (int64_t)cur[i] : row;
+          const float4* p = reinterpret_cast<const float4*>(X + src * ldx + b * BLK_COLS + c * 8);
           v[2 * i] = __ldg(p);
           v[2 * i + 1] = __ldg(p + 1);
         } else {
@@ -173,7 +195,17 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
       }
       // fire-and-forget L2 prefetch of the SAME unit of the next tile (16 rows x 256 B = 32 lines, one per lane): HBM keeps
       // streaming into the 126 MB L2 while this warp's registers are tied up waiting for the shared-memory slot
-      if (pf_dist > 0 && pf_mode < 2) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
+      if (IDX) {
+        // the same unit of the NEXT tile, through its (already loaded) indices: lanes c = 0 and c = 4 own the two 128-byte
+        // lines of a row's 256-byte block slice
+        if (pf_dist > 0 && it + 1 < my_tiles && (c & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t prow = (blockIdx.x + (it + 1) * gridDim.x) * TILE_ROWS + 16 * qd + rl + 4 * i;
+            if (prow < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(X + (int64_t)nxt[i] * ldx + b * BLK_COLS + c * 8));
+          }
+        }
+      } else if (pf_dist > 0 && pf_mode < 2) {  // pf_dist is in blocks ahead in this warp-set's own sequence (8 = the same unit of the next tile)
         const int64_t itp = it + (pf_dist >= 8 ? pf_dist / 8 : 1);  // the same unit, pf_dist / 8 tiles ahead
         const int64_t prow = (blockIdx.x + itp * gridDim.x) * TILE_ROWS + 16 * qd + (lane >> 1);
         if (itp < my_tiles && prow < N) {
@@ -948,10 +980,15 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   do {                                                                                                                \
     static DeviceOnce attr_set;                                                                                     \
     if (!attr_set.test_and_set()) {                                                                                                  \
-      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<NBLK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<NBLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     }                                                                                                                 \
-    k_lik_tc<NBLK><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S,      \
-                                                         a.likelihood, Gpart, statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush, g_pf_mode);                     \
+    if (a.row_index != nullptr)                                                                                       \
+      k_lik_tc<NBLK, true><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S, a.likelihood, Gpart, \
+                                                                 statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush, g_pf_mode, a.row_index); \
+    else                                                                                                              \
+      k_lik_tc<NBLK, false><<<p.tc_ctas, tc::THREADS, smem, st>>>(a.X, a.ldx, a.y, a.N, theta, a.D, a.w_offset, (int)a.S, a.likelihood, Gpart, \
+                                                                  statpart, g_trace, g_stagger, g_ablate, g_pf, g_flush, g_pf_mode, nullptr); \
   } while (0)
   switch (nblk) {
     case 2: BJX_TC_LAUNCH(2); break;

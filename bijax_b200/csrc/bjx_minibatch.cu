@@ -5,9 +5,10 @@
 //     k_batch, k_elbo = jax.random.split(key)
 //     idx = jax.random.choice(k_batch, N, (B,))            # replace=True, p=None  ==  jax.random.randint(k_batch, (B,), 0, N)
 //     loss_fn(params, y[idx], {"X": X[idx]}, full_data_size=N, seed=k_elbo, n_samples=S)
-// runs here as ONE gather kernel in front of the step: every warp recomputes its row index from the key (a handful of
-// threefry blocks) and copies that row of X (raw fp32 or the prepared split-bf16 planes) and y into the batch buffers.
-// HBM traffic: B rows read + B rows written; the full dataset is never touched.
+// runs here as ONE kernel in front of the step: the row indices are recomputed from the key (a handful of threefry blocks
+// per row) and those rows of X (raw fp32 or the prepared split-bf16 planes) and y are copied into the batch buffers.
+// HBM traffic: B rows read + B rows written; the full dataset is never touched.  When the step's kernel can read the
+// dataset through the index itself (BjxElboArgs.row_index) only idx and y are produced here.
 //
 // jax.random.randint (jax/_src/random.py, _randint; int32 => 32-bit draws, all arithmetic in uint32 and wrapping as XLA's):
 //     k1, k2 = split(key);  hi = bits(k1, (B,));  lo = bits(k2, (B,));  span = N
@@ -54,11 +55,13 @@ struct GatherArgs {
   int layout, do_split, vec4;
 };
 
-// one warp per batch row
+// A warp owns `rpw` consecutive batch rows (a power of two <= 32): lane l < rpw draws the index of row l (one set of
+// threefry blocks per row, not per lane) and writes idx / y coalesced; the warp then copies the rows one after the other,
+// the index broadcast by shuffle.  rpw grows with B so that small batches still spread over all SMs.
 __global__ void __launch_bounds__(256) k_minibatch_gather(const uint32_t* __restrict__ key, const int64_t* __restrict__ key_index,
-                                                          GatherArgs g) {
+                                                          GatherArgs g, int rpw) {
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t base = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw;
   const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
   uint32_t kbatch[2] = {k[0], k[1]}, kelbo[2] = {0u, 0u};
   if (g.do_split) split2_keys(k[0], k[1], g.layout, kbatch, kelbo);
@@ -66,34 +69,41 @@ __global__ void __launch_bounds__(256) k_minibatch_gather(const uint32_t* __rest
     g.elbo_key_out[0] = kelbo[0];
     g.elbo_key_out[1] = kelbo[1];
   }
-  if (b >= g.B) return;
-  uint32_t k1[2], k2[2];
-  split2_keys(kbatch[0], kbatch[1], g.layout, k1, k2);
-  const uint32_t span = (uint32_t)g.N;
-  uint32_t mult = 65536u % span;
-  mult = (mult * mult) % span;
-  const int64_t r = (int64_t)randint_at(k1, k2, (uint64_t)b, (uint64_t)g.B, span, mult, g.layout);
-  if (lane == 0) {
-    if (g.idx_out) g.idx_out[b] = (int32_t)r;
-    if (g.yb) g.yb[b] = g.y[r];
+  if (base >= g.B) return;
+  int64_t mine = 0;
+  if (lane < rpw && base + lane < g.B) {
+    uint32_t k1[2], k2[2];
+    split2_keys(kbatch[0], kbatch[1], g.layout, k1, k2);
+    const uint32_t span = (uint32_t)g.N;
+    uint32_t mult = 65536u % span;
+    mult = (mult * mult) % span;
+    mine = (int64_t)randint_at(k1, k2, (uint64_t)(base + lane), (uint64_t)g.B, span, mult, g.layout);
+    if (g.idx_out) g.idx_out[base + lane] = (int32_t)mine;
+    if (g.yb) g.yb[base + lane] = g.y[mine];
   }
-  if (g.Xb) {
-    const float* src = g.X + r * g.ldx;
-    float* dst = g.Xb + b * g.Dw;
-    if (g.vec4) {
-      const float4* s4 = (const float4*)src;
-      float4* d4 = (float4*)dst;
-      for (int64_t c = lane; c < g.Dw / 4; c += 32) d4[c] = __ldg(s4 + c);
-    } else {
-      for (int64_t c = lane; c < g.Dw; c += 32) dst[c] = __ldg(src + c);
+  if (!g.Xb && !g.planes_b) return;
+  const int64_t row16 = g.Dp / 8;  // uint4 (8 bf16) per plane row
+  for (int j = 0; j < rpw; ++j) {
+    const int64_t b = base + j;
+    if (b >= g.B) break;
+    const int64_t r = __shfl_sync(0xffffffffu, mine, j);
+    if (g.Xb) {
+      const float* src = g.X + r * g.ldx;
+      float* dst = g.Xb + b * g.Dw;
+      if (g.vec4) {
+        const float4* s4 = (const float4*)src;
+        float4* d4 = (float4*)dst;
+        for (int64_t c = lane; c < g.Dw / 4; c += 32) d4[c] = __ldg(s4 + c);
+      } else {
+        for (int64_t c = lane; c < g.Dw; c += 32) dst[c] = __ldg(src + c);
+      }
     }
-  }
-  if (g.planes_b) {
-    const int64_t row16 = g.Dp / 8;  // uint4 (8 bf16) per plane row
-    for (int t = 0; t < 2; ++t) {
-      const uint4* src = g.planes + ((int64_t)t * g.N + r) * row16;
-      uint4* dst = g.planes_b + ((int64_t)t * g.B + b) * row16;
-      for (int64_t c = lane; c < row16; c += 32) dst[c] = __ldg(src + c);
+    if (g.planes_b) {
+      for (int t = 0; t < 2; ++t) {
+        const uint4* src = g.planes + ((int64_t)t * g.N + r) * row16;
+        uint4* dst = g.planes_b + ((int64_t)t * g.B + b) * row16;
+        for (int64_t c = lane; c < row16; c += 32) dst[c] = __ldg(src + c);
+      }
     }
   }
 }
@@ -114,7 +124,13 @@ int launch_minibatch_gather(const BjxMinibatch& mb, const uint32_t* key, const i
   g.idx_out = mb.idx_out, g.elbo_key_out = mb.elbo_key;
   g.layout = layout, g.do_split = mb.elbo_key != nullptr ? 1 : 0;
   g.vec4 = (mb.Xb && mb.Dw % 4 == 0 && mb.ldx_full % 4 == 0 && (((uintptr_t)mb.X_full | (uintptr_t)mb.Xb) & 15) == 0) ? 1 : 0;
-  k_minibatch_gather<<<(unsigned)((mb.B + 7) / 8), 256, 0, st>>>(key, key_index, g);
+  int rpw = 32;  // index-only calls: one thread per row
+  if (g.Xb || g.planes_b) {
+    rpw = 1;
+    while (rpw < 32 && mb.B / (2 * rpw) >= 4096) rpw *= 2;  // keep >= 4096 warps in flight before growing a warp's share
+  }
+  const int64_t warps = (mb.B + rpw - 1) / rpw;
+  k_minibatch_gather<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(key, key_index, g, rpw);
   BJX_LAUNCH_CHECK("k_minibatch_gather");
   return BJX_OK;
 }

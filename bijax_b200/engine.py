@@ -144,9 +144,27 @@ class ElboEngine:
             X = X.to(device=self.device, dtype=torch.float32)
         if X.dim() == 2 and X.stride(1) != 1:
             X = X.contiguous()  # rows may be pitched (ldx > Dw, e.g. a column slice of a wider matrix), columns must be dense
-        if X.dim() != 2 or X.shape[0] != N or X.shape[1] != self.Dw:
+        indexed = self._row_index_for(X) is not None  # rows are X[row_index[r]]: X is the full dataset, y the batch
+        if X.dim() != 2 or (X.shape[0] != N and not indexed) or X.shape[1] != self.Dw:
             raise ValueError(f"X must be [N={N}, D={self.Dw}] (rows = data, row-major); got {tuple(X.shape)}")
         return X, y, N, X.stride(0)
+
+    def bind_row_index(self, X: Optional[torch.Tensor], index: Optional[torch.Tensor]) -> None:
+        """Steps on the tensor ``X`` read it through ``index`` (int32 [B], BjxElboArgs.row_index) with ``y`` of length B --
+        the minibatch sampler's copy-free path; (None, None) removes the binding."""
+        self._bound_index = None if X is None or index is None else (X.data_ptr(), index)
+
+    def _row_index_for(self, X) -> Optional[int]:
+        bound = getattr(self, "_bound_index", None)
+        if bound is not None and X is not None and X.data_ptr() == bound[0]:
+            return bound[1].data_ptr()
+        return None
+
+    def supports_row_index(self, S, N) -> bool:
+        if self.Dw < 1:
+            return False
+        a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        return self.lib.bjx_elbo_supports_row_index(C.byref(a)) == 1
 
     def wants_planes(self, S, N) -> bool:
         """True if a step of this shape reads the dataset as prepared split-bf16 planes (TMA-fed tcgen05 kernels)."""
@@ -162,7 +180,7 @@ class ElboEngine:
 
     def _x_planes(self, a: nv.BjxElboArgs, X: torch.Tensor) -> Optional[int]:
         """Device pointer of the prepared operand planes of X if this step takes the GEMM path, else None."""
-        if not self.prepare_dataset or X is None:
+        if not self.prepare_dataset or X is None or self._row_index_for(X) is not None:
             return None
         if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
             return None
@@ -231,6 +249,7 @@ class ElboEngine:
             a.kwargs = kw.data_ptr()
         a.X = X.data_ptr() if X is not None else None
         a.y = y.data_ptr()
+        a.row_index = self._row_index_for(X)
         if out is None:
             out = torch.empty(1 + self.D + self.P + self.K, dtype=torch.float32, device=dev)
         a.out = out.data_ptr()
@@ -318,8 +337,19 @@ class ElboEngine:
             nv.check(self.lib.bjx_posterior_log_prob(C.byref(a), theta.data_ptr(), theta.shape[0], out.data_ptr(), nv.current_stream_ptr()))
         return out
 
-    def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
-                    n_samples, partitionable=None, minibatch=None):
+    def train_steps(self, *args, minibatch=None, **kwargs):
+        """See _train_steps; ``minibatch`` is the state of a MinibatchLoss (its batch buffers and BjxMinibatch)."""
+        indexed = minibatch is not None and minibatch["indexed"]
+        if indexed:
+            self.bind_row_index(minibatch["X"], minibatch["idx"])
+        try:
+            return self._train_steps(*args, minibatch=minibatch, **kwargs)
+        finally:
+            if indexed:
+                self.bind_row_index(None, None)
+
+    def _train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
+                     n_samples, partitionable=None, minibatch=None):
         """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip
         (bjx_train_steps; train_fn's scan body, utils.py:22-28).  ``keys`` is the [n, 2] uint32 array of per-step keys,
         ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place."""
@@ -331,6 +361,7 @@ class ElboEngine:
         a.X = X.data_ptr() if X is not None else None
         a.y = y.data_ptr()
         a.out = out.data_ptr()
+        a.row_index = self._row_index_for(X)
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
         if minibatch is not None:  # X / y are the sampler's batch buffers; it fills the planes itself (bjx_minibatch_gather)
             a.x_planes = minibatch["planes_b"].data_ptr() if minibatch["planes_b"] is not None else None

@@ -24,8 +24,12 @@ from . import _native as nv
 from . import random as brandom
 
 
+COPY_FREE_MIN_ROWS = 32768
+
+
 class MinibatchLoss:
-    def __init__(self, model, outputs, inputs, batch_size: int, n_samples: int = 1, full_data_size: Optional[int] = None):
+    def __init__(self, model, outputs, inputs, batch_size: int, n_samples: int = 1, full_data_size: Optional[int] = None,
+                 copy_free: Optional[bool] = None):
         nv.require_cuda()
         self.model = model
         self.B = int(batch_size)
@@ -36,6 +40,11 @@ class MinibatchLoss:
         if self.B < 1 or self.N < 1:
             raise ValueError("need batch_size >= 1 and a non-empty dataset")
         self.full_data_size = float(self.N if full_data_size is None else full_data_size)
+        # True: the step reads the dataset through the row index whenever its kernel can (BjxElboArgs.row_index); False:
+        # always gather the batch into its own buffers; None: by batch size -- measured on B200 at D = 512 (profiles/
+        # r01_minibatch.json) the copy-free path wins from a few tiles per SM upwards (76 vs 102 us per epoch at 64 Ki rows,
+        # 329 vs 562 us at 512 Ki) and loses below (46 vs 36 us at 4 Ki rows: one tile per CTA, latency-bound)
+        self.copy_free = (self.B >= COPY_FREE_MIN_ROWS) if copy_free is None else bool(copy_free)
         self._state = None  # (engine, buffers) built on first use: the engine depends on the params' trainable kwargs
 
     # ---- buffers ----------------------------------------------------------------------------------------------------
@@ -51,9 +60,12 @@ class MinibatchLoss:
         st["yb"] = torch.empty(self.B, dtype=torch.float32, device=dev)
         st["idx"] = torch.empty(self.B, dtype=torch.int32, device=dev)
         st["elbo_key"] = torch.zeros(2, dtype=torch.uint32, device=dev)
-        st["Xb"] = torch.zeros((self.B, engine.Dw), dtype=torch.float32, device=dev) if X is not None else None
+        st["indexed"] = X is not None and self.copy_free and engine.supports_row_index(self.S, self.B)
+        st["Xb"] = torch.zeros((self.B, engine.Dw), dtype=torch.float32, device=dev) if X is not None and not st["indexed"] else None
         st["planes_full"] = st["planes_b"] = None
-        if X is not None and engine.wants_planes(self.S, self.B):
+        if st["indexed"]:
+            pass  # the step reads the dataset through idx (BjxElboArgs.row_index): nothing to gather but y
+        elif X is not None and engine.wants_planes(self.S, self.B):
             # the batch step is TMA-fed: keep the FULL dataset as planes (made once) and gather plane rows
             lib = engine.lib
             full = torch.empty(int(lib.bjx_x_planes_bytes(N, engine.Dw)), dtype=torch.uint8, device=dev)
@@ -67,7 +79,7 @@ class MinibatchLoss:
         mb.idx_out, mb.elbo_key = st["idx"].data_ptr(), st["elbo_key"].data_ptr()
         if st["planes_b"] is not None:
             mb.x_planes_full, mb.planes_b = st["planes_full"].data_ptr(), st["planes_b"].data_ptr()
-        elif X is not None:
+        elif X is not None and not st["indexed"]:
             mb.X_full, mb.Xb = X.data_ptr(), st["Xb"].data_ptr()
         st["mb"] = mb
         self._state = st
@@ -81,12 +93,13 @@ class MinibatchLoss:
     # ---- one draw ---------------------------------------------------------------------------------------------------
     def sample(self, params, seed):
         """Draw the batch of ``seed``: returns (idx int32[B], y[idx], X[idx] or None, k_elbo).  The returned tensors are
-        the sampler's own buffers (overwritten by the next draw); X[idx] is None when the step reads gathered planes."""
+        the sampler's own buffers (overwritten by the next draw); X[idx] is None when the step reads the dataset through
+        idx (copy-free path) and stale when it reads gathered planes."""
         st = self._setup(self._engine(params))
         seed = brandom._check_key(seed)
         with torch.cuda.device(st["engine"].device):
             nv.check(st["engine"].lib.bjx_minibatch_gather(C.byref(st["mb"]), seed.data_ptr(), None, brandom._layout(None), nv.current_stream_ptr()))
-        return st["idx"], st["yb"], (st["Xb"] if st["planes_b"] is None else None), st["elbo_key"]
+        return st["idx"], st["yb"], st["Xb"], st["elbo_key"]
 
     def __call__(self, params, seed):
         """The loss of the docstring's ``loss(params, seed)``; differentiable like ``model.loss_fn``."""
@@ -94,10 +107,13 @@ class MinibatchLoss:
         self.sample(params, seed)
         engine = st["engine"]
         inputs = None
-        if st["Xb"] is not None:
-            inputs = {engine.x_name: st["Xb"]} if isinstance(self.inputs, dict) else st["Xb"]
+        Xin = st["X"] if st["indexed"] else st["Xb"]
+        if Xin is not None:
+            inputs = {engine.x_name: Xin} if isinstance(self.inputs, dict) else Xin
         engine.bind_planes(st["Xb"], st["planes_b"])
+        engine.bind_row_index(st["X"] if st["indexed"] else None, st["idx"])
         try:
             return self.model.loss_fn(params, st["yb"], inputs, self.full_data_size, st["elbo_key"], self.S)
         finally:
             engine.bind_planes(None, None)
+            engine.bind_row_index(None, None)

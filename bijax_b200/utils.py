@@ -70,7 +70,7 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
     mb_state = None
     if "minibatch" in kw:  # batch buffers of the on-device sampler; every step gathers a fresh batch into them
         mb_state = kw["minibatch"]._setup(engine)
-        outputs, X = mb_state["yb"], mb_state["Xb"]
+        outputs, X = mb_state["yb"], (mb_state["X"] if mb_state["indexed"] else mb_state["Xb"])
     else:
         outputs, inputs = kw["outputs"], kw["inputs"]
         X = None

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BJX_ABI_VERSION 2
+#define BJX_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define BJX_API __attribute__((visibility("default")))
@@ -177,6 +177,14 @@ typedef struct BjxElboArgs {
 
   /* optional (ABI 2): rank of the low-rank family (BJX_VI_LOW_RANK), 1..64 */
   int64_t rank;
+
+  /* optional (ABI 3): row indirection for minibatches drawn on the device.  When set, row r of this call's data is
+   * X[row_index[r]]: X is the FULL dataset, N the number of indexed rows (the batch size), and the kernel reads the dataset
+   * through the index -- one pass over the batch's own rows, no gathered copy.  y is NOT indexed (pass y[row_index[r]],
+   * e.g. BjxMinibatch.yb); x_planes must be NULL.  Only the fused tcgen05 kernel reads through an index (ask
+   * bjx_elbo_supports_row_index); every other shape returns BJX_ERR_UNSUPPORTED and the caller gathers rows instead
+   * (bjx_minibatch_gather). */
+  const int32_t* row_index;
 } BjxElboArgs;
 
 #define BJX_POINT_OFF 0
@@ -218,6 +226,8 @@ BJX_API int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t 
 /* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = fused tcgen05 single pass
  * (split-bf16), 3 = coin toss, 4 = two-pass TMA-fed tcgen05 GEMM (split-bf16) */
 BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
+/* 1 if a step of this shape can read X through BjxElboArgs.row_index, 0 if the rows must be gathered first */
+BJX_API int bjx_elbo_supports_row_index(const BjxElboArgs* args);
 
 /* ---- posterior access (.apply -> Posterior.sample / log_prob, core.py:39-75) */
 /* theta[S, D] = bijector(loc + scale * eps) for eps = normal(key, (S, D)); z_out optional */

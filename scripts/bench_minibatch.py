@@ -33,9 +33,9 @@ def ev_time(fn, steps, warmup=5):
 
 res = []
 keys = br.split(br.PRNGKey(0), 300)
-for B in (4096, 65536, 524288):
+for B, copy_free in [(b, cf) for b in (4096, 65536, 524288) for cf in (True, False)]:
     if B > N: continue
-    loss = model.minibatch_loss_fn(y, {"X": X}, batch_size=B, n_samples=S)
+    loss = model.minibatch_loss_fn(y, {"X": X}, batch_size=B, n_samples=S, copy_free=copy_free)
     params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.01 * br.normal(k, s))
     us_gather = ev_time(lambda i: loss.sample(params, keys[i]), 200)
     st = loss._state
@@ -44,8 +44,11 @@ for B in (4096, 65536, 524288):
     loc, raw = params["posterior"]["loc"], params["posterior"]["scale_diag"]
     o = torch.empty(1 + 2 * D, device=dev)
     eng.bind_planes(st["Xb"], st["planes_b"])
-    us_step = ev_time(lambda i: eng.step(keys[i], loc, raw, None, st["Xb"], st["yb"], N / B, S, out=o), 200)
+    eng.bind_row_index(st["X"] if st["indexed"] else None, st["idx"])
+    Xin = st["X"] if st["indexed"] else st["Xb"]
+    us_step = ev_time(lambda i: eng.step(keys[i], loc, raw, None, Xin, st["yb"], N / B, S, out=o), 200)
     eng.bind_planes(None, None)
+    eng.bind_row_index(None, None)
     n = 40 * 16
     def fresh():
         return model.init(br.PRNGKey(0), initializer=lambda k, s: 0.01 * br.normal(k, s))
@@ -57,14 +60,21 @@ for B in (4096, 65536, 524288):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     bj.train(loss, fresh(), optim.adam(0.01), n_epochs=nh, seed=br.PRNGKey(1), fused=False)
     torch.cuda.synchronize(); us_host = (time.perf_counter() - t0) * 1e6 / nh
-    gather_bytes = 2.0 * B * D * 4 + 2.0 * B * 4 + B * 4  # rows read + written (planes: 2 x bf16 = 4 B/elem), y read + written, idx written
-    rec = {"N": N, "B": B, "D": D, "S": S, "batch_layout": "split-bf16 planes (gathered plane rows)" if uses_planes else "raw fp32 rows",
+    if st["indexed"]:
+        gather_bytes = 3.0 * B * 4  # y read + written, idx written
+        layout = "none: the step reads X[idx[r]] through BjxElboArgs.row_index (raw fp32 rows, converted in registers)"
+    else:
+        gather_bytes = 2.0 * B * D * 4 + 3.0 * B * 4  # rows read + written (planes: 2 x bf16 = 4 B/elem), y read + written, idx written
+        layout = "split-bf16 planes (gathered plane rows)" if uses_planes else "raw fp32 rows (gathered)"
+    step_bytes = 4.0 * B * D + 4.0 * B
+    rec = {"N": N, "B": B, "D": D, "S": S, "batch_copy": layout,
            "step_kernel": eng.kernel_choice(S, B), "gather_us": us_gather, "gather_algorithmic_bytes": gather_bytes,
-           "gather_GBps": gather_bytes / us_gather * 1e-3, "step_us": us_step, "step_algorithmic_bytes": 4.0 * B * D + 4.0 * B,
-           "step_GBps": (4.0 * B * D + 4.0 * B) / us_step * 1e-3,
-           "fused_loop_us_per_epoch": us_fused, "host_driven_loop_us_per_epoch": us_host,
-           "final_loss": float(r["losses"][-16:].mean())}
-    if hbm: rec["gather_frac_of_hbm_peak"] = rec["gather_GBps"] / hbm
+           "gather_GBps": gather_bytes / us_gather * 1e-3, "step_us": us_step, "step_algorithmic_bytes": step_bytes,
+           "step_GBps": step_bytes / us_step * 1e-3,
+           "fused_loop_us_per_epoch": us_fused, "epoch_GBps_on_algorithmic_bytes": step_bytes / us_fused * 1e-3,
+           "host_driven_loop_us_per_epoch": us_host, "default_for_this_batch_size": (B >= 32768) == copy_free, "final_loss": float(r["losses"][-16:].mean())}
+    if hbm:
+        rec["epoch_frac_of_hbm_peak"] = rec["epoch_GBps_on_algorithmic_bytes"] / hbm
     res.append(rec)
     del loss
 # full-batch epoch for scale

@@ -45,7 +45,7 @@ def _logistic_model(D):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("case", ["raw_small_d", "planes_tc", "coin"])
+@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "planes_tc", "coin"])
 def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
     """sample(): idx / y[idx] / X[idx] (or the planes of X[idx]) / k_elbo against the oracle's split + randint; the
     minibatch loss and gradients equal loss_fn evaluated on the rows indexed by torch, bit for bit."""
@@ -58,7 +58,7 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
             model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}, {}, lk.GaussianLinear())
             params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
             params["log_noise_scale"] = torch.tensor(-0.7, device=dev)
-        elif case == "planes_tc":
+        elif case in ("planes_tc", "indexed_tc"):
             N, D, B, S = 3000, 128, 700, 32
             X, y = C.synth_logistic(N, D)
             model = _logistic_model(D)
@@ -71,7 +71,7 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         yd = torch.tensor(y, device=dev)
         Xd = torch.tensor(X, device=dev) if X is not None else None
         inputs = {"X": Xd} if Xd is not None else None
-        loss = model.minibatch_loss_fn(yd, inputs, batch_size=B, n_samples=S, full_data_size=3 * N)
+        loss = model.minibatch_loss_fn(yd, inputs, batch_size=B, n_samples=S, full_data_size=3 * N, copy_free={"planes_tc": False, "indexed_tc": True}.get(case))
         seed = br.PRNGKey(77)
         idx, yb, Xb, ke = loss.sample(params, seed)
         kb_np, ke_np = tf.split(tf.prng_key(77), 2, layout)
@@ -82,7 +82,10 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         uses_planes = case == "planes_tc"
         st = loss._state
         assert (st["planes_b"] is not None) == uses_planes
-        if X is not None and not uses_planes:
+        assert st["indexed"] == (case == "indexed_tc")  # the fused tcgen05 kernel reads the dataset through idx: no copy
+        if st["indexed"]:
+            assert Xb is None and st["mb"].Xb is None and st["mb"].planes_b is None
+        if X is not None and not uses_planes and not st["indexed"]:
             assert np.array_equal(Xb.cpu().numpy(), X[want_idx])
         if uses_planes:  # gathered plane rows == the planes of the gathered rows
             Xg = Xd[torch.as_tensor(want_idx, device=dev).long()].contiguous()
@@ -94,10 +97,17 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         li = torch.as_tensor(want_idx, device=dev).long()
         ref_inputs = {"X": Xd[li].contiguous()} if Xd is not None else None
         ke_t = torch.tensor(ke_np.astype(np.int64), dtype=torch.int64).to(torch.uint32).to(dev)
-        want, g_want = model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
+        ref_model = model
+        if case == "indexed_tc":  # the same kernel without the index: raw fp32 rows, converted in registers
+            ref_model = bj.ADVI(model.prior, {"weights": tfb.Identity()}, lk.BernoulliLogits(), vi_type="mean_field", prepare_dataset=False)
+        want, g_want = ref_model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
         assert got.item() == want.item()
         for k in ("loc", "scale_diag"):
             assert torch.equal(g_got["posterior"][k], g_want["posterior"][k])
+        if case == "indexed_tc":  # and the TMA-fed kernel on the gathered planes agrees to rounding
+            w2, g2 = model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
+            C.assert_close(got.item(), w2.item(), what="loss, indexed vs planes")
+            C.assert_close(g_got["posterior"]["loc"].cpu().numpy(), g2["posterior"]["loc"].cpu().numpy(), what="d loc, indexed vs planes")
     finally:
         br.config.threefry_partitionable = False
 
@@ -124,7 +134,7 @@ def test_minibatch_loss_against_the_float64_oracle():
     C.assert_close(grads["log_noise_scale"].cpu().numpy(), wgk["log_noise_scale"].numpy(), what="d log_noise_scale")
 
 
-@pytest.mark.parametrize("case", ["raw_small_d", "planes_tc"])
+@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "planes_tc"])
 def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
     """bjx_train_steps_minibatch in replayed CUDA graphs (gather -> step -> Adam per epoch, batch drawn from
     split(seed, n)[i] on the device) against the generic loop calling loss(params, seed=seeds[i])."""
@@ -147,7 +157,7 @@ def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
             p["log_noise_scale"] = torch.tensor(-1.0, device=dev)
         return p
 
-    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S)
+    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S, copy_free={"planes_tc": False, "indexed_tc": True}.get(case))
     n = 2 * U.GRAPH_STEPS + 3
     fused = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
     host = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3), fused=False)
@@ -178,3 +188,42 @@ def test_minibatch_argument_checks():
     assert b"y_full" in lib.bjx_last_error()
     with pytest.raises(ValueError):
         br.randint(k, (3,), 0, 2**31 + 5)
+
+
+@pytest.mark.parametrize("D,S,N,B", [(512, 32, 30000, 4097), (256, 7, 9000, 1), (384, 20, 5000, 5000)])
+def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
+    """BjxElboArgs.row_index (ABI 3): the fused tcgen05 kernel reading X[idx[r]] gives, bit for bit, what it gives on the
+    gathered rows (repeated indices, B not a multiple of the 64-row tile, every block count); shapes outside that kernel
+    say so instead of ignoring the index."""
+    dev = torch.device("cuda")
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model = bj.ADVI(prior, {"weights": tfb.Identity()}, lk.BernoulliLogits(), prepare_dataset=False)
+    eng, _ = model._engine_for({})
+    assert eng.supports_row_index(S, B)
+    idx = br.randint(br.PRNGKey(D + B), (B,), 0, N)
+    li = idx.long()
+    loc = 0.05 * br.normal(br.PRNGKey(1), (D,))
+    raw = torch.full((D,), -2.0, device=dev)
+    key = br.PRNGKey(4)
+    want = eng.step(key, loc, raw, None, Xd[li].contiguous(), yd[li].contiguous(), N / B, S).clone()
+    eng.bind_row_index(Xd, idx)
+    try:
+        got = eng.step(key, loc, raw, None, Xd, yd[li].contiguous(), N / B, S).clone()
+    finally:
+        eng.bind_row_index(None, None)
+    assert torch.equal(got, want)
+    # a shape the fused kernel does not take
+    small = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(5, np.float32), scale_diag=np.ones(5, np.float32))},
+                    {"weights": tfb.Identity()}, lk.BernoulliLogits())
+    e2, _ = small._engine_for({})
+    assert not e2.supports_row_index(S, B)
+    X5 = torch.zeros((N, 5), device=dev)
+    e2.bind_row_index(X5, idx)
+    try:
+        with pytest.raises(nv.BjxError):
+            e2.step(key, torch.zeros(5, device=dev), torch.zeros(5, device=dev), None, X5, yd[li].contiguous(), 1.0, S)
+    finally:
+        e2.bind_row_index(None, None)
+
