@@ -62,18 +62,25 @@ __global__ void __launch_bounds__(256) k_minibatch_gather(const uint32_t* __rest
                                                           GatherArgs g, int rpw) {
   const int lane = threadIdx.x & 31;
   const int64_t base = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw;
-  const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
-  uint32_t kbatch[2] = {k[0], k[1]}, kelbo[2] = {0u, 0u};
-  if (g.do_split) split2_keys(k[0], k[1], g.layout, kbatch, kelbo);
-  if (g.elbo_key_out && blockIdx.x == 0 && threadIdx.x == 0) {
-    g.elbo_key_out[0] = kelbo[0];
-    g.elbo_key_out[1] = kelbo[1];
+  // the two key splits are the same for every row: once per block
+  __shared__ uint32_t s_keys[4];
+  if (threadIdx.x == 0) {
+    const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
+    uint32_t kbatch[2] = {k[0], k[1]}, kelbo[2] = {0u, 0u};
+    if (g.do_split) split2_keys(k[0], k[1], g.layout, kbatch, kelbo);
+    if (g.elbo_key_out && blockIdx.x == 0) {
+      g.elbo_key_out[0] = kelbo[0];
+      g.elbo_key_out[1] = kelbo[1];
+    }
+    uint32_t k1[2], k2[2];
+    split2_keys(kbatch[0], kbatch[1], g.layout, k1, k2);
+    s_keys[0] = k1[0], s_keys[1] = k1[1], s_keys[2] = k2[0], s_keys[3] = k2[1];
   }
+  __syncthreads();
   if (base >= g.B) return;
   int64_t mine = 0;
   if (lane < rpw && base + lane < g.B) {
-    uint32_t k1[2], k2[2];
-    split2_keys(kbatch[0], kbatch[1], g.layout, k1, k2);
+    const uint32_t k1[2] = {s_keys[0], s_keys[1]}, k2[2] = {s_keys[2], s_keys[3]};
     const uint32_t span = (uint32_t)g.N;
     uint32_t mult = 65536u % span;
     mult = (mult * mult) % span;
