@@ -489,7 +489,7 @@ struct Maps {
 };
 struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
   unsigned long long x_full[9], x_empty[9];
-  unsigned long long acc1_full, dl_full, dl_empty, done;
+  unsigned long long acc1_full[2], dl_full, dl_empty, done;  // one logits barrier per accumulator (tile parity)
   uint32_t tmem_base;
 };
 }  // namespace tcp
@@ -520,9 +520,16 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   // spare slot is reached by a leading-dimension byte offset of two blocks instead of one.
   // X slots are 16 KB: [x1 block | x2 block], i.e. 128 rows of 128 bytes -- GEMM1 takes the stacked pair as ONE UMMA A
   // operand with M = 128 (rows 0-63 the x1 terms, rows 64-127 the x2 terms of the same 64 data rows); slot -1 is the spare.
+  // Narrow problems (D = 128, 256): a tile is only 2 or 4 blocks, so the eight slots form a RING of R = 4 or 2 tiles
+  // (slot = (tile % R) * NBLK + block).  The producer then runs R tiles ahead of the tensor core, and the whole GEMM1 of
+  // tile t+1 is issued under the epilogue of tile t -- with one tile of slots the loads of tile t+1 could only start when
+  // GEMM2(t) released them and every tile paid a TMA round trip (0.43 of the HBM roofline at D = 128).
   constexpr int SLOT = 2 * BLK_BYTES;
+  constexpr int R = 8 / NBLK;
+  constexpr bool RING = R > 1;
+  constexpr int NSLOT = RING ? 8 : NBLK;
   uint8_t* sx = smem + SLOT;
-  uint8_t* sth = sx + NBLK * SLOT;
+  uint8_t* sth = sx + NSLOT * SLOT;
   uint8_t* sdl = sth + NBLK * BLK_BYTES;
   tcp::BarsP* bars = (tcp::BarsP*)(sdl + BLK_BYTES);
   float* sred = (float*)(bars + 1);
@@ -537,7 +544,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       mbar_init(&bars->x_full[b], 1);  // the producer's expect_tx arrival; completion is counted in bytes
       mbar_init(&bars->x_empty[b], 1);
     }
-    mbar_init(&bars->acc1_full, 1);
+    mbar_init(&bars->acc1_full[0], 1);
+    mbar_init(&bars->acc1_full[1], 1);
     mbar_init(&bars->dl_full, EW);
     mbar_init(&bars->dl_empty, 1);
     mbar_init(&bars->done, 1);
@@ -585,29 +593,43 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         tma_load_2d(slot, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
         tma_load_2d(slot + BLK_BYTES, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
       };
-      if (my_tiles > 0) issue_block0(0);
+      const int pf_ahead = pf_dist * R;  // the same distance in bytes for every D
+      if (!RING && my_tiles > 0) issue_block0(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
         auto bulk_pf = [&]() {
           // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
-          const int64_t rowp = (blockIdx.x + (it + pf_dist) * gridDim.x) * TILE_ROWS;
+          const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * TILE_ROWS;
           const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
           const uint32_t bytes = (uint32_t)(rows * D * 2);
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * D), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * D), "r"(bytes) : "memory");
         };
-        if (pf_mode == 0 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
-        for (int b = 1; b < NBLK; ++b) {
-          mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
-          BJX_TRACE(it, b);
-          mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
-          tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-          tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-          // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue it
-          // now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
-          if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
+        if (pf_mode == 0 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
+        if constexpr (RING) {
+          const int q0 = (int)(it % R) * NBLK;
+          const uint32_t use = (uint32_t)((it / R) & 1);
+          for (int b = 0; b < NBLK; ++b) {
+            const int q = q0 + b;
+            mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
+            BJX_TRACE(it, b);
+            mbar_expect_tx(&bars->x_full[q], 2u * BLK_BYTES);
+            tma_load_2d(sx + q * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+            tma_load_2d(sx + q * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+          }
+        } else {
+          for (int b = 1; b < NBLK; ++b) {
+            mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
+            BJX_TRACE(it, b);
+            mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
+            tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+            tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+            // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue
+            // it now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
+            if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
+          }
         }
-        if (pf_mode == 1 && pf_dist > 0 && it + pf_dist < my_tiles) bulk_pf();
+        if (pf_mode == 1 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
       }
     }
   } else if (warp == tcp::MMA_WARP) {
@@ -629,6 +651,20 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     // issued right after this tile's logits are committed, so it runs while the epilogue warps work on them)
     auto gemm1_block = [&](int64_t t, int b) {
       const bool alt = (t & 1) != 0;
+      if constexpr (RING) {
+        const int q = (int)(t % R) * NBLK + b;
+        mbar_wait(&bars->x_full[q], (uint32_t)((t / R) & 1));
+        if (lane == 0) BJX_TRACE(t, 16 + b);
+        if (!(ablate & 1) && elect_one()) {
+          const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);
+          const uint64_t boff = (uint64_t)((q * SLOT) >> 4);
+          const uint32_t acc = tmem + ACC1_COL + (alt ? NB : 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
+        }
+        __syncwarp();
+        return;
+      }
       if (b == 0)
         mbar_wait(&bars->x_full[alt ? 8 : 0], (uint32_t)((t >> 1) & 1));
       else
@@ -643,22 +679,44 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       }
       __syncwarp();
     };
-    if (my_tiles > 0) gemm1_block(0, 0);
+    if (my_tiles > 0) {
+      if constexpr (RING) {
+        for (int b = 0; b < NBLK; ++b) gemm1_block(0, b);
+        if (elect_one()) umma_commit(&bars->acc1_full[0]);
+        __syncwarp();
+      } else {
+        gemm1_block(0, 0);
+      }
+    }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      const bool alt = (it & 1) != 0;
+      const bool alt = RING ? false : (it & 1) != 0;
       const int idx0 = alt ? 8 : 0;
-      for (int b = 1; b < NBLK; ++b) gemm1_block(it, b);
-      if (elect_one()) umma_commit(&bars->acc1_full);
-      __syncwarp();
-      if (lane == 0) BJX_TRACE(it, 24);
-      if (it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
+      const int q0 = RING ? (int)(it % R) * NBLK : 0;  // first slot of this tile
+      if constexpr (RING) {
+        // the whole GEMM1 of the next tile (other logits accumulator, slots already in the ring) under this tile's epilogue
+        // Its barrier is the OTHER one (one per accumulator): the previous phase of that barrier was tile it - 1, which
+        // every epilogue warp consumed before dl_full(it - 1) -- so it may complete right away, and the epilogue goes from
+        // tile `it` straight into tile it + 1 without a hand-over through this warp.
+        if (lane == 0) BJX_TRACE(it, 24);
+        if (it + 1 < my_tiles) {
+          for (int b = 0; b < NBLK; ++b) gemm1_block(it + 1, b);
+          if (elect_one()) umma_commit(&bars->acc1_full[(it + 1) & 1]);
+          __syncwarp();
+        }
+      } else {
+        for (int b = 1; b < NBLK; ++b) gemm1_block(it, b);
+        if (elect_one()) umma_commit(&bars->acc1_full[it & 1]);
+        __syncwarp();
+        if (lane == 0) BJX_TRACE(it, 24);
+        if (it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
+      }
       mbar_wait(&bars->dl_full, ph);
       tc_fence_after();
       if (lane == 0) BJX_TRACE(it, 25);
       for (int ch = 0; ch < NCH; ++ch) {
         if (elect_one()) {
-          const uint64_t coff = (uint64_t)((2 * ch * SLOT) >> 4);
+          const uint64_t coff = (uint64_t)(((q0 + 2 * ch) * SLOT) >> 4);
           const uint64_t a1 = (ch == 0 && alt) ? tx1_alt : tx1 + coff;
           const uint64_t a2 = (ch == 0 && alt) ? tx2_alt : tx2 + coff;
 #pragma unroll
@@ -668,8 +726,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
                       (k != 0) || !(it == 0 || phase == ch * flush_step));
             umma_bf16(tmem + ACC2_COL + ch * NB, a2 + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
           }
-          umma_commit(&bars->x_empty[ch == 0 ? idx0 : 2 * ch]);
-          umma_commit(&bars->x_empty[2 * ch + 1]);
+          umma_commit(&bars->x_empty[(ch == 0 && !RING) ? idx0 : q0 + 2 * ch]);
+          umma_commit(&bars->x_empty[q0 + 2 * ch + 1]);
         }
         __syncwarp();
       }
@@ -754,7 +812,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       // fetch the next tile's label now: its latency hides behind this tile's GEMM1
       row += (int64_t)gridDim.x * TILE_ROWS;
       yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
-      mbar_wait(&bars->acc1_full, ph);
+      mbar_wait(&bars->acc1_full[it & 1], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
       uint32_t va[SG], vb[SG];
@@ -931,7 +989,8 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   const size_t smem = tc_smem_bytes(nblk);
   if (a.x_planes != nullptr) {
     // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
-    const size_t smem = (size_t)(3 * nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 + 8 * 256 * sizeof(float) + 1024;
+    const int nslot = 8 / nblk > 1 ? 8 : nblk;  // D = 128, 256: the eight slots are a ring of tiles (see the kernel)
+    const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 + 8 * 256 * sizeof(float) + 1024;
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");

@@ -227,3 +227,28 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
     finally:
         e2.bind_row_index(None, None)
 
+
+
+def test_minibatch_on_the_two_pass_gemm_path():
+    """A batch step outside the fused kernel's envelope (S = 64 > 32) runs the TMA-fed two-pass GEMM on gathered plane rows:
+    same numbers (to the rounding of its atomic reduction order) as loss_fn on host-indexed rows."""
+    dev = torch.device("cuda")
+    N, D, B, S = 40000, 192, 16384, 64
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model = bj.ADVI(prior, {"weights": tfb.Identity()}, lk.BernoulliLogits())
+    params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
+    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S)
+    seed = br.PRNGKey(31)
+    got, g_got = bj.value_and_grad(loss)(params, seed)
+    st = loss._state
+    assert st["engine"].kernel_choice(S, B) == "tcgen05_gemm_two_pass"
+    assert st["planes_b"] is not None and not st["indexed"]
+    kb, ke = tf.split(tf.prng_key(31), 2, 0)
+    li = torch.as_tensor(tf.randint(kb, B, 0, N, 0), device=dev).long()
+    ke_t = torch.tensor(ke.astype(np.int64), dtype=torch.int64).to(torch.uint32).to(dev)
+    want, g_want = model.value_and_grad(params, yd[li].contiguous(), {"X": Xd[li].contiguous()}, N, ke_t, S)
+    C.assert_close(got.item(), want.item(), rtol=2e-6, atol_scale=2e-6, what="loss")
+    for k in ("loc", "scale_diag"):
+        C.assert_close(g_got["posterior"][k].cpu().numpy(), g_want["posterior"][k].cpu().numpy(), rtol=2e-6, atol_scale=2e-6, what=k)
