@@ -1,4 +1,4 @@
-"""The fused single-pass kernel (k_lik_tc_tma, prepared planes) across its envelope: D in {128, 256, 384, 512}, S in {8, 32},
+"""The fused single-pass kernel (k_lik_tc_tma, prepared planes; ENV_RAW=1: k_lik_tc on raw fp32 X) across its envelope: D in {128, 256, 384, 512}, S in {8, 32},
 both likelihood families, X sized to ~10 GB so that every point streams from HBM (>> L2).  Reports ms/step and the
 achieved algorithmic bandwidth (4*N*D + 4*N bytes per step) against the measured HBM peak.  Not a bench.py line."""
 import json, math, os, sys
@@ -23,7 +23,7 @@ for D in (128, 256, 384, 512):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
     for fam in ("bernoulli_logits", "gaussian_linear"):
         like = lk.BernoulliLogits() if fam == "bernoulli_logits" else lk.GaussianLinear()
-        model = bj.ADVI(prior, {"weights": tfb.Identity()}, like)
+        model = bj.ADVI(prior, {"weights": tfb.Identity()}, like, prepare_dataset=os.environ.get("ENV_RAW", "0") != "1")
         kw = {} if fam == "bernoulli_logits" else {"log_noise_scale": torch.tensor(math.log(0.1), device=dev)}
         eng, _ = model._engine_for(kw)
         y = y_logit if fam == "bernoulli_logits" else y_lin
