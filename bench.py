@@ -166,9 +166,9 @@ def run_reference(args):
 
 
 def launches_per_step(kernel: str) -> int:
-    # k_prologue + likelihood + k_reduce_partials + k_tail + k_scalars (mean field)
+    # k_prologue + likelihood + k_reduce_partials + k_tail + k_scalars (mean field); the tiny coin-toss step is one launch
     # (two-pass GEMM path: + operand split of theta, pass 1, pass 2 instead of one likelihood launch)
-    return {"tcgen05_bf16_split": 5, "fp32_smalld": 5, "fp32_tiled": 6, "coin": 4, "tcgen05_gemm_two_pass": 7}[kernel]
+    return {"tcgen05_bf16_split": 5, "fp32_smalld": 5, "fp32_tiled": 6, "coin": 1, "tcgen05_gemm_two_pass": 7}[kernel]
 
 
 def run_ours(args):
