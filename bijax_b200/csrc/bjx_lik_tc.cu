@@ -534,6 +534,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   tcp::BarsP* bars = (tcp::BarsP*)(sdl + BLK_BYTES);
   float* sred = (float*)(bars + 1);
   float* xch = (float*)(((uintptr_t)(sred + 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
+  constexpr int XCH_FLOATS = EW * VPT * 32;                                    // (two of them in ring mode, see the epilogue)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
@@ -796,6 +797,19 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     uint32_t flushed = 0;
     int64_t row = (int64_t)blockIdx.x * TILE_ROWS + r;
     float yv = (my_tiles > 0 && row < N) ? y[row] : 0.0f;
+    uint32_t va[SG], vb[SG];  // partial logits of one tile
+    auto load_logits = [&](int64_t t) {
+      mbar_wait(&bars->acc1_full[t & 1], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t acc1 = t_lane + ACC1_COL + ((t & 1) ? NB : 0);  // the logits accumulator of the tile's parity
+      if constexpr (SG == 16) {
+        tmem_ld16(acc1 + h * SG, va);
+        tmem_ld16(acc1 + NS + h * SG, vb);
+      } else {
+        tmem_ld8(acc1 + h * SG, va);
+        tmem_ld8(acc1 + NS + h * SG, vb);
+      }
+    };
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       if (it > 0 && phase % flush_step == 0 && phase / flush_step < NCH) {
@@ -812,31 +826,26 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       // fetch the next tile's label now: its latency hides behind this tile's GEMM1
       row += (int64_t)gridDim.x * TILE_ROWS;
       yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
-      mbar_wait(&bars->acc1_full[it & 1], (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
+      // (Loading the next tile's logits early, under this tile's link function, was tried in ring mode and lost 10 %: the
+      // wait for GEMM1(t+1) -- queued behind GEMM2(t-1) on the tensor pipe -- then sits in front of this tile's hand-over.)
+      load_logits(it);
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
-      uint32_t va[SG], vb[SG];
-      const uint32_t acc1 = t_lane + ACC1_COL + ((it & 1) ? NB : 0);  // the logits accumulator of this tile's parity
-      if constexpr (SG == 16) {
-        tmem_ld16(acc1 + h * SG, va);
-        tmem_ld16(acc1 + NS + h * SG, vb);
-      } else {
-        tmem_ld8(acc1 + h * SG, va);
-        tmem_ld8(acc1 + NS + h * SG, vb);
-      }
       tmem_ld_wait();
+      // ring mode: the exchange buffers alternate with the tile (nothing orders my write for tile t+1 after the partner's
+      // read for tile t any more, now that the next logits do not wait for this tile's hand-over)
+      const int xoff = RING ? (int)(it & 1) * XCH_FLOATS : 0;
       float eta[VPT], g[VPT];
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
         // samples [VPT * (1 - part), +VPT) of my SG go to the partner, [VPT * part, +VPT) stay
         const float lo = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
         const float up = __uint_as_float(va[VPT + j]) + __uint_as_float(vb[VPT + j]);
-        xch_peer[j * 32 + lane] = part ? lo : up;
+        xch_peer[xoff + j * 32 + lane] = part ? lo : up;
         eta[j] = part ? up : lo;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
 #pragma unroll
-      for (int j = 0; j < VPT; ++j) eta[j] += xch_mine[j * 32 + lane];
+      for (int j = 0; j < VPT; ++j) eta[j] += xch_mine[xoff + j * 32 + lane];
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
       // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
       // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
@@ -990,7 +999,8 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   if (a.x_planes != nullptr) {
     // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
     const int nslot = 8 / nblk > 1 ? 8 : nblk;  // D = 128, 256: the eight slots are a ring of tiles (see the kernel)
-    const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 + 8 * 256 * sizeof(float) + 1024;
+    const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 +
+                        (nslot > nblk ? 2 : 1) * 8 * 256 * sizeof(float) + 1024;
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");
