@@ -1023,11 +1023,15 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     k_lik_tc_tma<NBLK, EW><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S, \
                                                               a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace); \
   } while (0)
-    static int epi_warps = -1;  // BJX_TC_EPI_WARPS = 8 | 16
-    if (epi_warps < 0) {
+    // Epilogue warps: eight everywhere except D = 128 with the Bernoulli-logit link, where the tile is so short that the
+    // epilogue's latency chain is the bound and sixteen warps (four finished values per thread) hide more of it: 0.65 ->
+    // 0.75-0.77 of the roofline in an A/B on one box; the Gaussian link and D >= 256 do not gain.  BJX_TC_EPI_WARPS forces.
+    static int forced_ew = -1;
+    if (forced_ew < 0) {
       const char* e = getenv("BJX_TC_EPI_WARPS");
-      epi_warps = (e && atoi(e) == 16) ? 16 : 8;
+      forced_ew = e ? (atoi(e) == 16 ? 16 : 8) : 0;
     }
+    const int epi_warps = forced_ew ? forced_ew : ((nblk == 2 && a.likelihood == BJX_LIK_BERNOULLI_LOGITS) ? 16 : 8);
 #define BJX_TCP_LAUNCH_EW(NBLK)                 \
   do {                                          \
     if (epi_warps == 16) BJX_TCP_LAUNCH(NBLK, 16); \
