@@ -133,7 +133,8 @@ class ElboEngine:
             t = t.to(device=device, dtype=torch.float32)
         return t.contiguous()
 
-    def _data(self, X, y):
+    def _data(self, X, y, indexed: bool = False):
+        """Validated (X, y, N, row pitch).  ``indexed``: the rows are X[row_index[r]] -- X is the full dataset, y the batch."""
         y = self._f32(y, self.device).reshape(-1)
         N = y.numel()
         if self.lik_id == nv.LIK_BERNOULLI_PROBS:
@@ -144,21 +145,15 @@ class ElboEngine:
             X = X.to(device=self.device, dtype=torch.float32)
         if X.dim() == 2 and X.stride(1) != 1:
             X = X.contiguous()  # rows may be pitched (ldx > Dw, e.g. a column slice of a wider matrix), columns must be dense
-        indexed = self._row_index_for(X) is not None  # rows are X[row_index[r]]: X is the full dataset, y the batch
         if X.dim() != 2 or (X.shape[0] != N and not indexed) or X.shape[1] != self.Dw:
             raise ValueError(f"X must be [N={N}, D={self.Dw}] (rows = data, row-major); got {tuple(X.shape)}")
         return X, y, N, X.stride(0)
 
-    def bind_row_index(self, X: Optional[torch.Tensor], index: Optional[torch.Tensor]) -> None:
-        """Steps on the tensor ``X`` read it through ``index`` (int32 [B], BjxElboArgs.row_index) with ``y`` of length B --
-        the minibatch sampler's copy-free path; (None, None) removes the binding."""
-        self._bound_index = None if X is None or index is None else (X.data_ptr(), index)
-
-    def _row_index_for(self, X) -> Optional[int]:
-        bound = getattr(self, "_bound_index", None)
-        if bound is not None and X is not None and X.data_ptr() == bound[0]:
-            return bound[1].data_ptr()
-        return None
+    @staticmethod
+    def _check_row_index(row_index: torch.Tensor, N: int) -> int:
+        if not (row_index.is_cuda and row_index.dtype == torch.int32 and row_index.is_contiguous() and row_index.numel() == N):
+            raise ValueError(f"row_index must be a contiguous CUDA int32 tensor with one entry per row of the batch ({N})")
+        return row_index.data_ptr()
 
     def supports_row_index(self, S, N) -> bool:
         if self.Dw < 1:
@@ -173,20 +168,12 @@ class ElboEngine:
         a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
         return self.lib.bjx_elbo_kernel_choice(C.byref(a)) in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"])
 
-    def bind_planes(self, X: Optional[torch.Tensor], planes: Optional[torch.Tensor]) -> None:
-        """The caller maintains the operand planes of the tensor ``X`` itself (the minibatch sampler gathers plane rows
-        straight into ``planes``); (None, None) removes the binding."""
-        self._bound_planes = None if X is None or planes is None else (X.data_ptr(), planes)
-
     def _x_planes(self, a: nv.BjxElboArgs, X: torch.Tensor) -> Optional[int]:
         """Device pointer of the prepared operand planes of X if this step takes the GEMM path, else None."""
-        if not self.prepare_dataset or X is None or self._row_index_for(X) is not None:
+        if not self.prepare_dataset or X is None:
             return None
         if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
             return None
-        bound = getattr(self, "_bound_planes", None)
-        if bound is not None and bound[0] == X.data_ptr():
-            return bound[1].data_ptr()
         key = (X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()))
         if self._planes_misses > 2 and key == self._last_raw_key:
             self._planes_misses = 0  # the same tensor came back: it is a dataset after all
@@ -227,18 +214,21 @@ class ElboEngine:
         return nv.KERNEL_NAMES[nv.check(self.lib.bjx_elbo_kernel_choice(C.byref(a)))]
 
     def step(self, key, loc, raw_scale, kwargs_vec, X, y, ll_scale, n_samples, prior_weight=1.0, out=None, eps_out=None,
-             partitionable=None, sample_shard=None) -> torch.Tensor:
+             partitionable=None, sample_shard=None, row_index=None, planes=None) -> torch.Tensor:
         """Enqueue one ELBO+grad step; returns the packed device tensor [loss | d loc | d raw_scale | d kwargs].
         ``sample_shard = (s_offset, S_total, entropy_weight)`` evaluates samples [s_offset, s_offset + n_samples) of a
         step with S_total samples (shard the Monte-Carlo samples when N is small); the packed
-        outputs of all shards sum to the unsharded step."""
+        outputs of all shards sum to the unsharded step.
+        ``row_index`` (int32 [len(y)]): row r of the batch is X[row_index[r]] -- X is the full dataset, read through the
+        index (BjxElboArgs.row_index; only where ``supports_row_index``).  ``planes``: operand planes of X maintained by
+        the caller (the minibatch sampler gathers plane rows itself) instead of the engine's own cache."""
         dev = self.device
         key = brandom._check_key(key)
         loc = self._f32(loc, dev).reshape(-1)
         raw = self._f32(raw_scale, dev).reshape(-1)
         if loc.numel() != self.D or raw.numel() != self.P:
             raise ValueError(f"loc must have {self.D} and raw scale {self.P} elements")
-        X, y, N, ldx = self._data(X, y)
+        X, y, N, ldx = self._data(X, y, indexed=row_index is not None)
         a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
         a.key, a.loc, a.raw_scale = key.data_ptr(), loc.data_ptr(), raw.data_ptr()
         kw = None
@@ -249,7 +239,8 @@ class ElboEngine:
             a.kwargs = kw.data_ptr()
         a.X = X.data_ptr() if X is not None else None
         a.y = y.data_ptr()
-        a.row_index = self._row_index_for(X)
+        if row_index is not None:
+            a.row_index = self._check_row_index(row_index, N)
         if out is None:
             out = torch.empty(1 + self.D + self.P + self.K, dtype=torch.float32, device=dev)
         a.out = out.data_ptr()
@@ -257,7 +248,8 @@ class ElboEngine:
             a.eps_out = eps_out.data_ptr()
         if sample_shard is not None:
             a.s_offset, a.S_total, a.entropy_weight = int(sample_shard[0]), int(sample_shard[1]), float(sample_shard[2])
-        a.x_planes = self._x_planes(a, X)
+        if row_index is None:
+            a.x_planes = planes.data_ptr() if planes is not None else self._x_planes(a, X)
         ws = self._workspace(a)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(dev):
@@ -337,23 +329,15 @@ class ElboEngine:
             nv.check(self.lib.bjx_posterior_log_prob(C.byref(a), theta.data_ptr(), theta.shape[0], out.data_ptr(), nv.current_stream_ptr()))
         return out
 
-    def train_steps(self, *args, minibatch=None, **kwargs):
-        """See _train_steps; ``minibatch`` is the state of a MinibatchLoss (its batch buffers and BjxMinibatch)."""
-        indexed = minibatch is not None and minibatch["indexed"]
-        if indexed:
-            self.bind_row_index(minibatch["X"], minibatch["idx"])
-        try:
-            return self._train_steps(*args, minibatch=minibatch, **kwargs)
-        finally:
-            if indexed:
-                self.bind_row_index(None, None)
-
-    def _train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
-                     n_samples, partitionable=None, minibatch=None):
+    def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
+                    n_samples, partitionable=None, minibatch=None):
         """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip
         (bjx_train_steps; train_fn's scan body, utils.py:22-28).  ``keys`` is the [n, 2] uint32 array of per-step keys,
-        ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place."""
-        X, y, N, ldx = self._data(X, y)
+        ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place.
+        ``minibatch``: the state of a MinibatchLoss (batch buffers + BjxMinibatch) -- every step first draws a fresh batch
+        (bjx_train_steps_minibatch); X / y are then its batch buffers, or the full X read through its index."""
+        indexed = minibatch is not None and minibatch["indexed"]
+        X, y, N, ldx = self._data(X, y, indexed=indexed)
         a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, 1.0, brandom._layout(partitionable))
         assert keys.dtype == torch.uint32 and keys.is_cuda and keys.is_contiguous()
         assert params_flat.numel() == self.D + self.P + self.K and params_flat.is_contiguous()
@@ -361,9 +345,10 @@ class ElboEngine:
         a.X = X.data_ptr() if X is not None else None
         a.y = y.data_ptr()
         a.out = out.data_ptr()
-        a.row_index = self._row_index_for(X)
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
-        if minibatch is not None:  # X / y are the sampler's batch buffers; it fills the planes itself (bjx_minibatch_gather)
+        if indexed:
+            a.row_index = self._check_row_index(minibatch["idx"], N)
+        elif minibatch is not None:  # the sampler fills the batch's planes itself (bjx_minibatch_gather)
             a.x_planes = minibatch["planes_b"].data_ptr() if minibatch["planes_b"] is not None else None
         else:
             a.x_planes = self._x_planes(a, X)

@@ -39,6 +39,8 @@ class MinibatchLoss:
         self.N = len(outputs)
         if self.B < 1 or self.N < 1:
             raise ValueError("need batch_size >= 1 and a non-empty dataset")
+        if getattr(model, "_group", None) is not None:
+            raise NotImplementedError("MinibatchLoss draws from one device's dataset; it does not combine with model.distributed()")
         self.full_data_size = float(self.N if full_data_size is None else full_data_size)
         # True: the step reads the dataset through the row index whenever its kernel can (BjxElboArgs.row_index); False:
         # always gather the batch into its own buffers; None: by batch size -- measured on B200 at D = 512 (profiles/
@@ -103,17 +105,19 @@ class MinibatchLoss:
 
     def __call__(self, params, seed):
         """The loss of the docstring's ``loss(params, seed)``; differentiable like ``model.loss_fn``."""
-        st = self._setup(self._engine(params))
+        from .advi import _ElboFunction
+
+        model = self.model
+        loc, raw, kwargs = model._split_params(params)
+        engine, kw_leaves = model._engine_for(kwargs)
+        kw = torch.cat([l.reshape(-1).to(torch.float32) for l in kw_leaves]) if kw_leaves else None
+        st = self._setup(engine)
         self.sample(params, seed)
-        engine = st["engine"]
-        inputs = None
+        ll_scale = self.full_data_size / float(self.B)  # advi.py:92
         Xin = st["X"] if st["indexed"] else st["Xb"]
-        if Xin is not None:
-            inputs = {engine.x_name: Xin} if isinstance(self.inputs, dict) else Xin
-        engine.bind_planes(st["Xb"], st["planes_b"])
-        engine.bind_row_index(st["X"] if st["indexed"] else None, st["idx"])
-        try:
-            return self.model.loss_fn(params, st["yb"], inputs, self.full_data_size, st["elbo_key"], self.S)
-        finally:
-            engine.bind_planes(None, None)
-            engine.bind_row_index(None, None)
+
+        def run(loc_, raw_, kw_):
+            return engine.step(st["elbo_key"], loc_, raw_, kw_, Xin, st["yb"], ll_scale, self.S,
+                               row_index=st["idx"] if st["indexed"] else None, planes=st["planes_b"])
+
+        return _ElboFunction.apply(loc, raw, kw, run)

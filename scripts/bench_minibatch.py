@@ -43,12 +43,9 @@ for B, copy_free in [(b, cf) for b in (4096, 65536, 524288) for cf in (True, Fal
     eng = st["engine"]
     loc, raw = params["posterior"]["loc"], params["posterior"]["scale_diag"]
     o = torch.empty(1 + 2 * D, device=dev)
-    eng.bind_planes(st["Xb"], st["planes_b"])
-    eng.bind_row_index(st["X"] if st["indexed"] else None, st["idx"])
     Xin = st["X"] if st["indexed"] else st["Xb"]
-    us_step = ev_time(lambda i: eng.step(keys[i], loc, raw, None, Xin, st["yb"], N / B, S, out=o), 200)
-    eng.bind_planes(None, None)
-    eng.bind_row_index(None, None)
+    us_step = ev_time(lambda i: eng.step(keys[i], loc, raw, None, Xin, st["yb"], N / B, S, out=o,
+                                         row_index=st["idx"] if st["indexed"] else None, planes=st["planes_b"]), 200)
     n = 40 * 16
     def fresh():
         return model.init(br.PRNGKey(0), initializer=lambda k, s: 0.01 * br.normal(k, s))

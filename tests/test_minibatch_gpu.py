@@ -208,11 +208,7 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
     raw = torch.full((D,), -2.0, device=dev)
     key = br.PRNGKey(4)
     want = eng.step(key, loc, raw, None, Xd[li].contiguous(), yd[li].contiguous(), N / B, S).clone()
-    eng.bind_row_index(Xd, idx)
-    try:
-        got = eng.step(key, loc, raw, None, Xd, yd[li].contiguous(), N / B, S).clone()
-    finally:
-        eng.bind_row_index(None, None)
+    got = eng.step(key, loc, raw, None, Xd, yd[li].contiguous(), N / B, S, row_index=idx).clone()
     assert torch.equal(got, want)
     # a shape the fused kernel does not take
     small = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(5, np.float32), scale_diag=np.ones(5, np.float32))},
@@ -220,12 +216,10 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
     e2, _ = small._engine_for({})
     assert not e2.supports_row_index(S, B)
     X5 = torch.zeros((N, 5), device=dev)
-    e2.bind_row_index(X5, idx)
-    try:
-        with pytest.raises(nv.BjxError):
-            e2.step(key, torch.zeros(5, device=dev), torch.zeros(5, device=dev), None, X5, yd[li].contiguous(), 1.0, S)
-    finally:
-        e2.bind_row_index(None, None)
+    with pytest.raises(nv.BjxError):
+        e2.step(key, torch.zeros(5, device=dev), torch.zeros(5, device=dev), None, X5, yd[li].contiguous(), 1.0, S, row_index=idx)
+    with pytest.raises(ValueError):  # one index per batch row
+        eng.step(key, loc, raw, None, Xd, yd[li].contiguous(), N / B, S, row_index=idx[:-1].contiguous() if B > 1 else idx.long())
 
 
 
