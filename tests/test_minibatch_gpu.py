@@ -246,3 +246,14 @@ def test_minibatch_on_the_two_pass_gemm_path():
     C.assert_close(got.item(), want.item(), rtol=2e-6, atol_scale=2e-6, what="loss")
     for k in ("loc", "scale_diag"):
         C.assert_close(g_got["posterior"][k].cpu().numpy(), g_want["posterior"][k].cpu().numpy(), rtol=2e-6, atol_scale=2e-6, what=k)
+
+
+def test_randint_against_the_committed_vectors():
+    """tests/golden/randint_vectors.json: the CUDA sampler against the committed index draws (both layouts)."""
+    import json
+    from pathlib import Path
+
+    fx = json.loads((Path(__file__).parent / "golden" / "randint_vectors.json").read_text())
+    for c in fx["cases"]:
+        got = br.randint(br.PRNGKey(c["seed"]), (c["n"],), c["minval"], c["maxval"], partitionable=bool(c["layout"]))
+        assert got.cpu().tolist() == c["values"], c

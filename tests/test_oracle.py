@@ -254,3 +254,13 @@ def test_randint_restatement_properties(layout):
     assert got.dtype == np.int32 and got.min() >= -3 and got.max() <= 3 and len(set(got.tolist())) == 7
     assert np.array_equal(got, tf.randint(key, n, -3, 4, layout))
 
+
+
+def test_randint_regression_vectors():
+    """tests/golden/randint_vectors.json (scripts/make_randint_fixture.py): the index draws the oracle and the CUDA sampler
+    agreed on when the fixture was committed -- a change of either shows up here (CPU) or in tests/test_minibatch_gpu.py."""
+    fx = json.loads((Path(__file__).parent / "golden" / "randint_vectors.json").read_text())
+    assert len(fx["cases"]) == 14
+    for c in fx["cases"]:
+        got = tf.randint(tf.prng_key(c["seed"]), c["n"], c["minval"], c["maxval"], c["layout"])
+        assert [int(v) for v in got] == c["values"], c
