@@ -105,6 +105,10 @@ class ADVI:
                 vi_type = args.pop(0)
             if args:
                 raise TypeError("too many positional arguments")
+        # which params key init() returns: the v2 signature is the reference's current source (advi.py:78,
+        # {"approx_posterior": ...}); the v1 signature is the README / notebook surface (params["posterior"])
+        self._posterior_key = "approx_posterior" if (bijector is None and log_likelihood_fn is None and
+                                                      (likelihood_fn is not None or prior_constraints is not None)) else "posterior"
         constraints = bijector if bijector is not None else prior_constraints
         if constraints is None:
             constraints = {}
@@ -158,18 +162,20 @@ class ADVI:
 
     # ------------------------------------------------------------------------------------------------------------------
     def init(self, seed, initializer: Optional[Callable] = None):
-        """advi.py:77-78: raw params = initializer(seed, (P,)), default normal(stddev=1), unraveled in (loc, scale) order."""
+        """advi.py:77-78: raw params = initializer(seed, (P,)), default normal(stddev=1), unraveled in (loc, scale) order.
+        The top-level key is the reference's "approx_posterior" (advi.py:78) for the v2 constructor form and "posterior" for
+        the v1 (README / notebook) form; loss_fn / apply / train accept either."""
         D = self.size
         if self.vi_type == "low_rank":
             # leaves in constructor-argument order: loc [D], scale_diag [D], scale_perturb_factor [D, rank]  (utils.py:53-55)
             r = int(self.rank)
             flat = brandom.normal(seed, (2 * D + D * r,)) if initializer is None else initializer(seed, (2 * D + D * r,))
-            return {"posterior": {"loc": flat[:D].clone(), "scale_diag": flat[D : 2 * D].clone(),
+            return {self._posterior_key: {"loc": flat[:D].clone(), "scale_diag": flat[D : 2 * D].clone(),
                                   "scale_perturb_factor": flat[2 * D :].reshape(D, r).clone()}}
         P = D if self.vi_type == "mean_field" else (D * (D + 1) // 2 if self.packed_tril else D * D)
         flat = brandom.normal(seed, (D + P,)) if initializer is None else initializer(seed, (D + P,))
         scale = flat[D:].reshape((P,) if (self.vi_type == "mean_field" or self.packed_tril) else (D, D))
-        return {"posterior": {"loc": flat[:D].clone(), _scale_key(self.vi_type): scale.clone()}}
+        return {self._posterior_key: {"loc": flat[:D].clone(), _scale_key(self.vi_type): scale.clone()}}
 
     # ------------------------------------------------------------------------------------------------------------------
     def _split_params(self, params):

@@ -61,8 +61,9 @@ class ElboEngine:
         self.prepare_dataset = prepare_dataset
         self._planes: Optional[torch.Tensor] = None
         self._planes_key = None
+        self._planes_storage = None  # strong reference to the storage of the tensor the planes were made from
         self._planes_misses = 0
-        self._last_raw_key = None
+        self._last_raw = None
         self._point_key: Optional[torch.Tensor] = None
         self._resolve_likelihood()
 
@@ -130,6 +131,8 @@ class ElboEngine:
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
         if t.device != device or t.dtype != torch.float32:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("inputs must be CUDA float32 on the engine's device before CUDA-graph capture")
             t = t.to(device=device, dtype=torch.float32)
         return t.contiguous()
 
@@ -142,6 +145,8 @@ class ElboEngine:
         if not isinstance(X, torch.Tensor):
             X = torch.as_tensor(X)
         if X.device != self.device or X.dtype != torch.float32:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("X must be CUDA float32 on the engine's device before CUDA-graph capture")
             X = X.to(device=self.device, dtype=torch.float32)
         if X.dim() == 2 and X.stride(1) != 1:
             X = X.contiguous()  # rows may be pitched (ldx > Dw, e.g. a column slice of a wider matrix), columns must be dense
@@ -174,33 +179,52 @@ class ElboEngine:
             return None
         if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
             return None
-        key = (X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()))
-        if self._planes_misses > 2 and key == self._last_raw_key:
+        # identity of the dataset the planes were made from: the engine HOLDS the tensor's storage, so the allocator cannot
+        # hand the same address to another tensor while the planes live (a caller that passes y[idx], X[idx] temporaries,
+        # the reference's minibatch pattern, would otherwise hit the cache with a recycled address and version 0); views
+        # of one storage (X, X[:n]) share its version counter and compare by offset / shape / strides
+        storage = X.untyped_storage()
+        key = (storage._cdata, X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()))
+        if self._planes_misses > 2 and self._last_raw is not None and key == self._last_raw[1]:
             self._planes_misses = 0  # the same tensor came back: it is a dataset after all
         if self._planes_key != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("dataset planes must be prepared before CUDA-graph capture (engine.prepare)")
             # a caller that passes a fresh minibatch every step (advi.py:92 scaling) would pay a preparation per step:
             # after two consecutive misses the engine stays on the kernels that read raw fp32 X until a tensor repeats
             self._planes_misses += 1
             if self._planes_misses > 2:
-                self._planes, self._planes_key = None, None
-                self._last_raw_key = key
+                self._planes, self._planes_key, self._planes_storage = None, None, None
+                self._last_raw = (storage, key)  # held, so that "the same tensor came back" cannot be a recycled address
                 return None
-            self._planes = None  # release the old planes before allocating new ones
+            self._planes, self._planes_storage = None, None  # release the old planes before allocating new ones
             n = int(self.lib.bjx_x_planes_bytes(int(a.N), int(a.Dw)))
             try:
                 self._planes = torch.empty(n, dtype=torch.uint8, device=self.device)
             except torch.cuda.OutOfMemoryError:
-                # no room for a second copy of the dataset: stay on the kernels that read raw fp32 X
+                # no room for a second copy of the dataset: stay on the kernels that read raw fp32 X -- a slower path
+                # (DESIGN.md section 3.1), so say so instead of flipping silently
+                import warnings
+
+                warnings.warn(f"bijax_b200: no room for the {n / 1e9:.1f} GB of prepared operand planes of X; this engine now "
+                              "reads raw fp32 X every step (register-converting kernel, about 0.6 of the HBM roofline "
+                              "instead of 0.8-0.9).  Free memory or pass prepare_dataset=False to silence this.",
+                              RuntimeWarning, stacklevel=3)
                 self.prepare_dataset = False
-                self._planes, self._planes_key = None, None
+                self._planes, self._planes_key, self._planes_storage = None, None, None
                 return None
             with torch.cuda.device(self.device):
                 nv.check(self.lib.bjx_prepare_x_planes(X.data_ptr(), int(a.N), int(a.Dw), int(a.ldx), self._planes.data_ptr(),
                                                        nv.current_stream_ptr()))
-            self._planes_key = key
+            self._planes_key, self._planes_storage = key, storage
+            self._last_raw = None
         else:
             self._planes_misses = 0
         return self._planes.data_ptr()
+
+    def release_planes(self) -> None:
+        """Drop the prepared operand planes (and the hold on their source tensor's storage)."""
+        self._planes, self._planes_key, self._planes_storage, self._last_raw = None, None, None, None
 
     def prepare(self, X, y, n_samples) -> bool:
         """Prepare the dataset's operand planes now (otherwise the first step does it).  Returns True if this engine keeps

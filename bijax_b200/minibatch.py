@@ -101,6 +101,9 @@ class MinibatchLoss:
         seed = brandom._check_key(seed)
         with torch.cuda.device(st["engine"].device):
             nv.check(st["engine"].lib.bjx_minibatch_gather(C.byref(st["mb"]), seed.data_ptr(), None, brandom._layout(None), nv.current_stream_ptr()))
+        for t in (st["idx"], st["yb"], st["Xb"], st["elbo_key"]):
+            if t is not None:  # written by a raw kernel: tell torch (and the engine's planes cache) that the contents changed
+                torch.autograd.graph.increment_version(t)
         return st["idx"], st["yb"], st["Xb"], st["elbo_key"]
 
     def __call__(self, params, seed):

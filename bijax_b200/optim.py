@@ -44,32 +44,34 @@ class AdamState(NamedTuple):
     nu: Any
 
 
-def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> GradientTransformation:
-    """optax.adam (eps outside the square root, bias correction on both moments)."""
+def adam(learning_rate, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> GradientTransformation:
+    """optax.adam (eps outside the square root, bias correction on both moments).  ``learning_rate`` may be an
+    optax-style schedule ``count -> lr`` (evaluated on the host at the 0-based step count, like optax's
+    ``scale_by_learning_rate``); a schedule keeps train_fn on its host-driven loop."""
+    schedule = learning_rate if callable(learning_rate) else None
 
     def init(params):
         return AdamState(0, tree_map(torch.zeros_like, params), tree_map(torch.zeros_like, params))
 
     def update(grads, state, params=None):
         count = state.count + 1
+        lr = float(schedule(state.count)) if schedule is not None else float(learning_rate)
         g_leaves, td = tree_flatten(grads)
         m_leaves, _ = tree_flatten(state.mu)
         v_leaves, _ = tree_flatten(state.nu)
         lib = nv.load()
         ups = []
         for g, m, v in zip(g_leaves, m_leaves, v_leaves):
+            if not (g.is_cuda and g.dtype == torch.float32):
+                raise TypeError("optim.adam updates CUDA float32 leaves on the device (bjx_adam_update); there is no CPU path")
             g = g.contiguous()
-            if g.is_cuda and g.dtype == torch.float32:
-                # the kernel applies p -= step in place; run it on a zero buffer to obtain the additive update
-                u = torch.zeros_like(g)
-                with torch.cuda.device(g.device):
-                    nv.check(lib.bjx_adam_update(u.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), g.numel(), count,
-                                                 learning_rate, b1, b2, eps, nv.current_stream_ptr()))
-            else:
-                m.mul_(b1).add_(g, alpha=1 - b1)
-                v.mul_(b2).addcmul_(g, g, value=1 - b2)
-                u = -learning_rate * (m / (1 - b1**count)) / (torch.sqrt(v / (1 - b2**count)) + eps)
+            # the kernel applies p -= step in place; run it on a zero buffer to obtain the additive update
+            u = torch.zeros_like(g)
+            with torch.cuda.device(g.device):
+                nv.check(lib.bjx_adam_update(u.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), g.numel(), count,
+                                             lr, b1, b2, eps, nv.current_stream_ptr()))
             ups.append(u)
         return tree_unflatten(td, ups), AdamState(count, state.mu, state.nu)
 
-    return AdamTransformation(init, update, (float(learning_rate), float(b1), float(b2), float(eps)))
+    hyper = None if schedule is not None else (float(learning_rate), float(b1), float(b2), float(eps))
+    return AdamTransformation(init, update, hyper)

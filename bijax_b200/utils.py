@@ -78,6 +78,11 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
             X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
     ll_scale = float(kw["full_data_size"]) / float(len(outputs))  # advi.py:92
     S = int(kw.get("n_samples", 1))
+    if mb_state is None:
+        # normalise the dataset ONCE (device, fp32, dense columns): the warm-up step, the captured steps and the trailing
+        # eager steps must all see the same persistent tensors -- a conversion inside capture would allocate from the
+        # graph's private pool, miss the planes cache and re-split the dataset on every replay
+        X, outputs, _, _ = engine._data(X, outputs)
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
     done = torch.zeros(1, dtype=torch.int64, device=dev)
     losses = torch.empty(max(n_epochs, 1), dtype=torch.float32, device=dev)
@@ -140,7 +145,7 @@ def train_fn(loss_fn, params, optimizer, n_epochs, seed=None, return_args: Set[s
         if isinstance(post, dict):
             return _train_fused(spec[0], spec[1], params, optimizer, n_epochs, seed)
     value_and_grad_fn = value_and_grad(loss_fn)
-    state = optimizer.init(params)
+    state = state0 = optimizer.init(params)
     seeds = brandom.split(seed, n_epochs) if seed is not None else None
     losses = []
     params_list = [] if "params_list" in return_args else None
@@ -157,7 +162,11 @@ def train_fn(loss_fn, params, optimizer, n_epochs, seed=None, return_args: Set[s
     losses = torch.stack(losses) if losses else torch.zeros(0)
     states = state
     return_dict = {"params": params, "losses": losses}
-    local = {"params_list": params_list, "states": states, "seeds": seeds}
+    # the reference hands back any of its locals by name (utils.py:33-35, ``locals()[key]``): ``state`` is the optimiser
+    # state BEFORE the scan, ``states`` the one after it
+    local = {"params_list": params_list, "states": states, "seeds": seeds, "state": state0, "losses": losses, "params": params,
+             "loss_fn": loss_fn, "optimizer": optimizer, "n_epochs": n_epochs, "seed": seed, "return_args": return_args,
+             "value_and_grad_fn": value_and_grad_fn}
     for key in return_args:
         return_dict[key] = local[key]
     return return_dict

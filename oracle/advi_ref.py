@@ -357,6 +357,71 @@ class ADVIRef:
         p = sum(self.prior[k].log_prob(theta[k]).sum() + self.bijector[k].fldj(tree[k]).sum() for k in self.names)
         return p + self.log_likelihood_fn(theta, outputs, inputs)
 
+    def value_and_grad_chunked(self, loc, raw_scale, kwargs, outputs, X, full_data_size, eps, chunk_rows=1 << 18,
+                               n_total=None):
+        """``value_and_grad`` for problems too large for one autograd graph (BASELINE.json's full sizes: c3 10M rows, a c5
+        shard of 12.5M rows, c4 at D=2048 / S=256 / N=1M).  Same formulas as ``loss`` (advi.py:80-95), float64 throughout:
+
+          * sampling, q.log_prob and the unconstrained-prior terms are evaluated for all S samples at once (the ``vmap`` of
+            advi.py:95) -- they are O(S*D) / O(S*D^2);
+          * the log-likelihood (advi.py:90-91) is the user's ``log_likelihood_fn`` itself, called on row blocks of
+            (outputs, X) with the S constrained samples stacked on a trailing axis; because the loss is linear in the
+            per-sample log-likelihoods, only sum_s ll_s and its cotangents are accumulated over the blocks;
+          * the chain rule back to (loc, raw_scale, kwargs) goes through one autograd pass of the small graph.
+
+        It runs wherever ``outputs`` / ``X`` live (``outputs.device``): the -m gpu tests keep the float32 dataset on the
+        GPU and let torch do the float64 arithmetic there -- torch is the CHECKER's calculator here, not the product.
+        ``n_total``: the global ``len(outputs)`` when (outputs, X) is one row shard of a larger dataset.
+        Returns loss, dloc, draw_scale, {dkwargs} like ``value_and_grad``."""
+        dev = outputs.device
+        f64 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float64)
+        loc = f64(loc).clone().requires_grad_(True)
+        raw_scale = f64(raw_scale).clone().requires_grad_(True)
+        kw = {k: f64(v).clone().requires_grad_(True) for k, v in kwargs.items()}
+        eps = f64(eps)
+        S, D = eps.shape[0], self.size
+        if self.vi_type == "mean_field":
+            sigma = self.scale_bijector.forward(raw_scale)
+            samples = loc + sigma * eps
+            zz = (samples - loc) / sigma
+            q = (-0.5 * zz * zz - torch.log(sigma)).sum(-1) - 0.5 * D * LOG_2PI
+        else:
+            tril = torch.tril(self.scale_bijector.forward(raw_scale))
+            samples = loc + eps @ tril.T
+            zz = torch.linalg.solve_triangular(tril, (samples - loc).T, upper=False)  # [D, S]
+            q = -0.5 * (zz * zz).sum(0) - torch.log(torch.abs(torch.diagonal(tril))).sum() - 0.5 * D * LOG_2PI
+        p = torch.zeros(S, dtype=torch.float64, device=dev)
+        theta, o = {}, 0
+        for k in self.names:
+            n = self.sizes[k]
+            zk = samples[:, o : o + n].reshape((S,) + tuple(self.shapes[k]))
+            o += n
+            b = self.bijector[k]
+            th = b.forward(zk)
+            p = p + self.prior[k].log_prob(th).reshape(S, -1).sum(-1) + b.fldj(zk).reshape(S, -1).sum(-1)
+            theta[k] = th.movedim(0, -1)  # sample axis last: X @ theta[weights] is [rows, S]
+        th_leaf = {k: v.detach().clone().requires_grad_(True) for k, v in theta.items()}
+        kw_leaf = {k: v.detach().clone().requires_grad_(True) for k, v in kw.items()}
+        leaves = list(th_leaf.values()) + list(kw_leaf.values())
+        acc = [torch.zeros_like(l) for l in leaves]
+        ll_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        N = outputs.shape[0]
+        for i in range(0, N, int(chunk_rows)):
+            yc = outputs[i : i + chunk_rows].to(torch.float64)[:, None]
+            inputs = {"X": X[i : i + chunk_rows].to(torch.float64)} if X is not None else None
+            ll = self.log_likelihood_fn(th_leaf, yc, inputs, **kw_leaf)  # sum over the block's rows AND the S samples
+            gs = torch.autograd.grad(ll, leaves, allow_unused=True)
+            for a, g in zip(acc, gs):
+                if g is not None:
+                    a += g
+            ll_sum += ll.detach()
+        c = float(full_data_size) / float(n_total if n_total is not None else N)  # advi.py:92
+        loss = (q - p).mean() - (c / S) * ll_sum
+        surrogate = (q - p).mean() - (c / S) * sum((a * v).sum() for a, v in zip(acc, list(theta.values()) + list(kw.values())))
+        grads = torch.autograd.grad(surrogate, [loc, raw_scale] + list(kw.values()), allow_unused=True)
+        gk = {k: (g if g is not None else torch.zeros_like(v)) for (k, v), g in zip(kw.items(), grads[2:])}
+        return loss.detach(), grads[0], grads[1], gk
+
     def value_and_grad(self, loc, raw_scale, kwargs, outputs, inputs, full_data_size, eps):
         """jax.value_and_grad(loss_fn) (utils.py:7): returns loss, dloc, draw_scale, {dkwargs}."""
         loc = loc.detach().clone().requires_grad_(True)

@@ -113,13 +113,14 @@ def oracle_step(ref, loc, raw, kwargs, y, X, full_data_size, key_np, S, layout):
 
 
 def assert_close(got, want, rtol=1e-5, atol_scale=1e-5, what=""):
-    """rtol 1e-5 as north_star states; entries that are tiny relative to the largest one get an absolute floor."""
+    """rtol 1e-5 as north_star states: ``tol = max(rtol*|want|, atol_scale*max|want|)`` -- entries that are tiny relative to
+    the largest one of their block get the block's absolute floor, the large ones exactly rtol."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert np.isfinite(want).all(), f"{what}: oracle value is not finite"
     assert np.isfinite(got).all(), f"{what}: result is not finite: {got}"
     scale = max(float(np.max(np.abs(want))), 1e-30)
     err = np.abs(got - want)
-    tol = rtol * np.abs(want) + atol_scale * scale
+    tol = np.maximum(rtol * np.abs(want), atol_scale * scale)
     bad = err > tol
     assert not bad.any(), f"{what}: max err {err.max():.3e} (rel-to-max {err.max() / scale:.3e}) at {np.argmax(err)}; want {want.ravel()[np.argmax(err)]:.6e} got {got.ravel()[np.argmax(err)]:.6e}"

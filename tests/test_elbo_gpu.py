@@ -541,6 +541,49 @@ def test_packed_fill_triangular_parameterisation():
     assert torch.equal(q["posterior"]["scale_tril"].grad, gp["posterior"]["scale_tril"])
 
 
+def test_reference_style_minibatch_temporaries_never_reuse_stale_planes():
+    """The reference's minibatch pattern ``loss_fn(params, y[idx], X[idx], N, seed)`` frees X[idx] after every call, and the
+    caching allocator hands the next X[idx] the same address (version 0, same shape): the prepared-planes cache must not
+    take that for the previous batch.  Every step against an engine that never prepares planes and against the float64
+    oracle; also a buffer rewritten in place by a raw kernel after ``increment_version``."""
+    from bijax_b200 import random as br
+
+    N, B, D, S = 8192, 1024, 128, 16
+    X, y = _device_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.BernoulliLogits())
+    raw_model, _ = C.build_pair(prior, {}, lk.BernoulliLogits(), prepare_dataset=False)
+    eng = model._engine_for({})[0]
+    assert eng.kernel_choice(S, B) == "tcgen05_bf16_split"
+    loc = 0.05 * br.normal(br.PRNGKey(5), (D,), partitionable=True)
+    rawp = torch.full((D,), -2.0, device=X.device)
+    params = {"posterior": {"loc": loc, "scale_diag": rawp}}
+    addresses = set()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for i in range(5):
+        idx = torch.randint(0, N, (B,), device="cuda", generator=g)
+        xb = X[idx]
+        addresses.add(xb.data_ptr())
+        got, grads = model.value_and_grad(params, y[idx], {"X": xb}, N, br.PRNGKey(i), S)
+        want, wgrads = raw_model.value_and_grad(params, y[idx], {"X": X[idx]}, N, br.PRNGKey(i), S)
+        C.assert_close(got.item(), want.item(), rtol=2e-6, atol_scale=2e-6, what=f"loss of batch {i}")
+        C.assert_close(grads["posterior"]["loc"].cpu().numpy(), wgrads["posterior"]["loc"].cpu().numpy(), rtol=1e-5, what=f"d loc of batch {i}")
+        (wl, wgl, _, _), _ = C.oracle_step(ref, loc.cpu().numpy(), rawp.cpu().numpy(), {}, y[idx].cpu().numpy(), xb.cpu().numpy(), N,
+                                           tf.prng_key(i), S, 0)
+        C.assert_close(got.item(), wl.item(), what=f"loss of batch {i} vs oracle")
+        C.assert_close(grads["posterior"]["loc"].cpu().numpy(), wgl.numpy(), what=f"d loc of batch {i} vs oracle")
+        del xb
+    # one persistent batch buffer rewritten in place (what a sampler's own buffers are): the version counter is the signal
+    buf, ybuf = X[:B].clone(), y[:B].clone()
+    for i in range(3):
+        idx = torch.randint(0, N, (B,), device="cuda", generator=g)
+        buf.copy_(X[idx])
+        ybuf.copy_(y[idx])
+        got, _ = model.value_and_grad(params, ybuf, {"X": buf}, N, br.PRNGKey(i), S)
+        want, _ = raw_model.value_and_grad(params, ybuf, {"X": buf}, N, br.PRNGKey(i), S)
+        C.assert_close(got.item(), want.item(), rtol=2e-6, atol_scale=2e-6, what=f"in-place batch {i}")
+
+
 def test_fresh_minibatches_fall_back_to_raw_fp32_and_a_repeated_dataset_is_prepared_again():
     """advi.py:92 scales a minibatch to the full data size; a caller passing a NEW tensor every step must not pay a dataset
     preparation per step: after two consecutive cache misses the engine reads raw fp32 X, and prepares again once a tensor

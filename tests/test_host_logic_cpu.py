@@ -82,3 +82,24 @@ def test_value_and_grad_and_pytree_helpers():
     assert back["z"].tolist() == [2.0, 4.0] and back["a"]["k"].shape == ()
     doubled = tree_map(lambda a, b: a + b, params, params)
     assert doubled["a"]["unused"].item() == 10.0
+
+
+def test_adam_has_no_cpu_path_and_schedules_stay_on_the_host_loop():
+    """optim.adam updates on the device only (no CPU fallback on the product path); an optax-style schedule is accepted and
+    keeps train_fn on the generic loop (no static hyper-parameters to hand to bjx_train_steps)."""
+    adam = optim.adam(0.1)
+    state = adam.init({"w": torch.zeros(3)})
+    with pytest.raises(TypeError, match="no CPU path"):
+        adam.update({"w": torch.ones(3)}, state)
+    sched = optim.adam(lambda count: 0.1 / (1 + count))
+    assert sched.hyper is None and adam.hyper == (0.1, 0.9, 0.999, 1e-8)
+    m = _FakeModel()
+    canonical = partial(m.loss_fn, outputs=[1.0], inputs=None, full_data_size=1, n_samples=4)
+    assert U._fused_loop_spec(canonical, sched, seed=object(), return_args=frozenset()) is None
+
+
+def test_return_args_cover_the_reference_locals():
+    """utils.py:33-35 returns ``locals()[key]`` for any requested name: ``state`` is the optimiser state before the scan."""
+    res = U.train_fn(lambda p: (p["w"] ** 2).sum(), {"w": torch.ones(2)}, optim.sgd(0.1), n_epochs=3,
+                     return_args={"state", "states", "n_epochs", "losses"})
+    assert res["state"] == () and res["states"] == () and res["n_epochs"] == 3 and res["losses"].shape == (3,)

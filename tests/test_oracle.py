@@ -119,6 +119,56 @@ def test_batched_restatements_agree_with_the_per_sample_one():
     assert torch.allclose(a[3]["log_noise_scale"], b[3], rtol=1e-12)
 
 
+@pytest.mark.parametrize("case", ["logistic", "linreg_kwarg", "full_rank", "coin", "noise_latent"])
+def test_chunked_checker_is_the_per_sample_restatement(case):
+    """``value_and_grad_chunked`` (the checker of the full-size GPU parity tests) against ``value_and_grad`` on problems
+    where both run: ragged row blocks, every likelihood exemplar, constrained latents, a row shard with ``n_total``."""
+    from tests import cases as C
+    from bijax_b200 import likelihoods as lk
+
+    torch.manual_seed(3)
+    D, N, S = 6, 101, 5
+    X = torch.randn(N, D, dtype=torch.float64) / 2
+    eps = torch.randn(S, D, dtype=torch.float64)
+    loc = torch.randn(D, dtype=torch.float64) * 0.2
+    raw = torch.randn(D, dtype=torch.float64) * 0.1 - 1
+    prior = {"weights": R.MultivariateNormalDiag(torch.zeros(D), torch.ones(D))}
+    kwargs, vi = {}, "mean_field"
+    if case == "logistic":
+        m = R.ADVIRef(prior, {}, R.bernoulli_logits_loglik())
+        y = (torch.rand(N, dtype=torch.float64) < 0.4).double()
+    elif case == "linreg_kwarg":
+        m = R.ADVIRef(prior, {}, R.gaussian_linear_loglik())
+        y, kwargs = torch.randn(N, dtype=torch.float64), {"log_noise_scale": torch.tensor(-0.3, dtype=torch.float64)}
+    elif case == "full_rank":
+        vi = "full_rank"
+        m = R.ADVIRef(prior, {}, R.gaussian_linear_loglik(), vi)
+        y, kwargs = torch.randn(N, dtype=torch.float64), {"log_noise_scale": torch.tensor(-0.3, dtype=torch.float64)}
+        raw = (0.4 * torch.eye(D) + 0.05 * torch.randn(D, D)).double()
+    elif case == "coin":
+        m, X, D = _coin_model(), None, 1
+        y = (torch.rand(N, dtype=torch.float64) < 0.7).double()
+        loc, raw, eps = loc[:1], raw[:1], eps[:, :1]
+    else:  # a constrained scalar latent next to the weights (sorted keys: noise < weights)
+        pr = {"noise": R.Gamma(2.0, 3.0), "weights": R.MultivariateNormalDiag(torch.zeros(D - 1), torch.ones(D - 1))}
+        m = R.ADVIRef(pr, {"noise": R.Softplus()}, C.oracle_likelihood(lk.GaussianLinear(noise_latent="noise")))
+        X, y = X[:, : D - 1], torch.randn(N, dtype=torch.float64)
+    inputs = {"X": X} if X is not None else None
+    a = m.value_and_grad(loc, raw, kwargs, y, inputs, 3 * N, eps)
+    b = m.value_and_grad_chunked(loc, raw, kwargs, y, X, 3 * N, eps, chunk_rows=17)
+    for u, v in zip(a[:3], b[:3]):
+        assert torch.allclose(u, v, rtol=1e-11, atol=1e-11)
+    for k in kwargs:
+        assert torch.allclose(a[3][k], b[3][k], rtol=1e-11, atol=1e-11)
+    # two row shards, each told the global length, sum to the whole once the q / prior terms are counted once
+    cut = 37
+    s0 = m.value_and_grad_chunked(loc, raw, kwargs, y[:cut], X[:cut] if X is not None else None, 3 * N, eps, chunk_rows=16, n_total=N)
+    s1 = m.value_and_grad_chunked(loc, raw, kwargs, y[cut:], X[cut:] if X is not None else None, 3 * N, eps, chunk_rows=16, n_total=N)
+    z = m.value_and_grad_chunked(loc, raw, kwargs, y[:0], X[:0] if X is not None else None, 3 * N, eps, n_total=N)  # q / prior terms alone
+    for u, v0, v1, vz in zip(a[:3], s0[:3], s1[:3], z[:3]):
+        assert torch.allclose(u, v0 + v1 - vz, rtol=1e-10, atol=1e-10)
+
+
 def test_coin_toss_loss_is_bounded_by_the_log_evidence():
     """coin_toss.ipynb: tosses [0,1,1,1,1,0], prior Beta(1,2): log evidence -4.941642, so -ELBO >= 4.9416 for any q."""
     y = torch.tensor([0, 1, 1, 1, 1, 0], dtype=torch.float64)
@@ -264,3 +314,36 @@ def test_randint_regression_vectors():
     for c in fx["cases"]:
         got = tf.randint(tf.prng_key(c["seed"]), c["n"], c["minval"], c["maxval"], c["layout"])
         assert [int(v) for v in got] == c["values"], c
+
+
+def test_optax_adam_restatement():
+    """oracle/optax_ref.py: closed forms of optax.adam (first update; constant gradient) and an independent implementation
+    of the same published algorithm (torch.optim.Adam in float64: eps outside the root, both bias corrections)."""
+    from oracle import optax_ref as O
+
+    rng = np.random.default_rng(0)
+    n, lr, eps = 9, 0.03, 1e-8
+    g = rng.normal(size=n)
+    st = O.adam_init(n)
+    u1 = O.adam_update(g, st, lr)
+    assert np.allclose(u1, -lr * g / (np.abs(g) + eps), rtol=1e-14, atol=0)
+    for _ in range(5):  # constant gradient: mu^ = g and nu^ = g^2 at every step
+        assert np.allclose(O.adam_update(g, st, lr), u1, rtol=1e-12, atol=0)
+    assert st.count == 6
+    # a quadratic bowl, 60 steps, against torch.optim.Adam
+    A = rng.normal(size=(n, n))
+    A = A @ A.T / n + np.eye(n)
+    b = rng.normal(size=n)
+    res = O.train(lambda p, key: (0.5 * p @ A @ p - b @ p, A @ p - b), np.zeros(n), range(60), lr, 0.8, 0.95, 1e-6)
+    p = torch.zeros(n, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=lr, betas=(0.8, 0.95), eps=1e-6)
+    At, bt = torch.tensor(A), torch.tensor(b)
+    losses = []
+    for _ in range(60):
+        opt.zero_grad()
+        loss = 0.5 * p @ At @ p - bt @ p
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert np.allclose(res["params"], p.detach().numpy(), rtol=1e-10, atol=1e-12)
+    assert np.allclose(res["losses"], losses, rtol=1e-10, atol=1e-12)
