@@ -13,7 +13,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_lib" / "libbjx.so"
 
 # ---- constants mirrored from include/bjx.h ----------------------------------------------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, -1, -2, -3, -4
 LAYOUT_LEGACY, LAYOUT_PARTITIONABLE = 0, 1
 VI_MEAN_FIELD, VI_FULL_RANK, VI_LOW_RANK = 0, 1, 2
@@ -146,7 +146,7 @@ def load() -> C.CDLL:
 
         _build.build()
     lib = C.CDLL(str(_LIB_PATH))
-    i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+    i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
     lib.bjx_abi_version.restype = C.c_int
     lib.bjx_last_error.restype = C.c_char_p
     lib.bjx_device_sm_count.restype = C.c_int
@@ -160,9 +160,9 @@ def load() -> C.CDLL:
     lib.bjx_elbo_step_host.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp, vp]
     lib.bjx_elbo_kernel_choice.argtypes = [C.POINTER(BjxElboArgs)]
     lib.bjx_elbo_supports_row_index.argtypes = [C.POINTER(BjxElboArgs)]
-    lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
+    lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f64, f64, f64, f64, vp, vp, vp]
     lib.bjx_minibatch_gather.argtypes = [C.POINTER(BjxMinibatch), vp, vp, i32, vp]
-    lib.bjx_train_steps_minibatch.argtypes = [C.POINTER(BjxElboArgs), C.POINTER(BjxMinibatch), i64, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
+    lib.bjx_train_steps_minibatch.argtypes = [C.POINTER(BjxElboArgs), C.POINTER(BjxMinibatch), i64, vp, vp, vp, f64, f64, f64, f64, vp, vp, vp]
     lib.bjx_p2p_buffer_bytes.argtypes = [i64, i32]
     lib.bjx_p2p_buffer_bytes.restype = C.c_size_t
     lib.bjx_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
@@ -177,7 +177,7 @@ def load() -> C.CDLL:
     lib.bjx_posterior_log_prob.argtypes = [C.POINTER(BjxElboArgs), vp, i64, vp, vp]
     lib.bjx_fill_triangular.argtypes = [vp, i64, vp, vp]
     lib.bjx_fill_triangular_vjp.argtypes = [vp, i64, vp, vp]
-    lib.bjx_adam_update.argtypes = [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, vp]
+    lib.bjx_adam_update.argtypes = [vp, vp, vp, vp, i64, i64, f64, f64, f64, f64, vp]
     lib.bjx_profile_begin.argtypes = [i32]
     lib.bjx_profile_collect.argtypes = [vp, i32, vp]
     lib.bjx_profile_end.argtypes = []

@@ -527,21 +527,34 @@ __global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t 
   }
 }
 
-// ---- optax.adam on one element (eps outside the square root, bias-corrected); t = 1-based step number ------------------------
+// ---- optax.adam on one element (eps outside the square root, bias-corrected) ------------------------------------------------
+// Hyper-parameters arrive as doubles and are rounded ONCE: (1 - b) is the float nearest to the exact complement (1.0f - 0.999f
+// is 1.3e-5 off 0.001), and the bias corrections 1 - b^t come from expm1(t log b) in double (1 - powf(b, t) loses 1e-5
+// relative while b^t is close to 1, i.e. during the first steps).
+struct AdamHyper {
+  float lr, b1, omb1, b2, omb2, eps;
+  double lb1, lb2;  // log b1, log b2
+};
+static AdamHyper adam_hyper(double lr, double b1, double b2, double eps) {
+  return AdamHyper{(float)lr, (float)b1, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, log(b1), log(b2)};
+}
+__device__ __forceinline__ void adam_bias(const AdamHyper& h, int64_t t, float& c1, float& c2) {  // t = 1-based step number
+  c1 = (float)(-expm1((double)t * h.lb1));
+  c2 = (float)(-expm1((double)t * h.lb2));
+}
 __device__ __forceinline__ void adam_one(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float gi, int64_t i,
-                                         float lr, float b1, float b2, float eps, float t) {
-  const float c1 = 1.0f - powf(b1, t), c2 = 1.0f - powf(b2, t);
-  const float mi = b1 * m[i] + (1.0f - b1) * gi;
-  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+                                         const AdamHyper& h, float c1, float c2) {
+  const float mi = h.b1 * m[i] + h.omb1 * gi;
+  const float vi = h.b2 * v[i] + h.omb2 * gi * gi;
   m[i] = mi;
   v[i] = vi;
-  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  p[i] -= h.lr * (mi / c1) / (sqrtf(vi / c2) + h.eps);
 }
 
 // the rest of a training step (Adam, loss record, step counter) for kernels that can finish it themselves
 struct TrainTail {
   float *params, *m, *v;  // params == nullptr: not a training step
-  float lr, b1, b2, eps;
+  AdamHyper h;
   int64_t* steps_done;
   float* losses;
   int64_t n;
@@ -635,7 +648,9 @@ __global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restri
   if (tt.params != nullptr) {
     __syncthreads();  // out[] written above by this block
     const int64_t t0 = *tt.steps_done;
-    for (int64_t i = tid; i < tt.n; i += 256) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.lr, tt.b1, tt.b2, tt.eps, (float)(t0 + 1));
+    float c1, c2;
+    adam_bias(tt.h, t0 + 1, c1, c2);
+    for (int64_t i = tid; i < tt.n; i += 256) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.h, c1, c2);
     __syncthreads();  // everybody has read the step number (and the key it selects)
     if (tid == 0) {
       if (tt.losses) tt.losses[t0] = out[0];
@@ -782,33 +797,33 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
 
 // ---- fused optimiser step (optax.adam, eps outside the square root, bias-corrected) ---------------------------------
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                              const float* __restrict__ g, int64_t n, float lr, float b1, float b2,
-                                              float eps, float c1, float c2) {
+                                              const float* __restrict__ g, int64_t n, AdamHyper h, float c1, float c2) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  const float gi = g[i];
-  const float mi = b1 * m[i] + (1.0f - b1) * gi;
-  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  adam_one(p, m, v, g[i], i, h, c1, c2);
 }
 
 // device-resident training loop: the step number lives on the device, so that a captured CUDA graph of whole training
 // steps (ELBO + gradient -> Adam -> bookkeeping) can be replayed without any per-replay update
 __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                  const float* __restrict__ g, int64_t n, float lr, float b1, float b2,
-                                                  float eps, const int64_t* __restrict__ steps_done) {
+                                                  const float* __restrict__ g, int64_t n, AdamHyper h,
+                                                  const int64_t* __restrict__ steps_done) {
+  __shared__ float c[2];
+  if (threadIdx.x == 0) adam_bias(h, *steps_done + 1, c[0], c[1]);
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  adam_one(p, m, v, g[i], i, lr, b1, b2, eps, (float)(*steps_done + 1));
+  adam_one(p, m, v, g[i], i, h, c[0], c[1]);
 }
 
 // few parameters (n <= 1024): Adam and the bookkeeping of k_train_bump in one block, one launch
 __global__ void __launch_bounds__(1024) k_adam_bump_small(TrainTail tt, const float* __restrict__ out) {
+  __shared__ float c[2];
   const int64_t t0 = *tt.steps_done;
+  if (threadIdx.x == 0) adam_bias(tt.h, t0 + 1, c[0], c[1]);
+  __syncthreads();
   const int64_t i = threadIdx.x;
-  if (i < tt.n) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.lr, tt.b1, tt.b2, tt.eps, (float)(t0 + 1));
+  if (i < tt.n) adam_one(tt.params, tt.m, tt.v, out[1 + i], i, tt.h, c[0], c[1]);
   __syncthreads();
   if (threadIdx.x == 0) {
     if (tt.losses) tt.losses[t0] = out[0];
@@ -934,7 +949,7 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
 }
 
 static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,
-                            float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses,
+                            float* adam_v, double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses,
                             void* stream) {
   using namespace bjx;
   BJX_REQUIRE(args != nullptr && params_flat && adam_m && adam_v && steps_done, "null pointer");
@@ -957,7 +972,7 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = a.D + p.Pn + a.K;
-  const TrainTail tt{params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, n};
+  const TrainTail tt{params_flat, adam_m, adam_v, adam_hyper(lr, b1, b2, eps), steps_done, losses, n};
   for (int64_t i = 0; i < n_steps; ++i) {
     if (mb) {
       rc = launch_minibatch_gather(*mb, args->key, steps_done, a.threefry_layout, st);
@@ -972,7 +987,7 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
       BJX_LAUNCH_CHECK("k_adam_bump_small");
       continue;
     }
-    k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params_flat, adam_m, adam_v, a.out + 1, n, lr, b1, b2, eps, steps_done);
+    k_adam_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params_flat, adam_m, adam_v, a.out + 1, n, tt.h, steps_done);
     BJX_LAUNCH_CHECK("k_adam_dev");
     k_train_bump<<<1, 1, 0, st>>>(steps_done, a.out, losses);
     BJX_LAUNCH_CHECK("k_train_bump");
@@ -981,12 +996,12 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
 }
 
 int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
-                    float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream) {
+                    double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses, void* stream) {
   return train_steps_impl(args, nullptr, n_steps, params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, stream);
 }
 
 int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,
-                              float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done, float* losses,
+                              float* adam_v, double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses,
                               void* stream) {
   using namespace bjx;
   BJX_REQUIRE(mb != nullptr, "mb is null");
@@ -1039,14 +1054,16 @@ int bjx_profile_end(void) {
   return BJX_OK;
 }
 
-int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
-                    float b2, float eps, void* stream) {
+int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, double lr, double b1,
+                    double b2, double eps, void* stream) {
   using namespace bjx;
   BJX_REQUIRE(params && m && v && grads, "null pointer");
   BJX_REQUIRE(n >= 0 && step >= 1, "need n >= 0 and step >= 1");
+  BJX_REQUIRE(b1 > 0.0 && b1 < 1.0 && b2 > 0.0 && b2 < 1.0, "need 0 < b1, b2 < 1");
   if (n == 0) return BJX_OK;
-  const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
-  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, n, lr, b1, b2, eps, c1, c2);
+  const AdamHyper h = adam_hyper(lr, b1, b2, eps);
+  const float c1 = (float)(-expm1((double)step * h.lb1)), c2 = (float)(-expm1((double)step * h.lb2));
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, n, h, c1, c2);
   BJX_LAUNCH_CHECK("k_adam");
   return BJX_OK;
 }

@@ -225,6 +225,7 @@ class ElboEngine:
     def release_planes(self) -> None:
         """Drop the prepared operand planes (and the hold on their source tensor's storage)."""
         self._planes, self._planes_key, self._planes_storage, self._last_raw = None, None, None, None
+        self._planes_misses = 0
 
     def prepare(self, X, y, n_samples) -> bool:
         """Prepare the dataset's operand planes now (otherwise the first step does it).  Returns True if this engine keeps

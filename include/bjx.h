@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BJX_ABI_VERSION 3
+#define BJX_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define BJX_API __attribute__((visibility("default")))
@@ -244,9 +244,10 @@ BJX_API int bjx_posterior_log_prob(const BjxElboArgs* args, const float* theta, 
 BJX_API int bjx_fill_triangular(const float* packed, int64_t D, float* dense, void* stream);
 BJX_API int bjx_fill_triangular_vjp(const float* d_dense, int64_t D, float* d_packed, void* stream);
 
-/* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27) */
-BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, float lr, float b1,
-                    float b2, float eps, void* stream);
+/* ---- optimiser step fused on the device (optax.adam as used by train_fn, utils.py:26-27).  Hyper-parameters are doubles
+ * (ABI 4) and rounded once inside: (1 - b) and the bias corrections 1 - b^step are formed in double. */
+BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grads, int64_t n, int64_t step, double lr, double b1,
+                    double b2, double eps, void* stream);
 
 /* ---- the training loop of train_fn (utils.py:22-31) resident on the device -----------------------------------------
  * Enqueues n_steps x { ELBO + gradients at key[*steps_done] -> Adam update of params_flat in place -> losses[*steps_done]
@@ -256,8 +257,8 @@ BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grad
  * optax.adam moments (zero-initialised), args->key the [n, 2] key array, args->out the packed step output (scratch),
  * losses (optional) at least as long as the total number of steps.  Single device: under row sharding run
  * bjx_elbo_step + the all-reduce + bjx_adam_update from the host instead. */
-BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, float lr,
-                    float b1, float b2, float eps, int64_t* steps_done, float* losses, void* stream);
+BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, double lr,
+                    double b1, double b2, double eps, int64_t* steps_done, float* losses, void* stream);
 
 /* ---- on-device minibatch sampler (the scaling it feeds is advi.py:92) ----------------------
  * What a JAX user writes around loss_fn,
@@ -290,7 +291,7 @@ BJX_API int bjx_minibatch_gather(const BjxMinibatch* mb, const uint32_t* key, co
  * mb->Xb, y = mb->yb, x_planes = mb->planes_b or NULL, ll_scale = full_data_size / B); args->key is the [n, 2] array of
  * per-step keys; mb->elbo_key must be set.  Graph-capturable like bjx_train_steps. */
 BJX_API int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat,
-                                      float* adam_m, float* adam_v, float lr, float b1, float b2, float eps, int64_t* steps_done,
+                                      float* adam_m, float* adam_v, double lr, double b1, double b2, double eps, int64_t* steps_done,
                                       float* losses, void* stream);
 
 /* ---- the exchange step over NVLink peer memory (one kernel instead of an NCCL call) ---------------------------------

@@ -108,7 +108,7 @@ class Chain:
 
 # --------------------------------------------------------------------------- distributions (tfd.*)
 def _t(v, like):
-    return torch.as_tensor(v, dtype=like.dtype)
+    return torch.as_tensor(v, dtype=like.dtype, device=like.device)
 
 
 class Normal:
@@ -358,7 +358,7 @@ class ADVIRef:
         return p + self.log_likelihood_fn(theta, outputs, inputs)
 
     def value_and_grad_chunked(self, loc, raw_scale, kwargs, outputs, X, full_data_size, eps, chunk_rows=1 << 18,
-                               n_total=None):
+                               n_total=None, dtype=torch.float64):
         """``value_and_grad`` for problems too large for one autograd graph (BASELINE.json's full sizes: c3 10M rows, a c5
         shard of 12.5M rows, c4 at D=2048 / S=256 / N=1M).  Same formulas as ``loss`` (advi.py:80-95), float64 throughout:
 
@@ -372,9 +372,10 @@ class ADVIRef:
         It runs wherever ``outputs`` / ``X`` live (``outputs.device``): the -m gpu tests keep the float32 dataset on the
         GPU and let torch do the float64 arithmetic there -- torch is the CHECKER's calculator here, not the product.
         ``n_total``: the global ``len(outputs)`` when (outputs, X) is one row shard of a larger dataset.
+        ``dtype=torch.float32`` on CPU tensors is the timed CPU baseline of the full-rank configuration (bench.py).
         Returns loss, dloc, draw_scale, {dkwargs} like ``value_and_grad``."""
         dev = outputs.device
-        f64 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=torch.float64)
+        f64 = lambda t: torch.as_tensor(t).detach().to(device=dev, dtype=dtype)
         loc = f64(loc).clone().requires_grad_(True)
         raw_scale = f64(raw_scale).clone().requires_grad_(True)
         kw = {k: f64(v).clone().requires_grad_(True) for k, v in kwargs.items()}
@@ -390,7 +391,7 @@ class ADVIRef:
             samples = loc + eps @ tril.T
             zz = torch.linalg.solve_triangular(tril, (samples - loc).T, upper=False)  # [D, S]
             q = -0.5 * (zz * zz).sum(0) - torch.log(torch.abs(torch.diagonal(tril))).sum() - 0.5 * D * LOG_2PI
-        p = torch.zeros(S, dtype=torch.float64, device=dev)
+        p = torch.zeros(S, dtype=dtype, device=dev)
         theta, o = {}, 0
         for k in self.names:
             n = self.sizes[k]
@@ -404,11 +405,11 @@ class ADVIRef:
         kw_leaf = {k: v.detach().clone().requires_grad_(True) for k, v in kw.items()}
         leaves = list(th_leaf.values()) + list(kw_leaf.values())
         acc = [torch.zeros_like(l) for l in leaves]
-        ll_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        ll_sum = torch.zeros((), dtype=dtype, device=dev)
         N = outputs.shape[0]
         for i in range(0, N, int(chunk_rows)):
-            yc = outputs[i : i + chunk_rows].to(torch.float64)[:, None]
-            inputs = {"X": X[i : i + chunk_rows].to(torch.float64)} if X is not None else None
+            yc = outputs[i : i + chunk_rows].to(dtype)[:, None]
+            inputs = {"X": X[i : i + chunk_rows].to(dtype)} if X is not None else None
             ll = self.log_likelihood_fn(th_leaf, yc, inputs, **kw_leaf)  # sum over the block's rows AND the S samples
             gs = torch.autograd.grad(ll, leaves, allow_unused=True)
             for a, g in zip(acc, gs):

@@ -36,10 +36,11 @@ def test_adam_kernel_against_the_optax_restatement(count):
     p, m, v, gd = (torch.tensor(a, device="cuda") for a in (p0, m0, v0, g))
     nv.check(nv.load().bjx_adam_update(p.data_ptr(), m.data_ptr(), v.data_ptr(), gd.data_ptr(), n, count, lr, b1, b2, eps,
                                        nv.current_stream_ptr()))
-    C.assert_close(m.cpu().numpy(), st.mu, rtol=2e-6, atol_scale=1e-7, what="mu")
-    C.assert_close(v.cpu().numpy(), st.nu, rtol=2e-6, atol_scale=1e-12, what="nu")
-    C.assert_close(p.cpu().numpy().astype(np.float64) - p0, u, rtol=1e-4, atol_scale=2e-5, what="update")  # p0 + u rounds to fp32 of p
-    C.assert_close(p.cpu().numpy(), p0 + u, rtol=2e-6, atol_scale=1e-7, what="params")
+    # mu mixes signs (cancellation between b1*m and (1-b1)*g): float32 rounding of the larger term is the floor;
+    # nu is a sum of positives: a few float32 ulps relative, which also proves (1 - b2) is the float nearest to 0.001
+    C.assert_close(m.cpu().numpy(), st.mu, rtol=2e-6, atol_scale=2e-7, what="mu")
+    C.assert_close(v.cpu().numpy(), st.nu, rtol=5e-7, atol_scale=0.0, what="nu")
+    C.assert_close(p.cpu().numpy(), p0 + u, rtol=1e-5, atol_scale=2e-7, what="params")
 
 
 def _oracle_training(ref, flat0, D, P, kw_names, y, X, full, seed, n, S, lr, layout=tf.LAYOUT_LEGACY):
