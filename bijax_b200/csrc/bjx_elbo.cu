@@ -375,22 +375,33 @@ __global__ void __launch_bounds__(256) k_fullrank_dM(const float* __restrict__ g
 
 // ---- coin toss (tfd.Bernoulli(probs=p).log_prob(y).sum(), README.md:91-95): one block per sample ---------------------
 // aux[s] = (log p, log(1-p), d log p / dz, d log(1-p) / dz) from the prologue; G[s] is d ll_s / d z (not d/d theta).
+// The coin-toss log-likelihood is LINEAR in the labels: sum_n [(1 - y_n) A + y_n B] = (N - sum y) A + (sum y) B, for A, B the
+// per-sample log(1 - theta), log(theta) (or their z-derivatives).  Summing the N rounded products instead adds the SAME
+// two values thousands of times, and the rounding of such a sum is not random: it drifts systematically (4e-6 relative at
+// N = 4096, which the near-cancellation k - N*theta of the gradient amplifies past rtol 1e-5).  So: sum y once, in double.
+__device__ __forceinline__ double block_sum_f64(double v, double* red /* [8] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];  // fixed order: every thread gets the same bits
+  return t;
+}
+
 __global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, int64_t N, const float4* __restrict__ aux,
                                                   float* __restrict__ G, float* __restrict__ stat) {
-  __shared__ float red[32];
+  __shared__ double red[8];
   const int s = blockIdx.x;
-  const float4 a = aux[s];
-  float f = 0.0f, g = 0.0f;
-  for (int64_t n = threadIdx.x; n < N; n += 256) {
-    const float k = y[n];
-    f += (1.0f - k) * a.y + k * a.x;
-    g += (1.0f - k) * a.w + k * a.z;
-  }
-  const float fs = block_sum(f, red);
-  const float gs = block_sum(g, red);
+  double sy = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += 256) sy += (double)y[n];
+  sy = block_sum_f64(sy, red);
   if (threadIdx.x == 0) {
-    stat[s] = fs;
-    G[s] = gs;
+    const float4 a = aux[s];
+    const double k0 = (double)N - sy;
+    stat[s] = (float)(k0 * (double)a.y + sy * (double)a.x);
+    G[s] = (float)(k0 * (double)a.w + sy * (double)a.z);
   }
 }
 
@@ -577,6 +588,7 @@ __global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restri
   __shared__ float4 s_aux[TINY_S];
   __shared__ float s_G[TINY_S], s_stat[TINY_S];
   __shared__ float red[32];
+  __shared__ double s_red64[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = S * D;
   const uint32_t* k = key_index ? key + 2 * (*key_index) : key;
@@ -599,21 +611,15 @@ __global__ void __launch_bounds__(256) k_tiny_coin_step(const uint32_t* __restri
   }
   const float qp_sum = block_sum(term, red);  // valid in thread 0
   __syncthreads();
-  // ---- stage 2 (k_lik_coin): per sample, sums over the N tosses -- one warp per sample
-  for (int s = warp; s < S; s += 8) {
+  // ---- stage 2 (k_lik_coin): the labels are summed ONCE (the log-likelihood is linear in them, see k_lik_coin)
+  double sy = 0.0;
+  for (int n = tid; n < N; n += 256) sy += (double)y[n];
+  sy = block_sum_f64(sy, s_red64);
+  for (int s = tid; s < S; s += 256) {
     const float4 a = s_aux[s];
-    float f = 0.0f, g = 0.0f;
-    for (int n = lane; n < N; n += 32) {
-      const float kk = y[n];
-      f += (1.0f - kk) * a.y + kk * a.x;
-      g += (1.0f - kk) * a.w + kk * a.z;
-    }
-    f = warp_sum(f);
-    g = warp_sum(g);
-    if (lane == 0) {
-      s_stat[s] = N > 0 ? f : 0.0f;
-      s_G[s] = N > 0 ? g : 0.0f;
-    }
+    const double k0 = (double)N - sy;
+    s_stat[s] = N > 0 ? (float)(k0 * (double)a.y + sy * (double)a.x) : 0.0f;
+    s_G[s] = N > 0 ? (float)(k0 * (double)a.w + sy * (double)a.z) : 0.0f;
   }
   __syncthreads();
   // ---- stage 3 (k_tail): reparameterisation gradient, one warp per latent coordinate

@@ -113,13 +113,9 @@ def oracle_step(ref, loc, raw, kwargs, y, X, full_data_size, key_np, S, layout, 
     return ref.value_and_grad(t64(loc), t64(raw), kw, t64(y), inputs, full_data_size, eps), eps
 
 
-def assert_close(got, want, rtol=1e-5, atol_scale=1e-5, what="", fp32_uncertainty=None):
+def assert_close(got, want, rtol=1e-5, atol_scale=1e-5, what=""):
     """rtol 1e-5 as north_star states: ``tol = max(rtol*|want|, atol_scale*max|want|)`` -- entries that are tiny relative to
-    the largest one of their block get the block's absolute floor, the large ones exactly rtol.
-    ``fp32_uncertainty`` (only for outputs a test declares ill-conditioned): |float32 restatement - float64 restatement| of the
-    same quantity, i.e. how far ANY float32 evaluation of the reference's formulas -- the reference's own included -- sits
-    from exact arithmetic; four times that is added to the tolerance.  north_star's rtol 1e-5 is an agreement between two
-    float32 computations, which cannot be tighter than their own rounding noise."""
+    the largest one of their block get the block's absolute floor, the large ones exactly rtol."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert np.isfinite(want).all(), f"{what}: oracle value is not finite"
@@ -127,7 +123,5 @@ def assert_close(got, want, rtol=1e-5, atol_scale=1e-5, what="", fp32_uncertaint
     scale = max(float(np.max(np.abs(want))), 1e-30)
     err = np.abs(got - want)
     tol = np.maximum(rtol * np.abs(want), atol_scale * scale)
-    if fp32_uncertainty is not None:
-        tol = tol + 4.0 * np.abs(np.asarray(fp32_uncertainty, dtype=np.float64))
     bad = err > tol
     assert not bad.any(), f"{what}: max err {err.max():.3e} (rel-to-max {err.max() / scale:.3e}) at {np.argmax(err)}; want {want.ravel()[np.argmax(err)]:.6e} got {got.ravel()[np.argmax(err)]:.6e}"
