@@ -104,11 +104,64 @@ __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float 
   return fmaxf(lo, u);
 }
 
-// XLA ErfInv (f32, Giles' polynomial) under the pinned spec of oracle/threefry.py:
-// binary32 RN, no FMA, w = float(-log1p(-(double)(u*u))).
+// ---- the pinned float spec of oracle/threefry.py: binary32 round-to-nearest, every multiply and add rounded separately ----
+#define BJX_MADD(p, x, c) __fadd_rn(__fmul_rn((p), (x)), (c))
+
+// Cephes logf as XLA:CPU inlines it (GenerateVF32Log), for positive normal x; 0 -> -inf
+__device__ __forceinline__ float logf_spec(float x) {
+  const uint32_t bits = __float_as_uint(x);
+  float e = (float)((int)((bits >> 23) & 0xFFu) - 126);
+  float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F000000u);  // mantissa in [0.5, 1)
+  const bool lt = m < 0.707106781186547524f;
+  e = lt ? __fsub_rn(e, 1.0f) : e;
+  m = __fsub_rn(lt ? __fadd_rn(m, m) : m, 1.0f);
+  const float z = __fmul_rn(m, m);
+  float y = 7.0376836292e-2f;
+  y = BJX_MADD(y, m, -1.1514610310e-1f);
+  y = BJX_MADD(y, m, 1.1676998740e-1f);
+  y = BJX_MADD(y, m, -1.2420140846e-1f);
+  y = BJX_MADD(y, m, 1.4249322787e-1f);
+  y = BJX_MADD(y, m, -1.6668057665e-1f);
+  y = BJX_MADD(y, m, 2.0000714765e-1f);
+  y = BJX_MADD(y, m, -2.4999993993e-1f);
+  y = BJX_MADD(y, m, 3.3333331174e-1f);
+  y = __fmul_rn(__fmul_rn(y, m), z);
+  y = __fadd_rn(y, __fmul_rn(e, -2.12194440e-4f));
+  y = __fsub_rn(y, __fmul_rn(0.5f, z));
+  float r = __fadd_rn(m, y);
+  r = __fadd_rn(r, __fmul_rn(e, 0.693359375f));
+  return x == 0.0f ? __int_as_float(0xff800000) : r;
+}
+
+// XLA's single-precision Log1p (EmitLog1p): Cephes rational below sqrt(2) - 1, log(1 + x) of the rounded sum above
+__device__ __forceinline__ float log1p_spec(float x) {
+  if (fabsf(x) < 0.41421356237309504880f) {
+    float num = 4.5270000862445199635215e-5f;
+    num = BJX_MADD(num, x, 4.9854102823193375972212e-1f);
+    num = BJX_MADD(num, x, 6.5787325942061044846969e0f);
+    num = BJX_MADD(num, x, 2.9911919328553073277375e1f);
+    num = BJX_MADD(num, x, 6.0949667980987787057556e1f);
+    num = BJX_MADD(num, x, 5.7112963590585538103336e1f);
+    num = BJX_MADD(num, x, 2.0039553499201281259648e1f);
+    float den = 1.0f;
+    den = BJX_MADD(den, x, 1.5062909083469192043167e1f);
+    den = BJX_MADD(den, x, 8.3047565967967209469434e1f);
+    den = BJX_MADD(den, x, 2.2176239823732856465394e2f);
+    den = BJX_MADD(den, x, 3.0909872225312059774938e2f);
+    den = BJX_MADD(den, x, 2.1642788614495947685003e2f);
+    den = BJX_MADD(den, x, 6.0118660497603843919306e1f);
+    const float x2 = __fmul_rn(x, x);
+    const float q = __fmul_rn(__fmul_rn(x, x2), __fdiv_rn(num, den));
+    const float z = __fadd_rn(__fmul_rn(-0.5f, x2), q);
+    return __fadd_rn(x, z);
+  }
+  return logf_spec(__fadd_rn(1.0f, x));
+}
+
+// XLA ErfInv (f32, Giles' polynomial): w = -log1p(-u*u), then one of two degree-8 polynomials
 __device__ __forceinline__ float erfinv_spec(float u) {
   const float t = __fmul_rn(u, u);
-  float w = (float)(-log1p(-(double)t));
+  float w = -log1p_spec(-t);
   float p;
   if (w < 5.0f) {
     w = __fsub_rn(w, 2.5f);

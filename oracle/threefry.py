@@ -20,15 +20,33 @@ this file restates their *published* algorithm:
     single-precision ``ErfInv`` (Giles' polynomial).
 
 Pinned spec of the float pipeline ("the spec" in DESIGN.md): every operation
-is IEEE-754 binary32 round-to-nearest with NO fused multiply-add, except
-``w = -log1p(-u*u)`` which is evaluated as
-``float32(-log1p(float64(float32(u*u))))`` -- i.e. the correctly rounded
-value of the true function of the rounded argument.  The CUDA kernel follows
-the same spec so that the two agree bit for bit.
+is IEEE-754 binary32 round-to-nearest with NO fused multiply-add, and
+``w = -log1p(-u*u)`` follows XLA's own single-precision ``Log1p`` expansion
+(xla/service/elemental_ir_emitter.cc, EmitLog1p -- what the reference's
+jit-compiled CPU path executes): for |x| < sqrt(2) - 1 the Cephes rational
+``x + (-x^2/2 + x*x^2 * P(x)/Q(x))`` evaluated in binary32 (Horner, separate
+multiply and add, one division), otherwise ``log(1 + x)`` of the ROUNDED
+binary32 sum, with ``log`` the Cephes ``logf`` polynomial that XLA:CPU inlines
+for vectorised f32 logarithms (xla/service/cpu/llvm_ir_runtime.cc,
+GenerateVF32Log: mantissa in [sqrt(1/2), sqrt(2)), degree-8 polynomial,
+``e * ln 2`` added in two parts) -- again binary32 with separate multiply and
+add.  Nothing in the pipeline calls a libm, so NumPy and the CUDA kernel agree
+bit for bit by construction.  (Both expansions are restated from memory of
+XLA's sources, which are not on this box; what pins them is below.)
+``LOG1P_SPEC`` selects two alternatives kept
+for the record: "correctly_rounded" (``float32(-log1p(float64(u*u)))``, the
+round-1 spec, which misses one published value by one ulp) and "libm_f32"
+(binary32 ``log1p`` of the platform's libm, what XLA:GPU's libdevice call
+amounts to).
 
 PARITY STATUS: pinned against the Random123 KATs and the publicly documented
-``jax.random`` outputs listed in tests/golden/threefry_kat.json; NOT pinned
-against a live JAX (none available here).
+``jax.random`` outputs listed in tests/golden/threefry_kat.json -- bits, split,
+uniform and ALL FOUR documented normals exactly under the default spec; NOT
+pinned against a live JAX (none available here).  The published partitionable
+value for seed 0 is a sharp discriminator only by luck: log(1 - u*u) there sits
+0.004 ulp from a binary32 rounding tie, so the correctly rounded logarithm and
+the Cephes polynomial (0.79 ulp worst case) land on different floats, and the
+published value is the polynomial's.
 """
 from __future__ import annotations
 
@@ -141,12 +159,76 @@ _ERFINV_LARGE = [
 ]
 
 
-def erfinv_f32(u: np.ndarray) -> np.ndarray:
+# Cephes log1p rational (unity.c), the constants XLA's EmitLog1p carries: log1p(x) = x - x^2/2 + x^3 P(x)/Q(x)
+_LOG1P_P = [4.5270000862445199635215e-5, 4.9854102823193375972212e-1, 6.5787325942061044846969e0,
+            2.9911919328553073277375e1, 6.0949667980987787057556e1, 5.7112963590585538103336e1, 2.0039553499201281259648e1]
+_LOG1P_Q = [1.0, 1.5062909083469192043167e1, 8.3047565967967209469434e1, 2.2176239823732856465394e2,
+            3.0909872225312059774938e2, 2.1642788614495947685003e2, 6.0118660497603843919306e1]
+_LOG1P_SMALL = np.float32(0.41421356237309504880)  # sqrt(2) - 1
+LOG1P_SPEC = "xla_cpu"  # "xla_cpu" (default) | "correctly_rounded" | "libm_f32"
+
+
+_LOGF_P = [7.0376836292e-2, -1.1514610310e-1, 1.1676998740e-1, -1.2420140846e-1, 1.4249322787e-1, -1.6668057665e-1,
+           2.0000714765e-1, -2.4999993993e-1, 3.3333331174e-1]
+_LOGF_Q1, _LOGF_Q2 = np.float32(-2.12194440e-4), np.float32(0.693359375)  # ln 2 = q1 + q2
+_SQRTHF = np.float32(0.707106781186547524)
+
+
+def logf_cephes(x: np.ndarray) -> np.ndarray:
+    """Cephes logf as XLA:CPU inlines it, for positive normal binary32 x (0 -> -inf): all operations binary32, no FMA."""
+    x = np.asarray(x, dtype=np.float32)
+    bits = x.view(np.uint32)
+    e = (((bits >> U32(23)) & U32(0xFF)).astype(np.int32) - 126).astype(np.float32)
+    m = ((bits & U32(0x007FFFFF)) | U32(0x3F000000)).view(np.float32)  # mantissa in [0.5, 1)
+    lt = m < _SQRTHF
+    e = np.where(lt, e - np.float32(1.0), e).astype(np.float32)
+    m = (np.where(lt, (m + m).astype(np.float32), m) - np.float32(1.0)).astype(np.float32)
+    z = (m * m).astype(np.float32)
+    y = _horner_f32(m, _LOGF_P)
+    y = ((y * m).astype(np.float32) * z).astype(np.float32)
+    y = (y + (e * _LOGF_Q1).astype(np.float32)).astype(np.float32)
+    y = (y - (np.float32(0.5) * z).astype(np.float32)).astype(np.float32)
+    r = (m + y).astype(np.float32)
+    r = (r + (e * _LOGF_Q2).astype(np.float32)).astype(np.float32)
+    return np.where(x == np.float32(0.0), np.float32(-np.inf), r).astype(np.float32)
+
+
+def _horner_f32(x: np.ndarray, coeffs) -> np.ndarray:
+    """XLA's EvaluatePolynomial in binary32: poly = poly * x + c, multiply and add rounded separately."""
+    p = np.full_like(x, np.float32(coeffs[0]))
+    for c in coeffs[1:]:
+        p = (p * x).astype(np.float32)
+        p = (p + np.float32(c)).astype(np.float32)
+    return p
+
+
+def log1p_f32(x: np.ndarray, spec: str = None) -> np.ndarray:
+    """Single-precision log1p under the selected spec (module docstring)."""
+    spec = LOG1P_SPEC if spec is None else spec
+    x = np.asarray(x, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if spec == "correctly_rounded":
+            return np.log1p(x.astype(np.float64)).astype(np.float32)
+        if spec == "libm_f32":
+            return np.log1p(x).astype(np.float32)
+        if spec != "xla_cpu":
+            raise ValueError(f"unknown log1p spec {spec!r}")
+        big = logf_cephes((np.float32(1.0) + x).astype(np.float32))
+        num, den = _horner_f32(x, _LOG1P_P), _horner_f32(x, _LOG1P_Q)
+        x2 = (x * x).astype(np.float32)
+        r = (num / den).astype(np.float32)
+        q = ((x * x2).astype(np.float32) * r).astype(np.float32)
+        z = ((np.float32(-0.5) * x2).astype(np.float32) + q).astype(np.float32)
+        small = (x + z).astype(np.float32)
+        return np.where(np.abs(x) < _LOG1P_SMALL, small, big).astype(np.float32)
+
+
+def erfinv_f32(u: np.ndarray, spec: str = None) -> np.ndarray:
     """XLA ErfInv (f32, Giles) under the pinned spec in the module docstring."""
     u = np.asarray(u, dtype=np.float32)
     t = (u * u).astype(np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        w = (-np.log1p(-(t.astype(np.float64)))).astype(np.float32)
+        w = (-log1p_f32(-t, spec)).astype(np.float32)
         small = w < np.float32(5.0)
         ws = (w - np.float32(2.5)).astype(np.float32)
         wl = (np.sqrt(w).astype(np.float32) - np.float32(3.0)).astype(np.float32)
@@ -157,7 +239,7 @@ def erfinv_f32(u: np.ndarray) -> np.ndarray:
             p = (p * ww).astype(np.float32)  # separate multiply ...
             p = (c + p).astype(np.float32)   # ... and add: no FMA
         r = (p * u).astype(np.float32)
-    r = np.where(np.abs(u) == np.float32(1.0), np.float32(np.inf) * u, r).astype(np.float32)
+        r = np.where(np.abs(u) == np.float32(1.0), np.float32(np.inf) * u, r).astype(np.float32)
     return r
 
 

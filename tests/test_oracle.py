@@ -347,3 +347,44 @@ def test_optax_adam_restatement():
         losses.append(loss.item())
     assert np.allclose(res["params"], p.detach().numpy(), rtol=1e-10, atol=1e-12)
     assert np.allclose(res["losses"], losses, rtol=1e-10, atol=1e-12)
+
+
+def test_log1p_specs_against_the_documented_normals():
+    """The default float spec (XLA's own Log1p expansion with the Cephes logf it inlines on CPU) reproduces all four
+    documented jax.random.normal values exactly; so does the platform-libm float spec; the round-1 spec (correctly rounded
+    log1p) misses one of them by one ulp -- log(1 - u*u) sits 0.004 ulp from a rounding tie there."""
+    want = {"xla_cpu": [0, 0, 0, 0], "libm_f32": [0, 0, 0, 0], "correctly_rounded": [0, 1, 0, 0]}
+    old = tf.LOG1P_SPEC
+    try:
+        for spec, ulps in want.items():
+            tf.LOG1P_SPEC = spec
+            got = []
+            for v in KAT["normal"]:
+                for name, layout in (("legacy", tf.LAYOUT_LEGACY), ("partitionable", tf.LAYOUT_PARTITIONABLE)):
+                    x = tf.normal(tf.prng_key(v["seed"]), tuple(v["shape"]), layout).ravel()[0]
+                    got.append(abs(int(np.float32(x).view(np.int32)) - int(np.float32(v[name]).view(np.int32))))
+            assert got == ulps, (spec, got)
+    finally:
+        tf.LOG1P_SPEC = old
+    assert tf.LOG1P_SPEC == "xla_cpu"
+
+
+def test_float_spec_building_blocks():
+    """logf_cephes within one ulp of the true logarithm; log1p_f32 within two ulps of log1p on (-1, 0]; the three specs
+    agree to a few ulps on a million draws (they differ in ~1 % of them)."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(1e-7, 1.0, 200000), np.exp(rng.uniform(-80, 80, 200000))]).astype(np.float32)
+    ref = np.log(x.astype(np.float64))
+    err = np.abs(tf.logf_cephes(x).astype(np.float64) - ref) / np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+    assert err.max() < 1.0
+    assert tf.logf_cephes(np.zeros(1, np.float32))[0] == -np.inf
+    t = -rng.uniform(0.0, 1.0, 400000).astype(np.float32) ** 2
+    ref = np.log1p(t.astype(np.float64))
+    got = tf.log1p_f32(t, "xla_cpu").astype(np.float64)
+    assert (np.abs(got - ref) <= 2.0 * np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64) + 1e-45).all()
+    bits = tf.random_bits(tf.prng_key(9), 1 << 20, tf.LAYOUT_PARTITIONABLE)
+    u = tf.uniform_from_bits(bits, tf._LO, 1.0)
+    a, b, c = (tf.erfinv_f32(u, s) for s in ("xla_cpu", "correctly_rounded", "libm_f32"))
+    for other in (b, c):
+        d = np.abs(a.view(np.int32).astype(np.int64) - other.view(np.int32).astype(np.int64))
+        assert d.max() <= 4 and 0.0 < (d > 0).mean() < 0.05
