@@ -43,6 +43,9 @@ EXPORTED_SYMBOLS = (
     "bjx_train_steps",
     "bjx_minibatch_gather",
     "bjx_train_steps_minibatch",
+    "bjx_train_steps_sharded",
+    "bjx_allreduce_packed_p2p_dev",
+    "bjx_p2p_set_timeout_ms",
     "bjx_p2p_buffer_bytes",
     "bjx_p2p_alloc",
     "bjx_p2p_open",
@@ -163,6 +166,9 @@ def load() -> C.CDLL:
     lib.bjx_train_steps.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f64, f64, f64, f64, vp, vp, vp]
     lib.bjx_minibatch_gather.argtypes = [C.POINTER(BjxMinibatch), vp, vp, i32, vp]
     lib.bjx_train_steps_minibatch.argtypes = [C.POINTER(BjxElboArgs), C.POINTER(BjxMinibatch), i64, vp, vp, vp, f64, f64, f64, f64, vp, vp, vp]
+    lib.bjx_train_steps_sharded.argtypes = [C.POINTER(BjxElboArgs), i64, vp, vp, vp, f64, f64, f64, f64, vp, vp, vp, i32, i32, C.c_uint64, vp]
+    lib.bjx_allreduce_packed_p2p_dev.argtypes = [vp, i64, vp, i32, i32, C.c_uint64, vp, vp]
+    lib.bjx_p2p_set_timeout_ms.argtypes = [i64]
     lib.bjx_p2p_buffer_bytes.argtypes = [i64, i32]
     lib.bjx_p2p_buffer_bytes.restype = C.c_size_t
     lib.bjx_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]

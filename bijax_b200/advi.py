@@ -232,6 +232,22 @@ class ADVI:
         self._p2p_op = None
         return self
 
+    def _shard_context(self, engine, n_local: int, full_data_size: float):
+        """(ll_scale, prior_weight, exchange) of a row-sharded model with the peer-memory exchange."""
+        import torch.distributed as dist
+
+        if self._global_len is None:
+            t = torch.tensor([int(n_local)], dtype=torch.int64, device=engine.device)
+            dist.all_reduce(t, group=self._group)
+            self._global_len = int(t.item())
+        n_out = 1 + engine.D + engine.P + engine.K
+        if self._p2p_op is None or self._p2p_op.n != n_out:
+            from .parallel import P2PAllReduce
+
+            self._p2p_op = P2PAllReduce(n_out, self._group, engine.device)
+        prior_weight = 1.0 if dist.get_rank(self._group) == 0 else 0.0
+        return float(full_data_size) / float(self._global_len), prior_weight, self._p2p_op
+
     def _run(self, engine, seed, outputs, inputs, full_data_size, n_samples):
         X = None
         if engine.lik_id != nv.LIK_BERNOULLI_PROBS:

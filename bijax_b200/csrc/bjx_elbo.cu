@@ -954,9 +954,15 @@ int bjx_posterior_sample(const BjxElboArgs* args, float* theta_out, float* z_out
   return BJX_OK;
 }
 
+struct ShardExchange {  // row-sharded training: the packed step output is summed over the ranks before Adam
+  void* const* bufs_host;
+  int32_t rank, world;
+  uint64_t epoch_base;
+};
+
 static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,
                             float* adam_v, double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses,
-                            void* stream) {
+                            void* stream, const ShardExchange* xch = nullptr) {
   using namespace bjx;
   BJX_REQUIRE(args != nullptr && params_flat && adam_m && adam_v && steps_done, "null pointer");
   BJX_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
@@ -985,9 +991,13 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
       if (rc) return rc;
     }
     bool finished = false;
-    rc = run_step(a, p, st, &tt, &finished);
+    rc = run_step(a, p, st, xch ? nullptr : &tt, &finished);
     if (rc) return rc;
     if (finished) continue;  // the step kernel did Adam and the bookkeeping itself
+    if (xch) {  // every rank ends up with the same bits in a.out, so the replicated Adam states stay identical
+      rc = bjx_allreduce_packed_p2p_dev(a.out, 1 + n, xch->bufs_host, xch->rank, xch->world, xch->epoch_base, steps_done, stream);
+      if (rc) return rc;
+    }
     if (n <= 1024) {
       k_adam_bump_small<<<1, 1024, 0, st>>>(tt, a.out);
       BJX_LAUNCH_CHECK("k_adam_bump_small");
@@ -1004,6 +1014,15 @@ static int train_steps_impl(const BjxElboArgs* args, const BjxMinibatch* mb, int
 int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
                     double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses, void* stream) {
   return train_steps_impl(args, nullptr, n_steps, params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, stream);
+}
+
+int bjx_train_steps_sharded(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, double lr,
+                            double b1, double b2, double eps, int64_t* steps_done, float* losses, void* const* p2p_bufs_host,
+                            int32_t rank, int32_t world, uint64_t epoch_base, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(p2p_bufs_host != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad exchange arguments");
+  const ShardExchange xch{p2p_bufs_host, rank, world, epoch_base};
+  return train_steps_impl(args, nullptr, n_steps, params_flat, adam_m, adam_v, lr, b1, b2, eps, steps_done, losses, stream, &xch);
 }
 
 int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, int64_t n_steps, float* params_flat, float* adam_m,

@@ -7,6 +7,7 @@
 // Buffer of one rank:  slots[2][world][n_pad] floats  |  flags[2][world] uint64 (the epoch that filled the slot)
 // Two slot sets alternate by epoch parity.  A rank can start epoch e+1 (writing set (e+1)&1) while a peer still reads set
 // e&1, and it cannot reach epoch e+2 before every peer has signalled e+1, i.e. has finished reading set e&1.
+#include <cstdio>
 #include <cstring>
 
 #include "bjx_common.cuh"
@@ -26,8 +27,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(1024) k_allreduce_p2p(float* __restrict__ out, int64_t n, int64_t n_pad, P2PPeers peers, int rank,
-                                                        int world, unsigned long long epoch) {
+// A dead or hung peer must not hang this rank forever: the flag wait gives up after g_timeout_ns (default 30 s) and traps,
+// which surfaces on the host as a launch failure of this stream at the next synchronisation (BJX_ERR_CUDA from then on).
+__device__ unsigned long long g_p2p_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// push -> flag -> wait -> rank-ordered sum, by ONE block of 1024 threads; result in out[0..n) on every rank
+__device__ __forceinline__ void allreduce_p2p_block(float* __restrict__ out, int64_t n, int64_t n_pad, const P2PPeers& peers, int rank,
+                                                    int world, unsigned long long epoch) {
   const int tid = threadIdx.x;
   const int set = (int)(epoch & 1ull);
   const size_t slot_floats = (size_t)n_pad;
@@ -46,7 +58,13 @@ __global__ void __launch_bounds__(1024) k_allreduce_p2p(float* __restrict__ out,
   // 3. wait for every rank's slot in MY buffer
   if (tid < world) {
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(peers.buf[rank] + (size_t)2 * world * slot_floats);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(flags + (size_t)set * world + tid) != epoch) {
+      if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > g_p2p_timeout_ns) {
+        printf("bjx: peer-memory all-reduce timed out on rank %d waiting for rank %d at epoch %llu\n", rank, tid, epoch);
+        __trap();
+      }
     }
   }
   __syncthreads();
@@ -57,6 +75,19 @@ __global__ void __launch_bounds__(1024) k_allreduce_p2p(float* __restrict__ out,
     for (int p = 0; p < world; ++p) acc += __ldcv(mine + (size_t)p * slot_floats + i);
     out[i] = acc;
   }
+}
+
+__global__ void __launch_bounds__(1024) k_allreduce_p2p(float* __restrict__ out, int64_t n, int64_t n_pad, P2PPeers peers, int rank,
+                                                        int world, unsigned long long epoch) {
+  allreduce_p2p_block(out, n, n_pad, peers, rank, world, epoch);
+}
+
+// The exchange step of a device-resident training step (bjx_train_steps_sharded): the epoch comes from the DEVICE step
+// counter (epoch_base + *steps_done + 1), so a captured CUDA graph of whole training steps replays without updates.
+__global__ void __launch_bounds__(1024) k_allreduce_p2p_dev(float* __restrict__ out, int64_t n, int64_t n_pad, P2PPeers peers,
+                                                            int rank, int world, unsigned long long epoch_base,
+                                                            const int64_t* __restrict__ steps_done) {
+  allreduce_p2p_block(out, n, n_pad, peers, rank, world, epoch_base + (unsigned long long)(*steps_done) + 1ull);
 }
 
 static int64_t pad_floats(int64_t n) { return (n + 63) / 64 * 64; }
@@ -118,6 +149,29 @@ int bjx_allreduce_packed_p2p(float* out, int64_t n, void* const* bufs_host, int3
   for (int p = 0; p < 8; ++p) peers.buf[p] = p < world ? (float*)bufs_host[p] : nullptr;
   k_allreduce_p2p<<<1, 1024, 0, (cudaStream_t)stream>>>(out, n, pad_floats(n), peers, rank, world, (unsigned long long)epoch);
   BJX_LAUNCH_CHECK("k_allreduce_p2p");
+  return BJX_OK;
+}
+
+// The same exchange with the epoch taken from a device-resident step counter: epoch = epoch_base + *steps_done + 1.
+int bjx_allreduce_packed_p2p_dev(float* out, int64_t n, void* const* bufs_host, int32_t rank, int32_t world, uint64_t epoch_base,
+                                 const int64_t* steps_done, void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(out && bufs_host && steps_done && n >= 1, "bad arguments");
+  BJX_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8 and rank inside it");
+  P2PPeers peers;
+  for (int p = 0; p < 8; ++p) peers.buf[p] = p < world ? (float*)bufs_host[p] : nullptr;
+  k_allreduce_p2p_dev<<<1, 1024, 0, (cudaStream_t)stream>>>(out, n, pad_floats(n), peers, rank, world, (unsigned long long)epoch_base,
+                                                            steps_done);
+  BJX_LAUNCH_CHECK("k_allreduce_p2p_dev");
+  return BJX_OK;
+}
+
+// how long a rank waits for a peer's flag before it traps (0 restores the default of 30 s)
+int bjx_p2p_set_timeout_ms(int64_t ms) {
+  using namespace bjx;
+  BJX_REQUIRE(ms >= 0, "timeout must be >= 0");
+  const unsigned long long ns = ms == 0 ? 30ull * 1000ull * 1000ull * 1000ull : (unsigned long long)ms * 1000000ull;
+  BJX_CUDA_TRY(cudaMemcpyToSymbol(g_p2p_timeout_ns, &ns, sizeof(ns)));
   return BJX_OK;
 }
 

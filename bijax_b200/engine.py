@@ -355,15 +355,18 @@ class ElboEngine:
         return out
 
     def train_steps(self, keys, n_steps, params_flat, adam_m, adam_v, hyper, steps_done, losses, out, X, y, ll_scale,
-                    n_samples, partitionable=None, minibatch=None):
+                    n_samples, partitionable=None, minibatch=None, prior_weight=1.0, exchange=None):
         """Enqueue ``n_steps`` whole training steps (ELBO + gradients -> Adam -> loss record) with no host round trip
         (bjx_train_steps; train_fn's scan body, utils.py:22-28).  ``keys`` is the [n, 2] uint32 array of per-step keys,
         ``steps_done`` a device int64 counter, ``params_flat`` = [loc | raw_scale | kwargs] updated in place.
         ``minibatch``: the state of a MinibatchLoss (batch buffers + BjxMinibatch) -- every step first draws a fresh batch
-        (bjx_train_steps_minibatch); X / y are then its batch buffers, or the full X read through its index."""
+        (bjx_train_steps_minibatch); X / y are then its batch buffers, or the full X read through its index.
+        ``exchange``: a parallel.P2PAllReduce -- X / y are this rank's ROW SHARD, ``ll_scale`` uses the global length,
+        ``prior_weight`` is 1 on one rank, and every step sums the packed output over the ranks on the device before Adam
+        (bjx_train_steps_sharded); the caller advances ``exchange.epoch`` by the steps it enqueued."""
         indexed = minibatch is not None and minibatch["indexed"]
         X, y, N, ldx = self._data(X, y, indexed=indexed)
-        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, 1.0, brandom._layout(partitionable))
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
         assert keys.dtype == torch.uint32 and keys.is_cuda and keys.is_contiguous()
         assert params_flat.numel() == self.D + self.P + self.K and params_flat.is_contiguous()
         a.key = keys.data_ptr()
@@ -385,6 +388,13 @@ class ElboEngine:
                 nv.check(self.lib.bjx_train_steps_minibatch(C.byref(a), C.byref(minibatch["mb"]), int(n_steps), params_flat.data_ptr(),
                                                             adam_m.data_ptr(), adam_v.data_ptr(), lr, b1, b2, eps, steps_done.data_ptr(),
                                                             losses.data_ptr() if losses is not None else None, nv.current_stream_ptr()))
+            return
+        if exchange is not None:
+            assert exchange.n == out.numel(), "the exchange buffer must be sized for the packed step output"
+            with torch.cuda.device(self.device):
+                nv.check(self.lib.bjx_train_steps_sharded(C.byref(a), int(n_steps), params_flat.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),
+                                                          lr, b1, b2, eps, steps_done.data_ptr(), losses.data_ptr() if losses is not None else None,
+                                                          exchange._ptrs, exchange.rank, exchange.world, exchange.epoch, nv.current_stream_ptr()))
             return
         with torch.cuda.device(self.device):
             nv.check(self.lib.bjx_train_steps(C.byref(a), int(n_steps), params_flat.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr(),

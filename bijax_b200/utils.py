@@ -32,7 +32,8 @@ GRAPH_STEPS = 16  # training steps per captured CUDA graph in the device-residen
 def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
     """(model, call kwargs) if this train_fn call can run as the device-resident loop: loss_fn is
     functools.partial(model.loss_fn, outputs=..., inputs=..., full_data_size=..., n_samples=...), the optimiser is
-    optim.adam, a seed is given, nothing per-step is asked back, and the model is not row-sharded."""
+    optim.adam, a seed is given, nothing per-step is asked back, and the model is either on one device or row-sharded with
+    the peer-memory exchange (model.distributed(shard="rows", p2p=True): the all-reduce then runs on the device too)."""
     import functools
 
     if seed is None or return_args or getattr(optimizer, "hyper", None) is None:
@@ -52,8 +53,10 @@ def _fused_loop_spec(loss_fn, optimizer, seed, return_args):
     kw = dict(loss_fn.keywords)
     if not {"outputs", "inputs", "full_data_size"} <= set(kw) or set(kw) - {"outputs", "inputs", "full_data_size", "n_samples"}:
         return None
-    if getattr(model, "_group", None) is not None or getattr(model, "packed_tril", False):
+    if getattr(model, "packed_tril", False):
         return None
+    if getattr(model, "_group", None) is not None and not (getattr(model, "_shard", "rows") == "rows" and getattr(model, "_p2p", False)):
+        return None  # NCCL exchange or sample sharding: host-driven step + all-reduce
     return model, kw
 
 
@@ -78,6 +81,11 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
             X = inputs[engine.x_name] if isinstance(inputs, dict) else inputs
     ll_scale = float(kw["full_data_size"]) / float(len(outputs))  # advi.py:92
     S = int(kw.get("n_samples", 1))
+    prior_weight, exchange = 1.0, None
+    if getattr(model, "_group", None) is not None:
+        # row-sharded: len(outputs) of advi.py:92 is the GLOBAL length, the q / prior terms are counted on one rank, and the
+        # packed [loss | grads] buffer is summed over the ranks by the peer-memory kernel inside every device-resident step
+        ll_scale, prior_weight, exchange = model._shard_context(engine, len(outputs), float(kw["full_data_size"]))
     if mb_state is None:
         # normalise the dataset ONCE (device, fp32, dense columns): the warm-up step, the captured steps and the trailing
         # eager steps must all see the same persistent tensors -- a conversion inside capture would allocate from the
@@ -89,12 +97,15 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
     out = torch.empty(1 + flat.numel(), dtype=torch.float32, device=dev)
 
     def enqueue(n, flat_, m_, v_, done_, losses_):
-        engine.train_steps(keys, n, flat_, m_, v_, optimizer.hyper, done_, losses_, out, X, outputs, ll_scale, S, minibatch=mb_state)
+        engine.train_steps(keys, n, flat_, m_, v_, optimizer.hyper, done_, losses_, out, X, outputs, ll_scale, S, minibatch=mb_state,
+                           prior_weight=prior_weight, exchange=exchange)
 
     n_graphs, rest = divmod(n_epochs, GRAPH_STEPS)
     if n_graphs >= 2:
         # warm up on scratch state (first-use attribute calls, workspace and dataset preparation), then capture once
         enqueue(1, flat.clone(), m.clone(), v.clone(), done.clone(), None)
+        if exchange is not None:
+            exchange.epoch += 1  # the warm-up step used one epoch of the exchange (its scratch counter read 0)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
@@ -110,6 +121,10 @@ def _train_fused(model, kw, params, optimizer, n_epochs, seed):
         rest = n_epochs
     if rest:
         enqueue(rest, flat, m, v, done, losses)
+    if exchange is not None:
+        # the device used epochs epoch_base + 1 .. epoch_base + n_epochs (epoch_base is a launch constant, the step counter is
+        # on the device); keep the host-side counter of the exchange in step for whatever uses it next
+        exchange.epoch += n_epochs
     # back to the caller's pytree
     D, P = engine.D, engine.P
     key = next(k for k in ("posterior", "approx_posterior") if k in params)

@@ -255,8 +255,7 @@ BJX_API int bjx_adam_update(float* params, float* m, float* v, const float* grad
  * replayed as is, because the step number (bias correction, key index, loss slot) lives in `steps_done` on the device.
  * params_flat = [loc (D) | raw_scale (P) | kwargs (K)] (args->loc / raw_scale / kwargs are ignored), adam_m / adam_v the
  * optax.adam moments (zero-initialised), args->key the [n, 2] key array, args->out the packed step output (scratch),
- * losses (optional) at least as long as the total number of steps.  Single device: under row sharding run
- * bjx_elbo_step + the all-reduce + bjx_adam_update from the host instead. */
+ * losses (optional) at least as long as the total number of steps.  Single device; bjx_train_steps_sharded is the row-sharded form. */
 BJX_API int bjx_train_steps(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v, double lr,
                     double b1, double b2, double eps, int64_t* steps_done, float* losses, void* stream);
 
@@ -308,6 +307,23 @@ BJX_API int bjx_p2p_close(void* peer_ptr);
 BJX_API int bjx_p2p_free(void* own_ptr);
 BJX_API int bjx_allreduce_packed_p2p(float* out, int64_t n, void* const* bufs_host, int32_t rank, int32_t world, uint64_t epoch,
                              void* stream);
+
+/* The same exchange with the epoch read from a DEVICE step counter (epoch = epoch_base + *steps_done + 1): what a captured
+ * CUDA graph of whole training steps needs (ABI 4). */
+BJX_API int bjx_allreduce_packed_p2p_dev(float* out, int64_t n, void* const* bufs_host, int32_t rank, int32_t world,
+                                         uint64_t epoch_base, const int64_t* steps_done, void* stream);
+/* A rank waiting for a peer's flag gives up after this long (default 30 s; 0 restores it), prints the rank it waited for and
+ * traps: the stream then reports a launch failure instead of hanging on a dead peer (ABI 4). */
+BJX_API int bjx_p2p_set_timeout_ms(int64_t ms);
+
+/* bjx_train_steps under ROW SHARDING (the scan of utils.py:22-31 as one device-resident executable on every
+ * rank): per step { ELBO + gradients of this rank's rows at key[*steps_done] (args->prior_weight = 1 on one rank, ll_scale from the
+ * GLOBAL length) -> bjx_allreduce_packed_p2p_dev of the packed [loss | grads] buffer -> Adam on the replicated params_flat ->
+ * losses[*steps_done], ++*steps_done }.  Every rank computes the same reduced bits, so the replicated parameters and moments never
+ * diverge.  The caller advances its own epoch counter by the number of steps enqueued (epoch_base + total steps).  ABI 4. */
+BJX_API int bjx_train_steps_sharded(const BjxElboArgs* args, int64_t n_steps, float* params_flat, float* adam_m, float* adam_v,
+                                    double lr, double b1, double b2, double eps, int64_t* steps_done, float* losses,
+                                    void* const* p2p_bufs_host, int32_t rank, int32_t world, uint64_t epoch_base, void* stream);
 
 /* ---- in-library timing of the dominant (streaming likelihood) kernel -------
  * bjx_profile_begin(capacity): from now on every bjx_elbo_step on this thread records a CUDA event pair around its

@@ -314,3 +314,40 @@ def test_device_resident_loop_captures_the_two_pass_tensor_core_path():
     host = bj.train(loss_fn, fresh(), optim.adam(0.02), n_epochs=36, seed=br.PRNGKey(3), fused=False)
     assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-4)
     assert torch.allclose(fused["params"]["posterior"]["loc"], host["params"]["posterior"]["loc"], rtol=1e-4, atol=2e-5)
+
+
+def test_row_sharded_device_resident_loop_on_a_world_of_one(tmp_path):
+    """bjx_train_steps_sharded (ELBO -> peer-memory all-reduce with the epoch read from the device step counter -> Adam, in
+    replayed CUDA graphs): on a world of one the exchange is the identity, so the trajectory must equal the single-device
+    loop bit for bit, and the exchange's epoch counter must have advanced by one per step.  (Two ranks:
+    scripts/multi_gpu_train_check.py under torchrun; tests/test_multi_gpu.py runs it when the box has two GPUs.)"""
+    import torch.distributed as dist
+    from functools import partial
+    from tests import cases as C
+
+    N, D, S = 4096, 128, 8
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+
+    def run(sharded):
+        model = bj.ADVI(prior, {}, lk.BernoulliLogits())
+        if sharded:
+            model.distributed(shard="rows", p2p=True)
+        params = model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.01 * br.normal(k, shape))
+        loss_fn = partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=S)
+        n = 2 * U.GRAPH_STEPS + 3
+        res = bj.train(loss_fn, params, optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
+        return model, res, n
+
+    _, single, n = run(False)
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        model, sharded, _ = run(True)
+        assert model._p2p_op is not None and model._p2p_op.epoch == n + 1  # + the warm-up step before capture
+        assert torch.equal(single["losses"], sharded["losses"])
+        for k in ("loc", "scale_diag"):
+            assert torch.equal(single["params"]["posterior"][k], sharded["params"]["posterior"][k])
+        model._p2p_op.close()
+    finally:
+        dist.destroy_process_group()
