@@ -497,7 +497,7 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 template <int NBLK, int EW>  // D / 64; epilogue warps (8 or 16)
 __global__ void __launch_bounds__((tcp::EPI_WARP0 + EW) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
-             int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int S, int family,
+             int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
              long long* __restrict__ trace) {
 #define BJX_TRACE(it_, slot_)                                                                 \
@@ -560,7 +560,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const int s = idx / (D / 8), d8 = idx % (D / 8);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = s < S ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
+    for (int j = 0; j < 8; ++j) v[j] = (s < S && d8 * 8 + j < Dw) ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
     uint32_t p1[4], p2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], p1[j], p2[j]);
@@ -579,7 +579,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   if (warp == tcp::PROD_WARP) {
     // ===================================================== TMA producer ================================================
     const __nv_bfloat16* p1 = planes;
-    const __nv_bfloat16* p2 = planes + (size_t)N * D;
+    const __nv_bfloat16* p2 = planes + (size_t)N * Dp;  // Dp = columns of a plane (Dw padded to 64); blocks beyond it are TMA zero fill
     const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them
     const int pf_dist = pf_tiles & 255;
     if (lane == 0) {
@@ -602,9 +602,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
           const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * TILE_ROWS;
           const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
-          const uint32_t bytes = (uint32_t)(rows * D * 2);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * D), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * D), "r"(bytes) : "memory");
+          const uint32_t bytes = (uint32_t)(rows * Dp * 2);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
         };
         if (pf_mode == 0 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
         if constexpr (RING) {
@@ -761,7 +761,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     }
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
     const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
-    float* gp = Gpart + (size_t)blockIdx.x * S * D;
+    float* gp = Gpart + (size_t)blockIdx.x * S * Dw;  // the partial keeps the caller's [S, Dw] layout (Dw <= D = NBLK * 64)
     // The GEMM2 accumulators are folded every few tiles (the tensor core's fp32 accumulate truncates) into an fp32 partial
     // that lives in the 128 TMEM columns left over ([384, 512): 4 chunks x 32 samples, lane = weight column): registers
     // add, tcgen05.st writes back -- no global-memory traffic until the single store at the end of the kernel.
@@ -782,10 +782,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           fp[j] = __float_as_uint(val);
         }
         if (final) {
-          float* base = gp + (size_t)sb * D + ch * 128 + 32 * q + lane;
+          const int d = ch * 128 + 32 * q + lane;
+          float* base = gp + (size_t)sb * Dw + d;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (sb + j < S) __stcg(base + (size_t)j * D, __uint_as_float(fp[j]));
+            if (sb + j < S && d < Dw) __stcg(base + (size_t)j * Dw, __uint_as_float(fp[j]));
         } else {
           tmem_st8(t_lane + PART_COL + ch * NS + sb, fp);
         }
@@ -937,7 +938,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     if (my_tiles > 0) {
       for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, !((flushed >> ch) & 1u), true);
     } else {
-      for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * D; i += EW * 32) gp[i] = 0.0f;
+      for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * Dw; i += EW * 32) gp[i] = 0.0f;
     }
   }
 
@@ -959,12 +960,23 @@ static size_t tc_smem_bytes(int nblk) {
   return (size_t)(3 * nblk + 1) * tc::BLK_BYTES + sizeof(tc::Bars) + 4 * tc::NS * sizeof(float) + 1024;
 }
 
+static int64_t pad64(int64_t v) { return (v + 63) / 64 * 64; }
+// columns are a multiple of 128 in [128, 512]: both variants of the kernel apply (raw fp32 X or prepared planes)
+static bool tc_exact_width(const BjxElboArgs& a) { return a.Dw >= 128 && a.Dw <= 512 && a.Dw % 128 == 0; }
+
 bool tc_eligible(const BjxElboArgs& a) {
   if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
-  if (a.Dw < 128 || a.Dw > 512 || a.Dw % 128 != 0) return false;
   if (a.S < 1 || a.S > tc::NS) return false;
-  if (a.ldx % 4 != 0 || ((uintptr_t)a.X & 15) != 0) return false;  // 128-bit row loads
-  if (a.precision == BJX_PREC_BF16X3) return false;                // the three-term split runs on the two-pass GEMM path
+  if (a.precision == BJX_PREC_BF16X3) return false;  // the three-term split runs on the two-pass GEMM path
+  if (tc_exact_width(a)) {
+    if (a.x_planes == nullptr && (a.ldx % 4 != 0 || ((uintptr_t)a.X & 15) != 0)) return false;  // 128-bit row loads of raw X
+    return true;
+  }
+  // Any other width in [16, 512] runs on the TMA-fed variant over the split-bf16 planes (columns padded to 64 by
+  // bjx_prepare_x_planes): the kernel is instantiated for the next even number of 64-column blocks, and the blocks beyond
+  // the plane's extent are zero-filled by the copy engine (out-of-bounds TMA boxes cost no HBM traffic).  The raw-fp32 /
+  // row-index variant has no such fill, so a step without prepared planes splits X into the workspace first.
+  if (a.Dw < 16 || a.Dw > 512 || a.row_index != nullptr) return false;
   return true;
 }
 
@@ -979,7 +991,10 @@ int tc_plan(const BjxElboArgs& a, Plan& p) {
   return BJX_OK;
 }
 
-size_t tc_theta_bytes(const BjxElboArgs&, const Plan&) { return 0; }
+// workspace for the operand planes when a width outside {128, 256, 384, 512} arrives without prepared planes
+size_t tc_theta_bytes(const BjxElboArgs& a, const Plan&) {
+  return (!tc_exact_width(a) && a.x_planes == nullptr) ? x_planes_bytes(a.N, a.Dw) : 0;
+}
 
 int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
   static bool env_read = false;
@@ -994,9 +1009,16 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
   const float* theta = (const float*)(ws + p.o_theta);
   float* Gpart = (float*)(ws + p.o_Gpart);
   float* statpart = (float*)(ws + p.o_statpart);
-  const int nblk = (int)(a.Dw / tc::BLK_COLS);
+  const int64_t Dp = pad64(a.Dw);
+  const int nblk = (int)(((Dp / tc::BLK_COLS) + 1) & ~1ll);  // even: GEMM2 works on 128-column chunks
   const size_t smem = tc_smem_bytes(nblk);
-  if (a.x_planes != nullptr) {
+  const void* x_planes = a.x_planes;
+  if (x_planes == nullptr && !tc_exact_width(a)) {
+    int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, ws + p.o_tc_theta, st);
+    if (rc) return rc;
+    x_planes = ws + p.o_tc_theta;
+  }
+  if (x_planes != nullptr) {
     // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
     const int nslot = 8 / nblk > 1 ? 8 : nblk;  // D = 128, 256: the eight slots are a ring of tiles (see the kernel)
     const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 +
@@ -1010,17 +1032,17 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     // the raw-fp32 variant (bias of the truncating accumulate ~0.9e-6 instead of 1.7e-6)
     const int flush_tma = getenv("BJX_TC_FLUSH") ? g_flush : 8;
     tcp::Maps maps;
-    const __nv_bfloat16* planes = (const __nv_bfloat16*)a.x_planes;
+    const __nv_bfloat16* planes = (const __nv_bfloat16*)x_planes;
     int rc;
-    if ((rc = make_bf16_tensor_map(&maps.x1, planes, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
-    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * a.Dw, a.N, a.Dw, a.Dw, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x1, planes, a.N, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * Dp, a.N, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
 #define BJX_TCP_LAUNCH(NBLK, EW)                                                                                              \
   do {                                                                                                                    \
     static DeviceOnce attr_set;                                                                                         \
     if (!attr_set.test_and_set()) {                                                                                                      \
       BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK, EW><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.S, \
+    k_lik_tc_tma<NBLK, EW><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
                                                               a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace); \
   } while (0)
     // Epilogue warps: eight everywhere except D = 128 with the Bernoulli-logit link, where the tile is so short that the

@@ -323,6 +323,8 @@ def test_row_sharded_device_resident_loop_on_a_world_of_one(tmp_path):
     scripts/multi_gpu_train_check.py under torchrun; tests/test_multi_gpu.py runs it when the box has two GPUs.)"""
     import torch.distributed as dist
     from functools import partial
+    from bijax_b200 import random as br
+    from bijax_b200 import utils as U
     from tests import cases as C
 
     N, D, S = 4096, 128, 8

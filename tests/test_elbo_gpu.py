@@ -235,7 +235,10 @@ def test_error_paths():
     "N,D,S,lik",
     [(64, 128, 32, "logit"), (1, 128, 32, "logit"), (65, 256, 16, "logit"), (1000, 512, 32, "logit"),
      (20000, 512, 32, "logit"), (5000, 384, 7, "gauss"), (12345, 256, 32, "gauss"),
-     (40000, 128, 32, "logit"), (30000, 384, 20, "gauss"), (50000, 256, 32, "logit")],  # several tiles per CTA for every block count
+     (40000, 128, 32, "logit"), (30000, 384, 20, "gauss"), (50000, 256, 32, "logit"),  # several tiles per CTA for every block count
+     # widths that are not a multiple of 128: planes padded to 64 columns, the missing blocks are TMA zero fill
+     (20000, 500, 32, "logit"), (3000, 16, 32, "gauss"), (9000, 50, 5, "logit"), (4097, 64, 32, "logit"), (12000, 100, 17, "gauss"),
+     (30000, 200, 32, "logit"), (25000, 320, 32, "gauss"), (15000, 448, 9, "logit"), (777, 511, 32, "gauss"), (20000, 129, 32, "logit")],
 )
 @pytest.mark.parametrize("prepared", [True, False])
 def test_tensor_core_path(N, D, S, lik, prepared):
