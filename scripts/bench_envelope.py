@@ -12,7 +12,7 @@ peak = json.load(open("MEASURED_PEAKS.json")).get("hbm_gbs") if os.path.exists("
 GB = float(os.environ.get("ENV_GB", 10))
 res = []
 keys = br.split(br.PRNGKey(0), 64)
-for D in (128, 256, 384, 512):
+for D in tuple(int(v) for v in os.environ.get("ENV_D", "128,256,384,512").split(",")):
     N = int(GB * 1e9 / (4 * D)) // 64 * 64
     X = br.normal(br.PRNGKey(1234), (N, D), partitionable=True); X.mul_(1 / math.sqrt(D))
     w = br.normal(br.PRNGKey(1235), (D,), partitionable=True)
