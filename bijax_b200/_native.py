@@ -111,6 +111,7 @@ class BjxElboArgs(C.Structure):
         ("reserved3", C.c_int32),
         ("rank", C.c_int64),
         ("row_index", C.c_void_p),
+        ("N_full", C.c_int64),
     ]
 
 

@@ -132,8 +132,9 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
   }
 
   if (a.row_index != nullptr) {
-    if (p.kernel != KERNEL_TC_BF16 || a.x_planes != nullptr || a.N < 1)
-      return fail(BJX_ERR_UNSUPPORTED, "row_index: only the fused tcgen05 kernel on raw fp32 X reads through an index; gather the rows instead");
+    if (p.kernel != KERNEL_TC_BF16 || a.N < 1 || (a.x_planes != nullptr && a.N_full < 1))
+      return fail(BJX_ERR_UNSUPPORTED, "row_index: only the fused tcgen05 kernel reads through an index (raw fp32 X, or x_planes of the "
+                                       "full dataset together with N_full); gather the rows instead");
   }
   p.Pn = a.vi_type == BJX_VI_MEAN_FIELD ? a.D : (a.vi_type == BJX_VI_FULL_RANK ? a.D * a.D : a.D + a.D * a.rank);
   p.n_qp_blocks = (int)((a.S * a.D + 255) / 256);
@@ -876,7 +877,7 @@ int bjx_elbo_supports_row_index(const BjxElboArgs* args) {
   BjxElboArgs a = *args;
   static const int32_t dummy = 0;
   if (a.row_index == nullptr) a.row_index = &dummy;
-  a.x_planes = nullptr;
+  if (a.x_planes == nullptr) a.N_full = 0;  // asked for the raw-fp32 route
   Plan p;
   return make_plan(a, p) == BJX_OK ? 1 : 0;
 }

@@ -494,12 +494,15 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 };
 }  // namespace tcp
 
-template <int NBLK, int EW>  // D / 64; epilogue warps (8 or 16)
+// IDX: row r of the problem is row ridx[r] of the planes (a minibatch drawn on the device, BjxElboArgs.row_index + x_planes +
+// N_full): the producer warp gathers the batch's rows straight out of the FULL dataset's planes with tile::gather4 TMA loads
+// (four rows per instruction, sixteen lanes x two planes per 64-row block), so a batch costs one pass over its own rows.
+template <int NBLK, int EW, bool IDX>  // D / 64; epilogue warps (8 or 16)
 __global__ void __launch_bounds__((tcp::EPI_WARP0 + EW) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
-             long long* __restrict__ trace) {
+             long long* __restrict__ trace, const int32_t* __restrict__ ridx) {
 #define BJX_TRACE(it_, slot_)                                                                 \
   do {                                                                                        \
     if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
@@ -578,59 +581,112 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 
   if (warp == tcp::PROD_WARP) {
     // ===================================================== TMA producer ================================================
-    const __nv_bfloat16* p1 = planes;
-    const __nv_bfloat16* p2 = planes + (size_t)N * Dp;  // Dp = columns of a plane (Dw padded to 64); blocks beyond it are TMA zero fill
-    const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them
-    const int pf_dist = pf_tiles & 255;
-    if (lane == 0) {
-      auto issue_block0 = [&](int64_t t) {
-        const int alt = (int)(t & 1);
-        const int idx = alt ? 8 : 0;
-        const int64_t row0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
-        mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));  // released by chunk 0 of GEMM2 two tiles ago
-        BJX_TRACE(t, 0);
-        mbar_expect_tx(&bars->x_full[idx], 2u * BLK_BYTES);
-        uint8_t* slot = alt ? sx - SLOT : sx;
-        tma_load_2d(slot, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
-        tma_load_2d(slot + BLK_BYTES, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
+    if constexpr (IDX) {
+      // gather variant: lane j < 16 owns rows 4j .. 4j+3 of every tile (their indices live in its registers, loaded one tile
+      // ahead); per block the warp posts the byte count once and the sixteen lanes issue one gather4 per plane each.  Rows
+      // past N read row 0 of the dataset: the epilogue zeroes their g, so they contribute nothing to either GEMM's result.
+      const bool issuer = lane < 16;
+      auto load_idx = [&](int64_t t, int32_t(&v)[4]) {
+        const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS + 4 * lane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (issuer && t < my_tiles && r0 + i < N) ? __ldg(ridx + r0 + i) : 0;
       };
-      const int pf_ahead = pf_dist * R;  // the same distance in bytes for every D
-      if (!RING && my_tiles > 0) issue_block0(0);
+      auto issue = [&](uint8_t* slot, unsigned long long* bar, int b, const int32_t(&v)[4]) {
+        if (lane == 0) mbar_expect_tx(bar, 2u * BLK_BYTES);
+        __syncwarp();
+        if (issuer) {
+          tma_gather4_2d(slot + 512 * lane, &maps.x1, b * BLK_COLS, v[0], v[1], v[2], v[3], bar);
+          tma_gather4_2d(slot + BLK_BYTES + 512 * lane, &maps.x2, b * BLK_COLS, v[0], v[1], v[2], v[3], bar);
+        }
+      };
+      int32_t cur[4], nxt[4];
+      load_idx(0, cur);
+      load_idx(1, nxt);
+      if (!RING && my_tiles > 0) {
+        mbar_wait(&bars->x_empty[0], 1u);
+        issue(sx, &bars->x_full[0], 0, cur);
+      }
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
-        auto bulk_pf = [&]() {
-          // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
-          const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * TILE_ROWS;
-          const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
-          const uint32_t bytes = (uint32_t)(rows * Dp * 2);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
-        };
-        if (pf_mode == 0 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
         if constexpr (RING) {
           const int q0 = (int)(it % R) * NBLK;
           const uint32_t use = (uint32_t)((it / R) & 1);
           for (int b = 0; b < NBLK; ++b) {
             const int q = q0 + b;
-            mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
-            BJX_TRACE(it, b);
-            mbar_expect_tx(&bars->x_full[q], 2u * BLK_BYTES);
-            tma_load_2d(sx + q * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
-            tma_load_2d(sx + q * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+            mbar_wait(&bars->x_empty[q], use ^ 1);
+            issue(sx + q * SLOT, &bars->x_full[q], b, cur);
           }
         } else {
           for (int b = 1; b < NBLK; ++b) {
-            mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
-            BJX_TRACE(it, b);
-            mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
-            tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-            tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-            // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue
-            // it now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
-            if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
+            mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));
+            issue(sx + b * SLOT, &bars->x_full[b], b, cur);
+            if (b == 1 && it + 1 < my_tiles) {  // block 0 of the next tile into the other block-0 slot (see below)
+              const int64_t t = it + 1;
+              const int alt = (int)(t & 1);
+              const int idx = alt ? 8 : 0;
+              mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));
+              issue(alt ? sx - SLOT : sx, &bars->x_full[idx], 0, nxt);
+            }
           }
         }
-        if (pf_mode == 1 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        load_idx(it + 2, nxt);
+      }
+    } else {
+      const __nv_bfloat16* p1 = planes;
+      const __nv_bfloat16* p2 = planes + (size_t)N * Dp;  // Dp = columns of a plane (Dw padded to 64); blocks beyond it are TMA zero fill
+      const int pf_mode = pf_tiles >> 8;  // development switch: 0 bulk prefetch before the tile's loads, 1 after them
+      const int pf_dist = pf_tiles & 255;
+      if (lane == 0) {
+        auto issue_block0 = [&](int64_t t) {
+          const int alt = (int)(t & 1);
+          const int idx = alt ? 8 : 0;
+          const int64_t row0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
+          mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));  // released by chunk 0 of GEMM2 two tiles ago
+          BJX_TRACE(t, 0);
+          mbar_expect_tx(&bars->x_full[idx], 2u * BLK_BYTES);
+          uint8_t* slot = alt ? sx - SLOT : sx;
+          tma_load_2d(slot, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
+          tma_load_2d(slot + BLK_BYTES, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
+        };
+        const int pf_ahead = pf_dist * R;  // the same distance in bytes for every D
+        if (!RING && my_tiles > 0) issue_block0(0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+          const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
+          auto bulk_pf = [&]() {
+            // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
+            const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * TILE_ROWS;
+            const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
+            const uint32_t bytes = (uint32_t)(rows * Dp * 2);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
+          };
+          if (pf_mode == 0 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
+          if constexpr (RING) {
+            const int q0 = (int)(it % R) * NBLK;
+            const uint32_t use = (uint32_t)((it / R) & 1);
+            for (int b = 0; b < NBLK; ++b) {
+              const int q = q0 + b;
+              mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
+              BJX_TRACE(it, b);
+              mbar_expect_tx(&bars->x_full[q], 2u * BLK_BYTES);
+              tma_load_2d(sx + q * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+              tma_load_2d(sx + q * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+            }
+          } else {
+            for (int b = 1; b < NBLK; ++b) {
+              mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
+              BJX_TRACE(it, b);
+              mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
+              tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+              tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+              // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue
+              // it now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
+              if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
+            }
+          }
+          if (pf_mode == 1 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
+        }
       }
     }
   } else if (warp == tcp::MMA_WARP) {
@@ -968,6 +1024,9 @@ bool tc_eligible(const BjxElboArgs& a) {
   if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
   if (a.S < 1 || a.S > tc::NS) return false;
   if (a.precision == BJX_PREC_BF16X3) return false;  // the three-term split runs on the two-pass GEMM path
+  // rows read through an index (minibatches): either the register-converting kernel on raw fp32 X, or -- with the FULL
+  // dataset's planes and its row count -- the TMA-fed kernel gathering plane rows (tile::gather4)
+  if (a.row_index != nullptr && a.x_planes != nullptr && a.N_full < 1) return false;
   if (tc_exact_width(a)) {
     if (a.x_planes == nullptr && (a.ldx % 4 != 0 || ((uintptr_t)a.X & 15) != 0)) return false;  // 128-bit row loads of raw X
     return true;
@@ -976,7 +1035,8 @@ bool tc_eligible(const BjxElboArgs& a) {
   // bjx_prepare_x_planes): the kernel is instantiated for the next even number of 64-column blocks, and the blocks beyond
   // the plane's extent are zero-filled by the copy engine (out-of-bounds TMA boxes cost no HBM traffic).  The raw-fp32 /
   // row-index variant has no such fill, so a step without prepared planes splits X into the workspace first.
-  if (a.Dw < 16 || a.Dw > 512 || a.row_index != nullptr) return false;
+  if (a.Dw < 16 || a.Dw > 512) return false;
+  if (a.row_index != nullptr && a.x_planes == nullptr) return false;  // no planes to gather from, and no in-step split of a full dataset
   return true;
 }
 
@@ -993,7 +1053,7 @@ int tc_plan(const BjxElboArgs& a, Plan& p) {
 
 // workspace for the operand planes when a width outside {128, 256, 384, 512} arrives without prepared planes
 size_t tc_theta_bytes(const BjxElboArgs& a, const Plan&) {
-  return (!tc_exact_width(a) && a.x_planes == nullptr) ? x_planes_bytes(a.N, a.Dw) : 0;
+  return (!tc_exact_width(a) && a.x_planes == nullptr && a.row_index == nullptr) ? x_planes_bytes(a.N, a.Dw) : 0;
 }
 
 int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
@@ -1034,16 +1094,24 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     tcp::Maps maps;
     const __nv_bfloat16* planes = (const __nv_bfloat16*)x_planes;
     int rc;
-    if ((rc = make_bf16_tensor_map(&maps.x1, planes, a.N, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
-    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)a.N * Dp, a.N, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
-#define BJX_TCP_LAUNCH(NBLK, EW)                                                                                              \
+    const bool idx = a.row_index != nullptr;  // the planes are the FULL dataset's (N_full rows); gather4 boxes are one row high
+    const int64_t plane_rows = idx ? a.N_full : a.N;
+    const int box_rows = idx ? 1 : tc::TILE_ROWS;
+    if ((rc = make_bf16_tensor_map(&maps.x1, planes, plane_rows, Dp, Dp, tc::BLK_COLS, box_rows))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)plane_rows * Dp, plane_rows, Dp, Dp, tc::BLK_COLS, box_rows))) return rc;
+#define BJX_TCP_LAUNCH_I(NBLK, EW, IDX)                                                                                        \
   do {                                                                                                                    \
     static DeviceOnce attr_set;                                                                                         \
     if (!attr_set.test_and_set()) {                                                                                                      \
-      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK, EW><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
-                                                              a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace); \
+    k_lik_tc_tma<NBLK, EW, IDX><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
+                                                              a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace, a.row_index); \
+  } while (0)
+#define BJX_TCP_LAUNCH(NBLK, EW)                  \
+  do {                                            \
+    if (idx) BJX_TCP_LAUNCH_I(NBLK, EW, true);    \
+    else BJX_TCP_LAUNCH_I(NBLK, EW, false);       \
   } while (0)
     // Epilogue warps: eight everywhere except D = 128 with the Bernoulli-logit link, where the tile is so short that the
     // epilogue's latency chain is the bound and sixteen warps (four finished values per thread) hide more of it: 0.65 ->
@@ -1068,6 +1136,7 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     }
 #undef BJX_TCP_LAUNCH_EW
 #undef BJX_TCP_LAUNCH
+#undef BJX_TCP_LAUNCH_I
     BJX_LAUNCH_CHECK("k_lik_tc_tma");
     return BJX_OK;
   }

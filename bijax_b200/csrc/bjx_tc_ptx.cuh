@@ -110,6 +110,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
                "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// tile::gather4: four rows (r0..r3, any order) x box columns of a 2-D tensor -> four consecutive 128-byte rows at dst_smem.
+// The tensor map's box must be {cols, 1}; the mbarrier sees 4 * cols * elemsize bytes; the 128-byte swizzle is keyed by the
+// absolute shared-memory address, so a destination 512 bytes into a 1024-byte swizzle atom fills its rows 4-7 correctly
+// (all three facts measured with scripts/ubench/gather4_probe.cu).
+__device__ __forceinline__ void tma_gather4_2d(void* dst_smem, const void* tmap, int32_t c0, int32_t r0, int32_t r1, int32_t r2,
+                                               int32_t r3, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 // ---- CTA pairs (cta_group::2): two SMs of a TPC work on one 256-row tile; the B operand is split between them ----------
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
 __device__ __forceinline__ uint32_t cluster_ctarank() {

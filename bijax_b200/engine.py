@@ -160,10 +160,15 @@ class ElboEngine:
             raise ValueError(f"row_index must be a contiguous CUDA int32 tensor with one entry per row of the batch ({N})")
         return row_index.data_ptr()
 
-    def supports_row_index(self, S, N) -> bool:
+    def supports_row_index(self, S, N, planes: bool = False) -> bool:
+        """Can a step of this shape read its rows through a row index?  ``planes=False``: out of raw fp32 X (register-converting
+        kernel, Dw in {128, 256, 384, 512}); ``planes=True``: out of the full dataset's prepared planes with TMA gather4 loads
+        (any Dw in [16, 512])."""
         if self.Dw < 1:
             return False
         a = self._args(S, N, max(self.Dw, 1), 1.0, 1.0, nv.LAYOUT_LEGACY)
+        if planes:
+            a.x_planes, a.N_full = 1, max(int(N), 1)  # any non-NULL value: only the route is being asked about
         return self.lib.bjx_elbo_supports_row_index(C.byref(a)) == 1
 
     def wants_planes(self, S, N) -> bool:
@@ -239,14 +244,15 @@ class ElboEngine:
         return nv.KERNEL_NAMES[nv.check(self.lib.bjx_elbo_kernel_choice(C.byref(a)))]
 
     def step(self, key, loc, raw_scale, kwargs_vec, X, y, ll_scale, n_samples, prior_weight=1.0, out=None, eps_out=None,
-             partitionable=None, sample_shard=None, row_index=None, planes=None) -> torch.Tensor:
+             partitionable=None, sample_shard=None, row_index=None, planes=None, n_full=None) -> torch.Tensor:
         """Enqueue one ELBO+grad step; returns the packed device tensor [loss | d loc | d raw_scale | d kwargs].
         ``sample_shard = (s_offset, S_total, entropy_weight)`` evaluates samples [s_offset, s_offset + n_samples) of a
         step with S_total samples (shard the Monte-Carlo samples when N is small); the packed
         outputs of all shards sum to the unsharded step.
         ``row_index`` (int32 [len(y)]): row r of the batch is X[row_index[r]] -- X is the full dataset, read through the
         index (BjxElboArgs.row_index; only where ``supports_row_index``).  ``planes``: operand planes of X maintained by
-        the caller (the minibatch sampler gathers plane rows itself) instead of the engine's own cache."""
+        the caller (the minibatch sampler gathers plane rows itself) instead of the engine's own cache; together with
+        ``row_index`` they are the FULL dataset's planes (``n_full`` rows) and the kernel gathers the batch's rows out of them."""
         dev = self.device
         key = brandom._check_key(key)
         loc = self._f32(loc, dev).reshape(-1)
@@ -275,6 +281,8 @@ class ElboEngine:
             a.s_offset, a.S_total, a.entropy_weight = int(sample_shard[0]), int(sample_shard[1]), float(sample_shard[2])
         if row_index is None:
             a.x_planes = planes.data_ptr() if planes is not None else self._x_planes(a, X)
+        elif planes is not None:
+            a.x_planes, a.N_full = planes.data_ptr(), int(n_full if n_full is not None else X.shape[0])
         ws = self._workspace(a)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(dev):
@@ -376,6 +384,8 @@ class ElboEngine:
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
         if indexed:
             a.row_index = self._check_row_index(minibatch["idx"], N)
+            if minibatch.get("planes_full") is not None:  # gather the batch's rows out of the full dataset's planes (TMA gather4)
+                a.x_planes, a.N_full = minibatch["planes_full"].data_ptr(), int(X.shape[0])
         elif minibatch is not None:  # the sampler fills the batch's planes itself (bjx_minibatch_gather)
             a.x_planes = minibatch["planes_b"].data_ptr() if minibatch["planes_b"] is not None else None
         else:

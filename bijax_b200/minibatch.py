@@ -62,19 +62,22 @@ class MinibatchLoss:
         st["yb"] = torch.empty(self.B, dtype=torch.float32, device=dev)
         st["idx"] = torch.empty(self.B, dtype=torch.int32, device=dev)
         st["elbo_key"] = torch.zeros(2, dtype=torch.uint32, device=dev)
-        st["indexed"] = X is not None and self.copy_free and engine.supports_row_index(self.S, self.B)
+        tma_fed = X is not None and engine.wants_planes(self.S, self.B)
+        # copy-free routes, best first: the TMA-fed kernel gathering plane rows of the full dataset (tile::gather4), else the
+        # register-converting kernel reading raw fp32 X through the index
+        via_planes = tma_fed and self.copy_free and engine.supports_row_index(self.S, self.B, planes=True)
+        st["indexed"] = X is not None and self.copy_free and (via_planes or engine.supports_row_index(self.S, self.B))
         st["Xb"] = torch.zeros((self.B, engine.Dw), dtype=torch.float32, device=dev) if X is not None and not st["indexed"] else None
         st["planes_full"] = st["planes_b"] = None
-        if st["indexed"]:
-            pass  # the step reads the dataset through idx (BjxElboArgs.row_index): nothing to gather but y
-        elif X is not None and engine.wants_planes(self.S, self.B):
-            # the batch step is TMA-fed: keep the FULL dataset as planes (made once) and gather plane rows
+        if tma_fed and (via_planes or not st["indexed"]):
+            # keep the FULL dataset as planes (made once): the step gathers its rows itself, or the sampler copies them
             lib = engine.lib
             full = torch.empty(int(lib.bjx_x_planes_bytes(N, engine.Dw)), dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
                 nv.check(lib.bjx_prepare_x_planes(X.data_ptr(), N, engine.Dw, ldx, full.data_ptr(), nv.current_stream_ptr()))
             st["planes_full"] = full
-            st["planes_b"] = torch.empty(int(lib.bjx_x_planes_bytes(self.B, engine.Dw)), dtype=torch.uint8, device=dev)
+            if not st["indexed"]:
+                st["planes_b"] = torch.empty(int(lib.bjx_x_planes_bytes(self.B, engine.Dw)), dtype=torch.uint8, device=dev)
         mb = nv.BjxMinibatch()
         mb.N_full, mb.B, mb.Dw, mb.ldx_full = N, self.B, max(engine.Dw, 1), ldx if ldx else max(engine.Dw, 1)
         mb.y_full, mb.yb = y.data_ptr(), st["yb"].data_ptr()
@@ -121,6 +124,7 @@ class MinibatchLoss:
 
         def run(loc_, raw_, kw_):
             return engine.step(st["elbo_key"], loc_, raw_, kw_, Xin, st["yb"], ll_scale, self.S,
-                               row_index=st["idx"] if st["indexed"] else None, planes=st["planes_b"])
+                               row_index=st["idx"] if st["indexed"] else None,
+                               planes=st["planes_full"] if st["indexed"] else st["planes_b"], n_full=self.N)
 
         return _ElboFunction.apply(loc, raw, kw, run)

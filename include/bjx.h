@@ -183,8 +183,12 @@ typedef struct BjxElboArgs {
    * through the index -- one pass over the batch's own rows, no gathered copy.  y is NOT indexed (pass y[row_index[r]],
    * e.g. BjxMinibatch.yb); x_planes must be NULL.  Only the fused tcgen05 kernel reads through an index (ask
    * bjx_elbo_supports_row_index); every other shape returns BJX_ERR_UNSUPPORTED and the caller gathers rows instead
-   * (bjx_minibatch_gather). */
+   * (bjx_minibatch_gather).
+   * ABI 4: x_planes may be set together with row_index when N_full is given -- the planes are then those of the FULL dataset
+   * (bjx_prepare_x_planes(X_full, N_full, Dw)) and the TMA-fed kernel gathers the batch's plane rows with tile::gather4 loads
+   * (any Dw in [16, 512]); X itself is then not read. */
   const int32_t* row_index;
+  int64_t N_full; /* rows of the full dataset behind row_index + x_planes (0 = not given) */
 } BjxElboArgs;
 
 #define BJX_POINT_OFF 0
@@ -226,7 +230,9 @@ BJX_API int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t 
 /* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = fused tcgen05 single pass
  * (split-bf16), 3 = coin toss, 4 = two-pass TMA-fed tcgen05 GEMM (split-bf16) */
 BJX_API int bjx_elbo_kernel_choice(const BjxElboArgs* args);
-/* 1 if a step of this shape can read X through BjxElboArgs.row_index, 0 if the rows must be gathered first */
+/* 1 if a step of this shape can read its rows through BjxElboArgs.row_index, 0 if the rows must be gathered first.  Evaluated
+ * for the route the arguments describe: x_planes == NULL asks about raw fp32 X, x_planes != NULL (any non-NULL value) with
+ * N_full >= 1 about gathering plane rows. */
 BJX_API int bjx_elbo_supports_row_index(const BjxElboArgs* args);
 
 /* ---- posterior access (.apply -> Posterior.sample / log_prob, core.py:39-75) */

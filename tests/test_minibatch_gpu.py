@@ -39,16 +39,18 @@ def test_randint_offsets_shapes_and_choice():
     assert br.randint(k, (0,), 0, 10).numel() == 0
 
 
-def _logistic_model(D):
+def _logistic_model(D, prepare_dataset=True):
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
-    return bj.ADVI(prior, {"weights": tfb.Identity()}, lk.BernoulliLogits(), vi_type="mean_field")
+    return bj.ADVI(prior, {"weights": tfb.Identity()}, lk.BernoulliLogits(), vi_type="mean_field", prepare_dataset=prepare_dataset)
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "planes_tc", "coin"])
+@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "indexed_planes_tc", "indexed_planes_d200", "planes_tc", "coin"])
 def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
     """sample(): idx / y[idx] / X[idx] (or the planes of X[idx]) / k_elbo against the oracle's split + randint; the
-    minibatch loss and gradients equal loss_fn evaluated on the rows indexed by torch, bit for bit."""
+    minibatch loss and gradients equal loss_fn evaluated on the rows indexed by torch, bit for bit.  Copy-free routes:
+    indexed_tc = the register-converting kernel reading raw fp32 X through the index (engine without prepared planes);
+    indexed_planes_* = the TMA-fed kernel gathering rows of the FULL dataset's planes with tile::gather4 loads."""
     dev = torch.device("cuda")
     br.config.threefry_partitionable = bool(layout)
     try:
@@ -58,10 +60,10 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
             model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}, {}, lk.GaussianLinear())
             params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
             params["log_noise_scale"] = torch.tensor(-0.7, device=dev)
-        elif case in ("planes_tc", "indexed_tc"):
-            N, D, B, S = 3000, 128, 700, 32
+        elif case in ("planes_tc", "indexed_tc", "indexed_planes_tc", "indexed_planes_d200"):
+            N, D, B, S = 3000, (200 if case == "indexed_planes_d200" else 128), 700, 32
             X, y = C.synth_logistic(N, D)
-            model = _logistic_model(D)
+            model = _logistic_model(D, prepare_dataset=case != "indexed_tc")
             params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
         else:
             N, B, S = 777, 64, 16
@@ -71,7 +73,7 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         yd = torch.tensor(y, device=dev)
         Xd = torch.tensor(X, device=dev) if X is not None else None
         inputs = {"X": Xd} if Xd is not None else None
-        loss = model.minibatch_loss_fn(yd, inputs, batch_size=B, n_samples=S, full_data_size=3 * N, copy_free={"planes_tc": False, "indexed_tc": True}.get(case))
+        loss = model.minibatch_loss_fn(yd, inputs, batch_size=B, n_samples=S, full_data_size=3 * N, copy_free={"planes_tc": False, "indexed_tc": True, "indexed_planes_tc": True, "indexed_planes_d200": True}.get(case))
         seed = br.PRNGKey(77)
         idx, yb, Xb, ke = loss.sample(params, seed)
         kb_np, ke_np = tf.split(tf.prng_key(77), 2, layout)
@@ -82,9 +84,10 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         uses_planes = case == "planes_tc"
         st = loss._state
         assert (st["planes_b"] is not None) == uses_planes
-        assert st["indexed"] == (case == "indexed_tc")  # the fused tcgen05 kernel reads the dataset through idx: no copy
+        assert st["indexed"] == case.startswith("indexed")  # the fused tcgen05 kernel reads the dataset through idx: no copy
         if st["indexed"]:
             assert Xb is None and st["mb"].Xb is None and st["mb"].planes_b is None
+            assert (st["planes_full"] is not None) == case.startswith("indexed_planes")
         if X is not None and not uses_planes and not st["indexed"]:
             assert np.array_equal(Xb.cpu().numpy(), X[want_idx])
         if uses_planes:  # gathered plane rows == the planes of the gathered rows
@@ -97,15 +100,14 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
         li = torch.as_tensor(want_idx, device=dev).long()
         ref_inputs = {"X": Xd[li].contiguous()} if Xd is not None else None
         ke_t = torch.tensor(ke_np.astype(np.int64), dtype=torch.int64).to(torch.uint32).to(dev)
-        ref_model = model
-        if case == "indexed_tc":  # the same kernel without the index: raw fp32 rows, converted in registers
-            ref_model = bj.ADVI(model.prior, {"weights": tfb.Identity()}, lk.BernoulliLogits(), vi_type="mean_field", prepare_dataset=False)
-        want, g_want = ref_model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
+        # the same kernel without the index, on rows gathered by torch: raw fp32 rows converted in registers (indexed_tc), or
+        # the TMA-fed kernel on the planes of the gathered rows (every other tensor-core case) -- same tiles, same order
+        want, g_want = model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
         assert got.item() == want.item()
         for k in ("loc", "scale_diag"):
             assert torch.equal(g_got["posterior"][k], g_want["posterior"][k])
         if case == "indexed_tc":  # and the TMA-fed kernel on the gathered planes agrees to rounding
-            w2, g2 = model.value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
+            w2, g2 = _logistic_model(D).value_and_grad(params, yd[li].contiguous(), ref_inputs, 3 * N, ke_t, S)
             C.assert_close(got.item(), w2.item(), what="loss, indexed vs planes")
             C.assert_close(g_got["posterior"]["loc"].cpu().numpy(), g2["posterior"]["loc"].cpu().numpy(), what="d loc, indexed vs planes")
     finally:
@@ -221,6 +223,36 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
     with pytest.raises(ValueError):  # one index per batch row
         eng.step(key, loc, raw, None, Xd, yd[li].contiguous(), N / B, S, row_index=idx[:-1].contiguous() if B > 1 else idx.long())
 
+
+
+@pytest.mark.parametrize("D,S,N,B", [(512, 32, 30000, 4097), (256, 7, 9000, 1), (384, 20, 5000, 5000), (128, 32, 20000, 9001),
+                                     (200, 32, 7000, 3333), (64, 16, 4000, 700), (500, 32, 6000, 6000)])
+def test_step_gathering_plane_rows_equals_the_step_on_gathered_rows(D, S, N, B):
+    """BjxElboArgs.row_index + x_planes + N_full (ABI 4): the TMA-fed kernel gathering rows of the full dataset's planes with
+    tile::gather4 loads gives, bit for bit, what it gives on the planes of the gathered rows -- repeated indices, B not a
+    multiple of the 64-row tile, every block count (ring and spare-slot schedules), widths padded by TMA zero fill."""
+    dev = torch.device("cuda")
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model = bj.ADVI(prior, {"weights": tfb.Identity()}, lk.BernoulliLogits())
+    eng, _ = model._engine_for({})
+    assert eng.supports_row_index(S, B, planes=True)
+    lib = nv.load()
+    full = torch.empty(int(lib.bjx_x_planes_bytes(N, D)), dtype=torch.uint8, device=dev)
+    nv.check(lib.bjx_prepare_x_planes(Xd.data_ptr(), N, D, D, full.data_ptr(), nv.current_stream_ptr()))
+    idx = br.randint(br.PRNGKey(D + B), (B,), 0, N)
+    li = idx.long()
+    loc = 0.05 * br.normal(br.PRNGKey(1), (D,))
+    raw = torch.full((D,), -2.0, device=dev)
+    key = br.PRNGKey(4)
+    Xg, yg = Xd[li].contiguous(), yd[li].contiguous()
+    want = eng.step(key, loc, raw, None, Xg, yg, N / B, S).clone()  # prepares the planes of the gathered rows
+    assert eng._planes is not None and eng.kernel_choice(S, B) == "tcgen05_bf16_split"
+    got = eng.step(key, loc, raw, None, Xd, yg, N / B, S, row_index=idx, planes=full, n_full=N).clone()
+    assert torch.equal(got, want)
+    with pytest.raises(nv.BjxError):  # planes of the full dataset without its row count
+        eng.step(key, loc, raw, None, Xd, yg, N / B, S, row_index=idx, planes=full, n_full=0)
 
 
 def test_minibatch_on_the_two_pass_gemm_path():

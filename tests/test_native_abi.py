@@ -31,10 +31,10 @@ def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "bjx.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(BjxElboArgs), sizeof(BjxCoord), offsetof(BjxElboArgs, key),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(BjxElboArgs), sizeof(BjxCoord), offsetof(BjxElboArgs, key),'
         " offsetof(BjxElboArgs, workspace_bytes), offsetof(BjxElboArgs, ll_scale), offsetof(BjxElboArgs, kernel_override),"
         " offsetof(BjxElboArgs, x_planes), offsetof(BjxElboArgs, key_index), offsetof(BjxElboArgs, S_total),"
-        " offsetof(BjxElboArgs, point_mode), offsetof(BjxElboArgs, rank), offsetof(BjxElboArgs, row_index));return 0;}\n"
+        " offsetof(BjxElboArgs, point_mode), offsetof(BjxElboArgs, rank), offsetof(BjxElboArgs, row_index), offsetof(BjxElboArgs, N_full));return 0;}\n"
     )
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     want = [C.sizeof(nv.BjxElboArgs), C.sizeof(nv.BjxCoord), nv.BjxElboArgs.key.offset, nv.BjxElboArgs.workspace_bytes.offset,
             nv.BjxElboArgs.ll_scale.offset, nv.BjxElboArgs.kernel_override.offset, nv.BjxElboArgs.x_planes.offset,
             nv.BjxElboArgs.key_index.offset, nv.BjxElboArgs.S_total.offset, nv.BjxElboArgs.point_mode.offset, nv.BjxElboArgs.rank.offset,
-            nv.BjxElboArgs.row_index.offset]
+            nv.BjxElboArgs.row_index.offset, nv.BjxElboArgs.N_full.offset]
     assert got == want
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "bjx.h"\n'
