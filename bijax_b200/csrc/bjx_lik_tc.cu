@@ -495,20 +495,21 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 }  // namespace tcp
 
 // IDX: row r of the problem is row ridx[r] of the planes (a minibatch drawn on the device, BjxElboArgs.row_index + x_planes +
-// N_full): the producer warp gathers the batch's rows straight out of the FULL dataset's planes with tile::gather4 TMA loads
-// (four rows per instruction, sixteen lanes x two planes per 64-row block), so a batch costs one pass over its own rows.
-template <int NBLK, int EW, bool IDX>  // D / 64; epilogue warps (8 or 16)
-__global__ void __launch_bounds__((tcp::EPI_WARP0 + EW) * 32, 1)
+// N_full): the producer warp gathers the batch's rows straight out of the FULL dataset's planes with 16-byte cp.async copies
+// into the swizzled image, so a batch costs one pass over its own rows and nothing else.
+template <int NBLK, int EW, bool IDX>  // D / 64; epilogue warps (8 or 16); IDX adds a second producer warp at the end
+__global__ void __launch_bounds__((tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
-             long long* __restrict__ trace, const int32_t* __restrict__ ridx) {
+             long long* __restrict__ trace, const int32_t* __restrict__ ridx, int64_t plane_rows) {
 #define BJX_TRACE(it_, slot_)                                                                 \
   do {                                                                                        \
     if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
   } while (0)
   using namespace tc;
-  constexpr int NTHREADS = (tcp::EPI_WARP0 + EW) * 32;
+  constexpr int NTHREADS = (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32;
+  constexpr int PROD_WARP2 = tcp::EPI_WARP0 + EW;  // IDX only: the second producer warp (one per operand plane)
   constexpr int HG = EW / 4;    // groups of samples among the epilogue warps of one TMEM sub-partition
   constexpr int SG = NS / HG;   // samples whose partial logits a thread loads (16 or 8)
   constexpr int VPT = SG / 2;   // (row, sample) pairs a thread finishes after the swap with its partner (8 or 4)
@@ -538,6 +539,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   float* sred = (float*)(bars + 1);
   float* xch = (float*)(((uintptr_t)(sred + 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
   constexpr int XCH_FLOATS = EW * VPT * 32;                                    // (two of them in ring mode, see the epilogue)
+  int32_t* sidx = reinterpret_cast<int32_t*>(xch + (RING ? 2 : 1) * XCH_FLOATS);  // IDX only: [4 tiles][64] ring of row indices
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
@@ -545,7 +547,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 
   if (tid == 0) {
     for (int b = 0; b < 9; ++b) {
-      mbar_init(&bars->x_full[b], 1);  // the producer's expect_tx arrival; completion is counted in bytes
+      mbar_init(&bars->x_full[b], IDX ? 64 : 1);  // TMA: the producer's expect_tx arrival, completion counted in bytes;
+                                                  // gather: one cp.async.mbarrier.arrive per lane of the two producer warps
       mbar_init(&bars->x_empty[b], 1);
     }
     mbar_init(&bars->acc1_full[0], 1);
@@ -579,34 +582,106 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == tcp::PROD_WARP) {
+  if (warp == tcp::PROD_WARP || (IDX && warp == PROD_WARP2)) {
     // ===================================================== TMA producer ================================================
     if constexpr (IDX) {
-      // gather variant: lane j < 16 owns rows 4j .. 4j+3 of every tile (their indices live in its registers, loaded one tile
-      // ahead); per block the warp posts the byte count once and the sixteen lanes issue one gather4 per plane each.  Rows
-      // past N read row 0 of the dataset: the epilogue zeroes their g, so they contribute nothing to either GEMM's result.
-      const bool issuer = lane < 16;
-      auto load_idx = [&](int64_t t, int32_t(&v)[4]) {
-        const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS + 4 * lane;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (issuer && t < my_tiles && r0 + i < N) ? __ldg(ridx + r0 + i) : 0;
+      // Gather variant: TWO producer warps (one per operand plane: a single warp keeps only ~50 KB of copies in flight, 0.5
+      // of the roofline with everything else switched off) copy the batch's plane rows with 16-byte cp.async (LDGSTS): no
+      // registers in flight, any source address per lane, and the destination is the swizzled UMMA image itself.  Lane =
+      // (r4, c): row 4g + r4 of the tile for g = 0..15, 16-byte chunk c of the block's 128-byte row; one instruction covers
+      // four rows x 128 bytes, 16 instructions a block.  Each lane keeps the byte address of its sixteen source rows and
+      // arrives on the block's barrier through cp.async.mbarrier.arrive (64 arrivals per phase); the MMA warp adds the
+      // generic->async proxy fence after its wait.  Rows past N read row 0 of the dataset: the
+      // epilogue zeroes their g, so they contribute nothing.  Blocks beyond the planes' extent are zero-filled (src size 0).
+      // (tile::gather4 TMA loads were measured first: the copy engine retires one 512-byte gather4 per ~75 cycles, 0.27 of the
+      // HBM roofline -- profiles/r02_minibatch_gather4_rejected.json.)
+      const int r4 = lane >> 3, c = lane & 7;
+      const int pw = warp == tcp::PROD_WARP ? 0 : 1;  // which plane this warp copies
+      const int64_t pitch = (int64_t)Dp * 2;
+      const char* pl = reinterpret_cast<const char*>(planes) + (int64_t)pw * plane_rows * pitch;
+      const int dst_plane = pw * BLK_BYTES;
+      // Row indices travel through a four-tile ring in shared memory: the warp loads a tile's 64 indices coalesced (two per
+      // lane) THREE tiles ahead into registers, parks them in the ring one iteration later, and everything that needs an
+      // address -- the L2 touch two tiles ahead, the source rows one tile ahead -- reads the ring, never global memory, so
+      // no dependent global load sits in front of a copy.
+      int32_t stage0 = 0, stage1 = 0;
+      auto fetch_idx = [&](int64_t t) {  // -> registers (warp 0 of the pair)
+        if (pw != 0) return;
+        const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS + 2 * lane;
+        stage0 = (t < my_tiles && r0 < N) ? __ldg(ridx + r0) : 0;
+        stage1 = (t < my_tiles && r0 + 1 < N) ? __ldg(ridx + r0 + 1) : 0;
       };
-      auto issue = [&](uint8_t* slot, unsigned long long* bar, int b, const int32_t(&v)[4]) {
-        if (lane == 0) mbar_expect_tx(bar, 2u * BLK_BYTES);
-        __syncwarp();
-        if (issuer) {
-          tma_gather4_2d(slot + 512 * lane, &maps.x1, b * BLK_COLS, v[0], v[1], v[2], v[3], bar);
-          tma_gather4_2d(slot + BLK_BYTES + 512 * lane, &maps.x2, b * BLK_COLS, v[0], v[1], v[2], v[3], bar);
+      auto park_idx = [&](int64_t t) {  // registers -> ring slot t % 4, visible to both producer warps
+        if (pw == 0) {
+          int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
+          slot[2 * lane] = stage0;
+          slot[2 * lane + 1] = stage1;
+        }
+        asm volatile("bar.sync 14, 64;" ::: "memory");
+      };
+      auto load_rows = [&](int64_t t, const char*(&rb)[16]) {
+        const int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) rb[g] = pl + (int64_t)slot[4 * g + r4] * pitch + c * 16;
+      };
+      // A row's eight 128-byte pieces (one per block) are copied at different times, and the X slots have no slack, so the
+      // copies of tile t+1 can only be issued as GEMM2(t) releases its blocks: without help every tile pays a full random-
+      // access HBM latency between GEMM2 and the next GEMM1.  Touching ALL lines of a tile's rows two tiles ahead (per-lane
+      // prefetch.global.L2: lane c takes line c of row 4g + r4, both planes) turns that into an L2 hit.
+      const int pf_kind = pf_tiles & 255;  // 0 off | 1 one touch per 128-byte line | 2 one per 32-byte sector | 3 bulk prefetch per row
+      auto prefetch_rows = [&](int64_t t) {
+        if (pf_kind == 0 || t >= my_tiles) return;
+        const int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
+        const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
+        if (pf_kind == 3) {  // two rows per lane, the whole plane row (pitch bytes) in one request
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int r = 2 * lane + u;
+            if (r0 + r < N)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pl + (int64_t)slot[r] * pitch), "r"((uint32_t)pitch) : "memory");
+          }
+          return;
+        }
+        if (c * 128 >= pitch) return;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          if (r0 + r4 + 4 * g < N) {
+            const char* p = pl + (int64_t)slot[4 * g + r4] * pitch + c * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            if (pf_kind == 2) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 96));
+            }
+          }
         }
       };
-      int32_t cur[4], nxt[4];
-      load_idx(0, cur);
-      load_idx(1, nxt);
+      auto issue = [&](uint8_t* slot, unsigned long long* bar, int b, const char* const(&rb)[16]) {
+        const uint32_t nbytes = (b * BLK_COLS < Dp) ? 16u : 0u;
+        const int64_t boff = nbytes ? (int64_t)b * 128 : 0;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          const int r = 4 * g + r4;
+          cp_async16(slot + dst_plane + r * 128 + ((c ^ (r & 7)) << 4), rb[g] + boff, nbytes);
+        }
+        cp_async_mbar_arrive(bar);
+      };
+      for (int64_t t = 0; t < 3; ++t) {  // prologue: tiles 0, 1, 2 into the ring (the only exposed index latency)
+        fetch_idx(t);
+        park_idx(t);
+      }
+      fetch_idx(3);
+      const char *cur[16], *nxt[16];
+      load_rows(0, cur);
+      prefetch_rows(0);
+      prefetch_rows(1);
       if (!RING && my_tiles > 0) {
         mbar_wait(&bars->x_empty[0], 1u);
         issue(sx, &bars->x_full[0], 0, cur);
       }
       for (int64_t it = 0; it < my_tiles; ++it) {
+        prefetch_rows(it + 2);
+        load_rows(it + 1, nxt);
         if constexpr (RING) {
           const int q0 = (int)(it % R) * NBLK;
           const uint32_t use = (uint32_t)((it / R) & 1);
@@ -629,8 +704,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-        load_idx(it + 2, nxt);
+        for (int g = 0; g < 16; ++g) cur[g] = nxt[g];
+        park_idx(it + 3);   // fetched during the previous iteration; its ring slot held tile it - 1
+        fetch_idx(it + 4);
       }
     } else {
       const __nv_bfloat16* p1 = planes;
@@ -711,6 +787,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if constexpr (RING) {
         const int q = (int)(t % R) * NBLK + b;
         mbar_wait(&bars->x_full[q], (uint32_t)((t / R) & 1));
+        if constexpr (IDX) { if (!(ablate & 16)) fence_proxy_async(); }  // the block was written by cp.async (generic proxy); UMMA reads through the async proxy
         if (lane == 0) BJX_TRACE(t, 16 + b);
         if (!(ablate & 1) && elect_one()) {
           const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);
@@ -726,6 +803,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         mbar_wait(&bars->x_full[alt ? 8 : 0], (uint32_t)((t >> 1) & 1));
       else
         mbar_wait(&bars->x_full[b], (uint32_t)(t & 1));
+      if constexpr (IDX) { if (!(ablate & 16)) fence_proxy_async(); }
       if (lane == 0) BJX_TRACE(t, 16 + b);
       if (!(ablate & 1) && elect_one()) {
         const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
@@ -1082,7 +1160,8 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     // dataset prepared as split-bf16 planes: the TMA-fed variant (two extra block slots, see the kernel)
     const int nslot = 8 / nblk > 1 ? 8 : nblk;  // D = 128, 256: the eight slots are a ring of tiles (see the kernel)
     const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 +
-                        (nslot > nblk ? 2 : 1) * 8 * 256 * sizeof(float) + 1024;
+                        (nslot > nblk ? 2 : 1) * 8 * 256 * sizeof(float) + 1024 +
+                        (a.row_index != nullptr ? 4 * tc::TILE_ROWS * sizeof(int32_t) : 0);  // + the gather variant's index ring
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");
@@ -1090,23 +1169,27 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     }
     // folding the GEMM2 accumulators into the TMEM-resident partial is free of memory traffic: do it twice as often as
     // the raw-fp32 variant (bias of the truncating accumulate ~0.9e-6 instead of 1.7e-6)
+    static int pf_idx = -1;  // gather variant: how many tiles ahead whole plane rows are touched into L2 (BJX_TC_PF_IDX; 0 = off)
+    if (pf_idx < 0) {
+      const char* e = getenv("BJX_TC_PF_IDX");
+      pf_idx = e ? atoi(e) : 0;  // 0 off (default: no mode gained anything, profiles/r02_minibatch.json) | 1 per line | 2 per sector | 3 bulk per row
+    }
     const int flush_tma = getenv("BJX_TC_FLUSH") ? g_flush : 8;
     tcp::Maps maps;
     const __nv_bfloat16* planes = (const __nv_bfloat16*)x_planes;
     int rc;
-    const bool idx = a.row_index != nullptr;  // the planes are the FULL dataset's (N_full rows); gather4 boxes are one row high
+    const bool idx = a.row_index != nullptr;  // the planes are then the FULL dataset's (N_full rows), read through the index
     const int64_t plane_rows = idx ? a.N_full : a.N;
-    const int box_rows = idx ? 1 : tc::TILE_ROWS;
-    if ((rc = make_bf16_tensor_map(&maps.x1, planes, plane_rows, Dp, Dp, tc::BLK_COLS, box_rows))) return rc;
-    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)plane_rows * Dp, plane_rows, Dp, Dp, tc::BLK_COLS, box_rows))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x1, planes, plane_rows, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
+    if ((rc = make_bf16_tensor_map(&maps.x2, planes + (size_t)plane_rows * Dp, plane_rows, Dp, Dp, tc::BLK_COLS, tc::TILE_ROWS))) return rc;
 #define BJX_TCP_LAUNCH_I(NBLK, EW, IDX)                                                                                        \
   do {                                                                                                                    \
     static DeviceOnce attr_set;                                                                                         \
     if (!attr_set.test_and_set()) {                                                                                                      \
       BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK, EW, IDX><<<p.tc_ctas, (tcp::EPI_WARP0 + EW) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
-                                                              a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate, g_trace, a.row_index); \
+    k_lik_tc_tma<NBLK, EW, IDX><<<p.tc_ctas, (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
+                                                              a.likelihood, Gpart, statpart, idx ? pf_idx : pf_tiles, flush_tma, g_ablate, g_trace, a.row_index, plane_rows); \
   } while (0)
 #define BJX_TCP_LAUNCH(NBLK, EW)                  \
   do {                                            \

@@ -122,6 +122,15 @@ __device__ __forceinline__ void tma_gather4_2d(void* dst_smem, const void* tmap,
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
+// 16-byte asynchronous copy global -> shared that bypasses the register file (LDGSTS); src_bytes = 0 zero-fills the chunk.
+// Any per-thread source and destination address: the gather loader writes straight into the swizzled UMMA image.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once every cp.async this thread issued so far has landed (does not raise the barrier's pending count)
+__device__ __forceinline__ void cp_async_mbar_arrive(void* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // ---- CTA pairs (cta_group::2): two SMs of a TPC work on one 256-row tile; the B operand is split between them ----------
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
 __device__ __forceinline__ uint32_t cluster_ctarank() {

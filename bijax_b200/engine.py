@@ -162,7 +162,7 @@ class ElboEngine:
 
     def supports_row_index(self, S, N, planes: bool = False) -> bool:
         """Can a step of this shape read its rows through a row index?  ``planes=False``: out of raw fp32 X (register-converting
-        kernel, Dw in {128, 256, 384, 512}); ``planes=True``: out of the full dataset's prepared planes with TMA gather4 loads
+        kernel, Dw in {128, 256, 384, 512}); ``planes=True``: out of the full dataset's prepared planes with 16-byte cp.async copies
         (any Dw in [16, 512])."""
         if self.Dw < 1:
             return False
@@ -384,7 +384,7 @@ class ElboEngine:
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat
         if indexed:
             a.row_index = self._check_row_index(minibatch["idx"], N)
-            if minibatch.get("planes_full") is not None:  # gather the batch's rows out of the full dataset's planes (TMA gather4)
+            if minibatch.get("planes_full") is not None:  # gather the batch's rows out of the full dataset's planes (cp.async gather)
                 a.x_planes, a.N_full = minibatch["planes_full"].data_ptr(), int(X.shape[0])
         elif minibatch is not None:  # the sampler fills the batch's planes itself (bjx_minibatch_gather)
             a.x_planes = minibatch["planes_b"].data_ptr() if minibatch["planes_b"] is not None else None

@@ -63,10 +63,14 @@ class MinibatchLoss:
         st["idx"] = torch.empty(self.B, dtype=torch.int32, device=dev)
         st["elbo_key"] = torch.zeros(2, dtype=torch.uint32, device=dev)
         tma_fed = X is not None and engine.wants_planes(self.S, self.B)
-        # copy-free routes, best first: the TMA-fed kernel gathering plane rows of the full dataset (tile::gather4), else the
-        # register-converting kernel reading raw fp32 X through the index
-        via_planes = tma_fed and self.copy_free and engine.supports_row_index(self.S, self.B, planes=True)
-        st["indexed"] = X is not None and self.copy_free and (via_planes or engine.supports_row_index(self.S, self.B))
+        # two copy-free routes: (a) the register-converting kernel reading raw fp32 X through the index (Dw in {128, 256,
+        # 384, 512}), (b) the planes kernel gathering rows of the full dataset's planes with cp.async (any Dw in [16, 512]).
+        # Measured on B200 (profiles/r02_minibatch.json): (b) wins at Dw = 512 (0.56 vs 0.49 of the HBM roofline at 512 Ki
+        # rows), (a) at the narrower exact widths (Dw = 128: 271 vs 335 us per 1 Mi rows), and only (b) exists elsewhere.
+        raw_ok = X is not None and self.copy_free and engine.supports_row_index(self.S, self.B)
+        planes_ok = tma_fed and self.copy_free and engine.supports_row_index(self.S, self.B, planes=True)
+        via_planes = planes_ok and (engine.Dw > 384 or not raw_ok)
+        st["indexed"] = X is not None and self.copy_free and (via_planes or raw_ok)
         st["Xb"] = torch.zeros((self.B, engine.Dw), dtype=torch.float32, device=dev) if X is not None and not st["indexed"] else None
         st["planes_full"] = st["planes_b"] = None
         if tma_fed and (via_planes or not st["indexed"]):

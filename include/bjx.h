@@ -185,7 +185,7 @@ typedef struct BjxElboArgs {
    * bjx_elbo_supports_row_index); every other shape returns BJX_ERR_UNSUPPORTED and the caller gathers rows instead
    * (bjx_minibatch_gather).
    * ABI 4: x_planes may be set together with row_index when N_full is given -- the planes are then those of the FULL dataset
-   * (bjx_prepare_x_planes(X_full, N_full, Dw)) and the TMA-fed kernel gathers the batch's plane rows with tile::gather4 loads
+   * (bjx_prepare_x_planes(X_full, N_full, Dw)) and the TMA-fed kernel gathers the batch's plane rows with 16-byte cp.async copies (LDGSTS)
    * (any Dw in [16, 512]); X itself is then not read. */
   const int32_t* row_index;
   int64_t N_full; /* rows of the full dataset behind row_index + x_planes (0 = not given) */

@@ -50,7 +50,7 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
     """sample(): idx / y[idx] / X[idx] (or the planes of X[idx]) / k_elbo against the oracle's split + randint; the
     minibatch loss and gradients equal loss_fn evaluated on the rows indexed by torch, bit for bit.  Copy-free routes:
     indexed_tc = the register-converting kernel reading raw fp32 X through the index (engine without prepared planes);
-    indexed_planes_* = the TMA-fed kernel gathering rows of the FULL dataset's planes with tile::gather4 loads."""
+    indexed_planes_* = the TMA-fed kernel gathering rows of the FULL dataset's planes with 16-byte cp.async copies."""
     dev = torch.device("cuda")
     br.config.threefry_partitionable = bool(layout)
     try:
@@ -229,7 +229,7 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
                                      (200, 32, 7000, 3333), (64, 16, 4000, 700), (500, 32, 6000, 6000)])
 def test_step_gathering_plane_rows_equals_the_step_on_gathered_rows(D, S, N, B):
     """BjxElboArgs.row_index + x_planes + N_full (ABI 4): the TMA-fed kernel gathering rows of the full dataset's planes with
-    tile::gather4 loads gives, bit for bit, what it gives on the planes of the gathered rows -- repeated indices, B not a
+    16-byte cp.async copies gives, bit for bit, what it gives on the planes of the gathered rows -- repeated indices, B not a
     multiple of the 64-row tile, every block count (ring and spare-slot schedules), widths padded by TMA zero fill."""
     dev = torch.device("cuda")
     X, y = C.synth_logistic(N, D)
