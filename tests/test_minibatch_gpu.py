@@ -61,7 +61,7 @@ def test_gathered_batch_and_loss_match_indexing_on_the_host(case, layout):
             params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
             params["log_noise_scale"] = torch.tensor(-0.7, device=dev)
         elif case in ("planes_tc", "indexed_tc", "indexed_planes_tc", "indexed_planes_d200"):
-            N, D, B, S = 3000, (200 if case == "indexed_planes_d200" else 128), 700, 32
+            N, D, B, S = 3000, {"indexed_planes_d200": 200, "indexed_planes_tc": 512}.get(case, 128), 700, 32
             X, y = C.synth_logistic(N, D)
             model = _logistic_model(D, prepare_dataset=case != "indexed_tc")
             params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
@@ -136,7 +136,7 @@ def test_minibatch_loss_against_the_float64_oracle():
     C.assert_close(grads["log_noise_scale"].cpu().numpy(), wgk["log_noise_scale"].numpy(), what="d log_noise_scale")
 
 
-@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "planes_tc"])
+@pytest.mark.parametrize("case", ["raw_small_d", "indexed_tc", "indexed_planes_tc", "planes_tc"])
 def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
     """bjx_train_steps_minibatch in replayed CUDA graphs (gather -> step -> Adam per epoch, batch drawn from
     split(seed, n)[i] on the device) against the generic loop calling loss(params, seed=seeds[i])."""
@@ -148,7 +148,7 @@ def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
         X, y = C.synth_linear(N, D, noise=0.1)
         model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D), scale_diag=np.ones(D))}, {}, lk.GaussianLinear())
     else:
-        N, D, B, S = 20000, 128, 1024, 32
+        N, D, B, S = 20000, (200 if case == "indexed_planes_tc" else 128), 1024, 32  # 200: only the planes kernel gathers it
         X, y = C.synth_logistic(N, D)
         model = _logistic_model(D)
     Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
@@ -159,7 +159,8 @@ def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
             p["log_noise_scale"] = torch.tensor(-1.0, device=dev)
         return p
 
-    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S, copy_free={"planes_tc": False, "indexed_tc": True}.get(case))
+    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S,
+                                   copy_free={"planes_tc": False, "indexed_tc": True, "indexed_planes_tc": True}.get(case))
     n = 2 * U.GRAPH_STEPS + 3
     fused = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
     host = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3), fused=False)
@@ -167,6 +168,8 @@ def test_device_resident_minibatch_loop_matches_the_host_driven_loop(case):
     assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-5)
     for k in ("loc", "scale_diag"):
         assert torch.allclose(fused["params"]["posterior"][k], host["params"]["posterior"][k], rtol=1e-4, atol=1e-5)
+    if case == "indexed_planes_tc":
+        assert loss._state["indexed"] and loss._state["planes_full"] is not None
     # different epochs see different batches
     assert fused["losses"].unique().numel() == n
     # the idx buffer holds the LAST epoch's draw
