@@ -63,7 +63,7 @@ ffi::Error ElboStepImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> key, ffi::Buf
                         ffi::ResultBuffer<ffi::U8> workspace, int64_t S, int64_t w_offset, int32_t vi_type, int32_t scale_bijector,
                         int32_t likelihood, int32_t noise_src, int32_t noise_index, int32_t threefry_layout, int32_t precision,
                         float noise_value, float ll_scale, float prior_weight, int64_t rank, int64_t S_total, int64_t s_offset,
-                        float entropy_weight, int32_t point_mode) {
+                        float entropy_weight, int32_t point_mode, int64_t N_full) {
   BjxElboArgs a{};
   a.S = S;
   a.N = static_cast<int64_t>(y.element_count());
@@ -88,6 +88,7 @@ ffi::Error ElboStepImpl(cudaStream_t stream, ffi::Buffer<ffi::U32> key, ffi::Buf
   a.s_offset = s_offset;
   a.entropy_weight = entropy_weight;
   a.point_mode = point_mode;
+  a.N_full = N_full;  // rows of the full dataset behind row_index + planes (0: not that route)
   a.key = key.typed_data();
   a.loc = loc.typed_data();
   a.raw_scale = raw_scale.typed_data();
@@ -285,7 +286,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxElboStep, ElboStepImpl,
                                   .Attr<int64_t>("S_total")
                                   .Attr<int64_t>("s_offset")
                                   .Attr<float>("entropy_weight")
-                                  .Attr<int32_t>("point_mode"));
+                                  .Attr<int32_t>("point_mode")
+                                  .Attr<int64_t>("N_full"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxPrepareXPlanes, PrepareXPlanesImpl,
                               ffi::Ffi::Bind()

@@ -58,6 +58,6 @@ def test_shim_covers_the_entry_points_a_jax_host_needs():
     # every BjxElboArgs field a JAX host can vary is an operand or an attribute of BjxElboStep
     elbo = src[src.index("XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxElboStep"):src.index("XLA_FFI_DEFINE_HANDLER_SYMBOL(BjxPrepareXPlanes")]
     for attr in ("S", "w_offset", "vi_type", "scale_bijector", "likelihood", "noise_src", "noise_index", "threefry_layout", "precision",
-                 "noise_value", "ll_scale", "prior_weight", "rank", "S_total", "s_offset", "entropy_weight", "point_mode"):
+                 "noise_value", "ll_scale", "prior_weight", "rank", "S_total", "s_offset", "entropy_weight", "point_mode", "N_full"):
         assert f'"{attr}"' in elbo, attr
     assert "row_index" in elbo and "planes" in elbo
