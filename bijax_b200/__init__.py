@@ -8,6 +8,7 @@ C ABI of include/bjx.h) and raises if it is missing -- there is no CPU fallback.
 """
 from . import bijectors, distributions, likelihoods, optim, random  # noqa: F401
 from .advi import ADVI  # noqa: F401
+from .dataset import PreparedX  # noqa: F401
 from .minibatch import MinibatchLoss  # noqa: F401
 from .point import MAP, MCMC  # noqa: F401
 from .utils import train, train_fn, value_and_grad  # noqa: F401

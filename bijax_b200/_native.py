@@ -54,6 +54,7 @@ EXPORTED_SYMBOLS = (
     "bjx_allreduce_packed_p2p",
     "bjx_x_planes_bytes",
     "bjx_prepare_x_planes",
+    "bjx_prepare_x_planes_rows",
     "bjx_posterior_sample",
     "bjx_posterior_log_prob",
     "bjx_fill_triangular",
@@ -180,6 +181,7 @@ def load() -> C.CDLL:
     lib.bjx_x_planes_bytes.argtypes = [i64, i64]
     lib.bjx_x_planes_bytes.restype = C.c_size_t
     lib.bjx_prepare_x_planes.argtypes = [vp, i64, i64, i64, vp, vp]
+    lib.bjx_prepare_x_planes_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp]
     lib.bjx_posterior_sample.argtypes = [C.POINTER(BjxElboArgs), vp, vp, vp]
     lib.bjx_posterior_log_prob.argtypes = [C.POINTER(BjxElboArgs), vp, i64, vp, vp]
     lib.bjx_fill_triangular.argtypes = [vp, i64, vp, vp]

@@ -713,7 +713,10 @@ static int check_ptrs(const BjxElboArgs& a, const Plan& p) {
   BJX_REQUIRE(a.key && a.loc && a.raw_scale && a.coords && a.out, "null key/loc/raw_scale/coords/out pointer");
   BJX_REQUIRE(a.K == 0 || a.kwargs, "K > 0 but kwargs is null");
   BJX_REQUIRE(a.N == 0 || a.y, "y is null");
-  BJX_REQUIRE(a.likelihood == BJX_LIK_BERNOULLI_PROBS || a.N == 0 || a.X, "X is null");
+  // X may be absent when the dataset lives on the device only as its prepared planes and the planned kernel reads nothing else
+  const bool planes_only_ok = a.x_planes != nullptr && (p.kernel == KERNEL_TC_BF16 || (p.kernel == KERNEL_TC_GEMM && p.gm_nt == 2));
+  BJX_REQUIRE(a.likelihood == BJX_LIK_BERNOULLI_PROBS || a.N == 0 || a.X || planes_only_ok,
+              "X is null (allowed only with x_planes on the tensor-core kernels that read the planes)");
   BJX_REQUIRE(a.workspace != nullptr, "workspace is null");
   if (a.workspace_bytes < p.total)
     return fail(BJX_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", a.workspace_bytes, p.total);
@@ -1037,6 +1040,15 @@ int bjx_train_steps_minibatch(const BjxElboArgs* args, const BjxMinibatch* mb, i
 size_t bjx_x_planes_bytes(int64_t N, int64_t Dw) {
   if (N < 0 || Dw < 1) return 0;
   return bjx::x_planes_bytes(N, Dw);
+}
+
+int bjx_prepare_x_planes_rows(const float* X_rows, int64_t rows, int64_t Dw, int64_t ldx, void* planes, int64_t N_total, int64_t row0,
+                              void* stream) {
+  using namespace bjx;
+  BJX_REQUIRE(X_rows != nullptr && planes != nullptr, "null pointer");
+  BJX_REQUIRE(rows >= 0 && row0 >= 0 && row0 + rows <= N_total && Dw >= 1 && ldx >= Dw, "need 0 <= row0, row0 + rows <= N_total, Dw >= 1, ldx >= Dw");
+  BJX_REQUIRE(((uintptr_t)planes & 15) == 0, "planes must be 16-byte aligned");
+  return split_x_planes_rows(X_rows, rows, Dw, ldx, planes, N_total, row0, (cudaStream_t)stream);
 }
 
 int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, void* stream) {

@@ -49,6 +49,7 @@ int gemm_plan(const BjxElboArgs& a, Plan& p);  // fills gm_*
 int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
 int split_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, cudaStream_t st);
 size_t x_planes_bytes(int64_t N, int64_t Dw);
+int split_x_planes_rows(const float* X_rows, int64_t rows, int64_t Dw, int64_t ldx, void* planes, int64_t N_total, int64_t row0, cudaStream_t st);
 bool fullrank_tc_eligible(const BjxElboArgs& a);
 size_t fullrank_tc_bytes(const BjxElboArgs& a);
 int launch_fullrank_z_tc(const BjxElboArgs& a, const float* eps, float* z, char* scratch, cudaStream_t st);

@@ -604,6 +604,27 @@ int split_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* pla
   return BJX_OK;
 }
 
+// rows [row0, row0 + rows) of the planes of an N_total-row dataset, from a chunk X_rows [rows, ldx] holding just those rows
+int split_x_planes_rows(const float* X_rows, int64_t rows, int64_t Dw, int64_t ldx, void* planes, int64_t N_total, int64_t row0,
+                        cudaStream_t st) {
+  using namespace gemm;
+  if (rows <= 0) return BJX_OK;
+  const int64_t Dp = pad64(Dw);
+  __nv_bfloat16* x1 = (__nv_bfloat16*)planes + (size_t)row0 * Dp;
+  __nv_bfloat16* x2 = (__nv_bfloat16*)planes + (size_t)N_total * Dp + (size_t)row0 * Dp;
+  const int64_t total = rows * (Dp / 8);
+  if ((ldx % 4) == 0 && ((uintptr_t)X_rows & 15) == 0) {
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_split_x<<<(unsigned)blocks, 256, 0, st>>>(X_rows, ldx, rows, Dw, Dp, x1, x2);
+  } else {
+    k_split_planes<2, SrcPlain><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(SrcPlain{X_rows, ldx}, rows, Dw, Dp, x1, x2, nullptr);
+  }
+  BJX_LAUNCH_CHECK("k_split_x");
+  return BJX_OK;
+}
+
 size_t x_planes_bytes(int64_t N, int64_t Dw) { return (size_t)2 * (size_t)N * (size_t)gemm::pad64(Dw) * 2; }
 
 // =========================================================================================================================

@@ -11,6 +11,7 @@ import torch
 from . import _native as nv
 from . import likelihoods as lk
 from . import random as brandom
+from .dataset import PreparedX
 from .spec import LatentSpec
 
 _SCALE_IDS = {"Exp": nv.SCALE_EXP, "Softplus": nv.SCALE_SOFTPLUS, "Identity": nv.SCALE_IDENTITY}
@@ -142,6 +143,11 @@ class ElboEngine:
         N = y.numel()
         if self.lik_id == nv.LIK_BERNOULLI_PROBS:
             return None, y, N, 0
+        if isinstance(X, PreparedX):  # the dataset as planes only: nothing to convert, the kernels never read fp32 X
+            X._require_complete()
+            if X.device != self.device or (X.shape[0] != N and not indexed) or X.shape[1] != self.Dw:
+                raise ValueError(f"PreparedX must be [N={N}, D={self.Dw}] on {self.device}; got {X.shape} on {X.device}")
+            return X, y, N, self.Dw
         if not isinstance(X, torch.Tensor):
             X = torch.as_tensor(X)
         if X.device != self.device or X.dtype != torch.float32:
@@ -180,6 +186,11 @@ class ElboEngine:
 
     def _x_planes(self, a: nv.BjxElboArgs, X: torch.Tensor) -> Optional[int]:
         """Device pointer of the prepared operand planes of X if this step takes the GEMM path, else None."""
+        if isinstance(X, PreparedX):
+            if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]) \
+                    or self.precision == nv.PREC_BF16X3:
+                raise TypeError("this shape runs on a kernel that reads fp32 X; pass the tensor itself instead of a PreparedX")
+            return X.planes.data_ptr()
         if not self.prepare_dataset or X is None:
             return None
         if self.lib.bjx_elbo_kernel_choice(C.byref(a)) not in (nv.KERNEL_IDS["tcgen05_gemm_two_pass"], nv.KERNEL_IDS["tcgen05_bf16_split"]):
@@ -227,6 +238,10 @@ class ElboEngine:
             self._planes_misses = 0
         return self._planes.data_ptr()
 
+    @staticmethod
+    def _x_ptr(X):
+        return None if X is None or isinstance(X, PreparedX) else X.data_ptr()
+
     def release_planes(self) -> None:
         """Drop the prepared operand planes (and the hold on their source tensor's storage)."""
         self._planes, self._planes_key, self._planes_storage, self._last_raw = None, None, None, None
@@ -268,7 +283,7 @@ class ElboEngine:
             if kw.numel() != self.K:
                 raise ValueError(f"expected {self.K} kwarg values")
             a.kwargs = kw.data_ptr()
-        a.X = X.data_ptr() if X is not None else None
+        a.X = self._x_ptr(X)
         a.y = y.data_ptr()
         if row_index is not None:
             a.row_index = self._check_row_index(row_index, N)
@@ -281,8 +296,9 @@ class ElboEngine:
             a.s_offset, a.S_total, a.entropy_weight = int(sample_shard[0]), int(sample_shard[1]), float(sample_shard[2])
         if row_index is None:
             a.x_planes = planes.data_ptr() if planes is not None else self._x_planes(a, X)
-        elif planes is not None:
-            a.x_planes, a.N_full = planes.data_ptr(), int(n_full if n_full is not None else X.shape[0])
+        elif planes is not None or isinstance(X, PreparedX):
+            a.x_planes = planes.data_ptr() if planes is not None else X.planes.data_ptr()
+            a.N_full = int(n_full if n_full is not None else X.shape[0])
         ws = self._workspace(a)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(dev):
@@ -295,7 +311,7 @@ class ElboEngine:
         X / y stay device-resident, as they do for the reference (closure constants of the jitted scan, utils.py:22-31)."""
         X, y, N, ldx = self._data(X, y)
         a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
-        a.X = X.data_ptr() if X is not None else None
+        a.X = self._x_ptr(X)
         a.y = y.data_ptr()
         a.x_planes = self._x_planes(a, X)
         ws = self._workspace(a)
@@ -325,7 +341,7 @@ class ElboEngine:
         if self._point_key is None:
             self._point_key = torch.zeros(2, dtype=torch.uint32, device=dev)
         a.key, a.loc, a.raw_scale = self._point_key.data_ptr(), z.data_ptr(), z.data_ptr()  # raw_scale is ignored
-        a.X = X.data_ptr() if X is not None else None
+        a.X = self._x_ptr(X)
         a.y = y.data_ptr()
         if out is None:
             out = torch.empty(1 + 2 * self.D, dtype=torch.float32, device=dev)
@@ -378,7 +394,7 @@ class ElboEngine:
         assert keys.dtype == torch.uint32 and keys.is_cuda and keys.is_contiguous()
         assert params_flat.numel() == self.D + self.P + self.K and params_flat.is_contiguous()
         a.key = keys.data_ptr()
-        a.X = X.data_ptr() if X is not None else None
+        a.X = self._x_ptr(X)
         a.y = y.data_ptr()
         a.out = out.data_ptr()
         a.loc = a.raw_scale = params_flat.data_ptr()  # replaced inside the library by views into params_flat

@@ -62,12 +62,17 @@ class MinibatchLoss:
         st["yb"] = torch.empty(self.B, dtype=torch.float32, device=dev)
         st["idx"] = torch.empty(self.B, dtype=torch.int32, device=dev)
         st["elbo_key"] = torch.zeros(2, dtype=torch.uint32, device=dev)
-        tma_fed = X is not None and engine.wants_planes(self.S, self.B)
+        from .dataset import PreparedX
+
+        prepared = isinstance(X, PreparedX)  # the dataset as planes only: every route below that needs fp32 X is closed
+        tma_fed = X is not None and (engine.wants_planes(self.S, self.B) or prepared)
+        if prepared and not engine.supports_row_index(self.S, self.B, planes=True) and not engine.wants_planes(self.S, self.B):
+            raise TypeError("a PreparedX dataset needs a batch step that reads operand planes (tensor-core kernels)")
         # two copy-free routes: (a) the register-converting kernel reading raw fp32 X through the index (Dw in {128, 256,
         # 384, 512}), (b) the planes kernel gathering rows of the full dataset's planes with cp.async (any Dw in [16, 512]).
         # Measured on B200 (profiles/r02_minibatch.json): (b) wins at Dw = 512 (0.56 vs 0.49 of the HBM roofline at 512 Ki
         # rows), (a) at the narrower exact widths (Dw = 128: 271 vs 335 us per 1 Mi rows), and only (b) exists elsewhere.
-        raw_ok = X is not None and self.copy_free and engine.supports_row_index(self.S, self.B)
+        raw_ok = X is not None and not prepared and self.copy_free and engine.supports_row_index(self.S, self.B)
         planes_ok = tma_fed and self.copy_free and engine.supports_row_index(self.S, self.B, planes=True)
         via_planes = planes_ok and (engine.Dw > 384 or not raw_ok)
         st["indexed"] = X is not None and self.copy_free and (via_planes or raw_ok)
@@ -76,9 +81,12 @@ class MinibatchLoss:
         if tma_fed and (via_planes or not st["indexed"]):
             # keep the FULL dataset as planes (made once): the step gathers its rows itself, or the sampler copies them
             lib = engine.lib
-            full = torch.empty(int(lib.bjx_x_planes_bytes(N, engine.Dw)), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                nv.check(lib.bjx_prepare_x_planes(X.data_ptr(), N, engine.Dw, ldx, full.data_ptr(), nv.current_stream_ptr()))
+            if prepared:
+                full = X.planes
+            else:
+                full = torch.empty(int(lib.bjx_x_planes_bytes(N, engine.Dw)), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    nv.check(lib.bjx_prepare_x_planes(X.data_ptr(), N, engine.Dw, ldx, full.data_ptr(), nv.current_stream_ptr()))
             st["planes_full"] = full
             if not st["indexed"]:
                 st["planes_b"] = torch.empty(int(lib.bjx_x_planes_bytes(self.B, engine.Dw)), dtype=torch.uint8, device=dev)
@@ -89,6 +97,8 @@ class MinibatchLoss:
         if st["planes_b"] is not None:
             mb.x_planes_full, mb.planes_b = st["planes_full"].data_ptr(), st["planes_b"].data_ptr()
         elif X is not None and not st["indexed"]:
+            if prepared:
+                raise TypeError("this batch step reads fp32 rows; a PreparedX dataset holds only operand planes")
             mb.X_full, mb.Xb = X.data_ptr(), st["Xb"].data_ptr()
         st["mb"] = mb
         self._state = st

@@ -226,6 +226,12 @@ BJX_API int bjx_elbo_step_host(const BjxElboArgs* args, const uint32_t* key_host
  * relative), each [N, round_up(Dw, 64)] row-major, back to back in `planes` (bjx_x_planes_bytes bytes, 16-byte aligned). */
 BJX_API size_t bjx_x_planes_bytes(int64_t N, int64_t Dw);
 BJX_API int bjx_prepare_x_planes(const float* X, int64_t N, int64_t Dw, int64_t ldx, void* planes, void* stream);
+/* The same split chunk by chunk (ABI 4): X_rows [rows, ldx] holds rows [row0, row0 + rows) of an N_total-row dataset whose planes
+ * (bjx_x_planes_bytes(N_total, Dw) bytes) are being filled -- fp32 X then never has to be resident on the device as a whole:
+ * stream it through a staging buffer and keep only the planes (4 bytes per element).  A step may then pass X = NULL with
+ * x_planes set wherever the planned kernel reads the planes (bjx_elbo_kernel_choice 2, or 4 outside BJX_PREC_BF16X3). */
+BJX_API int bjx_prepare_x_planes_rows(const float* X_rows, int64_t rows, int64_t Dw, int64_t ldx, void* planes, int64_t N_total,
+                                      int64_t row0, void* stream);
 
 /* which streaming kernel a given problem resolves to: 0 = fp32 tiled, 1 = fp32 small-D, 2 = fused tcgen05 single pass
  * (split-bf16), 3 = coin toss, 4 = two-pass TMA-fed tcgen05 GEMM (split-bf16) */

@@ -717,3 +717,65 @@ def test_sample_count_invariance_of_eps_layout():
     eng.step(br.PRNGKey(3), loc, raw, None, X, y, 1.0, 32, eps_out=e32, partitionable=True)
     eng.step(br.PRNGKey(3), loc, raw, None, X, y, 1.0, 8, eps_out=e8, partitionable=True)
     assert torch.equal(e32[: 8 * D], e8)
+
+
+def test_dataset_held_only_as_planes():
+    """bj.PreparedX: X streamed through a staging buffer (host tensor in ragged chunks) and kept on the device only as its
+    split-bf16 planes.  The planes equal bjx_prepare_x_planes of the whole matrix bit for bit; the step, the host-buffer step,
+    the two-pass GEMM path and the device-resident training loop give the very numbers they give on the fp32 tensor; shapes
+    whose kernel reads fp32 X refuse it."""
+    from functools import partial
+
+    import bijax_b200 as bj
+    from bijax_b200 import _native as nv
+    from bijax_b200 import optim
+    from bijax_b200 import random as br
+
+    N, D, S = 10_000, 200, 32
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    Xp = bj.PreparedX.from_tensor(torch.tensor(X), chunk_rows=3333)  # from the HOST, ragged chunks
+    assert Xp.shape == (N, D) and Xp.rows_filled == N
+    lib = nv.load()
+    whole = torch.empty(int(lib.bjx_x_planes_bytes(N, D)), dtype=torch.uint8, device="cuda")
+    nv.check(lib.bjx_prepare_x_planes(Xd.data_ptr(), N, D, D, whole.data_ptr(), nv.current_stream_ptr()))
+    assert torch.equal(whole, Xp.planes)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, _ = C.build_pair(prior, {}, lk.BernoulliLogits())
+    eng = model._engine_for({})[0]
+    loc = 0.05 * br.normal(br.PRNGKey(5), (D,), partitionable=True)
+    raw = torch.full((D,), -2.0, device="cuda")
+    key = br.PRNGKey(9)
+    want = eng.step(key, loc, raw, None, Xd, yd, 1.0, S).clone()
+    got = eng.step(key, loc, raw, None, Xp, yd, 1.0, S).clone()
+    assert eng.kernel_choice(S, N) == "tcgen05_bf16_split" and torch.equal(got, want)
+    # through the reference-facing surface, and the autograd route
+    params = {"posterior": {"loc": loc, "scale_diag": raw}}
+    l1, g1 = model.value_and_grad(params, yd, {"X": Xp}, N, key, S)
+    l2, g2 = model.value_and_grad(params, yd, {"X": Xd}, N, key, S)
+    assert l1.item() == l2.item() and torch.equal(g1["posterior"]["loc"], g2["posterior"]["loc"])
+    # the two-pass GEMM path (S = 64) reads only planes as well
+    w64 = eng.step(key, loc, raw, None, Xd, yd, 1.0, 64).clone()
+    g64 = eng.step(key, loc, raw, None, Xp, yd, 1.0, 64).clone()
+    assert eng.kernel_choice(64, N) == "tcgen05_gemm_two_pass" and torch.equal(g64, w64)
+    # the device-resident training loop
+    fresh = lambda: model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.01 * br.normal(k, shape))
+    a = bj.train(partial(model.loss_fn, outputs=yd, inputs={"X": Xp}, full_data_size=N, n_samples=S), fresh(), optim.adam(0.02), 40, br.PRNGKey(3))
+    b = bj.train(partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=S), fresh(), optim.adam(0.02), 40, br.PRNGKey(3))
+    assert torch.equal(a["losses"], b["losses"])
+    # minibatches drawn on the device out of the planes alone
+    mb_p = model.minibatch_loss_fn(yd, {"X": Xp}, batch_size=2048, n_samples=S, copy_free=True)
+    mb_t = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=2048, n_samples=S, copy_free=True)
+    vp, _ = bj.value_and_grad(mb_p)(params, br.PRNGKey(21))
+    vt, _ = bj.value_and_grad(mb_t)(params, br.PRNGKey(21))
+    assert vp.item() == vt.item() and mb_p._state["planes_full"] is Xp.planes
+    # a shape whose kernel reads fp32 X
+    small = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(5, np.float32), scale_diag=np.ones(5, np.float32))}, {}, lk.BernoulliLogits())
+    X5 = bj.PreparedX.from_tensor(torch.zeros(100, 5))
+    with pytest.raises(TypeError):
+        small.value_and_grad({"posterior": {"loc": torch.zeros(5, device="cuda"), "scale_diag": torch.zeros(5, device="cuda")}},
+                             torch.zeros(100, device="cuda"), {"X": X5}, 100, key, 4)
+    with pytest.raises(RuntimeError):  # incomplete
+        half = bj.PreparedX(10, D)
+        half.append(torch.zeros(4, D))
+        eng.step(key, loc, raw, None, half, yd[:10], 1.0, S)
