@@ -326,17 +326,27 @@ def collect_kernel_ms(lib, nv, K):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def make_c3_data(br, torch, rows, row0, n_total, dev):
+def make_c3_data(br, torch, rows, row0, n_total, dev, planes_only=True, chunk=1 << 20):
+    """The synthetic shard [row0, row0 + rows) of the n_total-row dataset (counter = global flat index, so a shard is a slice of
+    the global stream).  planes_only: X is generated chunk by chunk and kept on the device ONLY as its split-bf16 operand planes
+    (bj.PreparedX: 4 bytes per element, the footprint of fp32 -- the dataset is resident once, not twice); otherwise the fp32
+    matrix is returned (the raw-fp32 kernels, or an engine that prepares the planes itself)."""
+    import bijax_b200 as bj
+
     D = D_C3
-    X = torch.empty((rows, D), dtype=torch.float32, device=dev)
-    br.normal(br.PRNGKey(1234), (rows * D,), partitionable=True, offset=row0 * D, total=n_total * D, out=X.view(-1))
-    X.mul_(1.0 / math.sqrt(D))
     w_true = br.normal(br.PRNGKey(1235), (D,), partitionable=True)
     u = br.uniform(br.PRNGKey(1236), (rows,), partitionable=True, offset=row0, total=n_total)
     y = torch.empty(rows, dtype=torch.float32, device=dev)
-    chunk = 1 << 20
+    X = bj.PreparedX(rows, D, dev) if planes_only else torch.empty((rows, D), dtype=torch.float32, device=dev)
+    buf = torch.empty((min(chunk, rows), D), dtype=torch.float32, device=dev) if planes_only else None
     for i in range(0, rows, chunk):
-        y[i : i + chunk] = (u[i : i + chunk] < torch.sigmoid(X[i : i + chunk] @ w_true)).float()
+        n = min(chunk, rows - i)
+        blk = buf[:n] if planes_only else X[i : i + n]
+        br.normal(br.PRNGKey(1234), (n * D,), partitionable=True, offset=(row0 + i) * D, total=n_total * D, out=blk.view(-1))
+        blk.mul_(1.0 / math.sqrt(D))
+        y[i : i + n] = (u[i : i + n] < torch.sigmoid(blk @ w_true)).float()
+        if planes_only:
+            X.append(blk)
     return X, y
 
 
@@ -362,7 +372,7 @@ def multi_gpu_check(torch, dist, br, engine, p2p, world, rank, dev):
     # (2) sharded step == single-GPU step
     n_chk, S = 2_000_000, S_C3
     lo, hi = rank * n_chk // world, (rank + 1) * n_chk // world
-    Xs, ys = make_c3_data(br, torch, hi - lo, lo, n_chk, dev)
+    Xs, ys = make_c3_data(br, torch, hi - lo, lo, n_chk, dev, planes_only=False)
     loc = 0.02 * br.normal(br.PRNGKey(5), (D_C3,), partitionable=True)
     raw = torch.full((D_C3,), math.log(0.1), device=dev)
     key = br.PRNGKey(77)
@@ -375,7 +385,7 @@ def multi_gpu_check(torch, dist, br, engine, p2p, world, rank, dev):
     del Xs, ys
     ok = torch.ones(1, device=dev)
     if rank == 0:
-        Xf, yf = make_c3_data(br, torch, n_chk, 0, n_chk, dev)
+        Xf, yf = make_c3_data(br, torch, n_chk, 0, n_chk, dev, planes_only=False)
         single = engine.step(key, loc, raw, None, Xf, yf, 1.0, S, 1.0, partitionable=False).clone()
         engine.release_planes()
         del Xf, yf
@@ -462,13 +472,15 @@ def run_c3(args):
 
     def measure(rows_, row0_, n_total_, want_e2e, want_sustained):
         """Data of `rows_` rows -> prepare -> W warm-ups -> K timed steps (+ e2e, + the >= 1 s sustained region)."""
-        X, y = make_c3_data(br, torch, rows_, row0_, n_total_, dev)
-        kernel = engine.kernel_choice(S, rows_)
         torch.cuda.synchronize()
         tp0 = time.perf_counter()
-        prepared = engine.prepare(X, y, S)  # once per dataset, outside the step: X -> split-bf16 planes (4 B/element)
+        # once per dataset, outside the step: X -> split-bf16 planes (4 B/element); with planes_only fp32 X is never resident
+        X, y = make_c3_data(br, torch, rows_, row0_, n_total_, dev, planes_only=not args.raw_fp32)
+        kernel = engine.kernel_choice(S, rows_)
+        prepared = engine.prepare(X, y, S)
         torch.cuda.synchronize()
         prepare_ms = 1e3 * (time.perf_counter() - tp0)
+        dataset_gb = (X.nbytes if prepared and not args.raw_fp32 else 4.0 * rows_ * D) / 1e9
         loc = torch.zeros(D, device=dev)
         raw = torch.full((D,), math.log(0.1), device=dev)
         ll_scale = 1.0  # full_data_size / len(outputs), both global
@@ -505,7 +517,7 @@ def run_c3(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         r = {"kernel": kernel, "prepared": prepared, "prepare_ms": prepare_ms, "elapsed_ms": float(t[0]), "kernel_ms": float(t[1]),
-             "kernel_ms_min_rank": -float(t[2]), "clocks": clocks, "loss": float(out[0]), "rows": rows_}
+             "kernel_ms_min_rank": -float(t[2]), "clocks": clocks, "loss": float(out[0]), "rows": rows_, "dataset_gb": dataset_gb}
 
         if want_e2e:
             params_host = torch.cat([loc.cpu(), raw.cpu()]).pin_memory()
@@ -613,7 +625,8 @@ def run_c3(args):
                 "exchange": ("none (one GPU)" if world == 1 else
                              "one-shot all-reduce kernel over NVLink peer memory (bjx_allreduce_packed_p2p); NCCL only bootstraps and barriers"
                              if p2p is not None else "NCCL all-reduce"),
-                "dataset_layout": ("split-bf16 planes x1+x2 (4 B/element, prepared once per dataset in %.1f ms, TMA-fed kernel)" % main["prepare_ms"]
+                "dataset_layout": ("split-bf16 planes x1+x2 only (bj.PreparedX: 4 B/element, %.1f GB resident per GPU; generated + split chunk by "
+                                   "chunk in %.0f ms, fp32 X never resident as a whole; TMA-fed kernel)" % (main["dataset_gb"], main["prepare_ms"])
                                    if prepared else "raw fp32 X (converted in registers every step)"),
             },
             "clocks": main["clocks"], "e2e": main.get("e2e"), "gpu_launches": n_launch * K,
