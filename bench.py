@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c4"])
     ap.add_argument("--precision", default="auto")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="override the per-GPU row count (0 = config default)")
-    ap.add_argument("--cpu-rows", type=int, default=200_000, help="row sample of the cpu_baseline leg of our own arm")
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="row sample of the cpu_baseline leg of our own arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline leg of our own arm")
     ap.add_argument("--ref-seconds", type=float, default=100.0,
                     help="--impl reference: target wall time of all (steps + warmup) sampled steps; the row sample is sized to it")
@@ -524,11 +524,13 @@ def run_c3(args):
             out_host = torch.empty(1 + 2 * D).pin_memory()
             keys_host = keys.cpu().numpy()
             stage = torch.empty_like(out)
+            keys_host = np.ascontiguousarray(keys_host, dtype=np.uint32)
+            host_step = engine.host_stepper(X, y, ll_scale, S, prior_weight, partitionable=False) if world == 1 else None
 
             def e2e_step(i):
                 if world == 1:
-                    # the reference-facing C-ABI call: host key/params in, packed loss+grads out, synchronous
-                    engine.step_host(keys_host[i], params_host, out_host, X, y, ll_scale, S, prior_weight, partitionable=False)
+                    # the reference-facing C-ABI call (bjx_elbo_step_host): host key/params in, packed loss+grads out, synchronous
+                    host_step(keys_host[i], params_host, out_host)
                 else:
                     p = params_host.to(dev, non_blocking=True)
                     k = torch.from_numpy(keys_host[i].astype(np.int64)).to(torch.uint32).to(dev, non_blocking=True)

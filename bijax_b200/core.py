@@ -18,12 +18,6 @@ class Posterior:
         self.model, self.engine = model, engine
         self.loc, self.raw_scale = loc, raw_scale
 
-    def _scale(self):
-        name = type(self.model.posterior_params_bijector[1]).__name__
-        raw = self.raw_scale.to(self.engine.device, torch.float32)
-        s = torch.exp(raw) if name == "Exp" else torch.nn.functional.softplus(raw) if name == "Softplus" else raw
-        return s if self.model.vi_type == "mean_field" else torch.tril(s)
-
     def sample(self, seed, sample_shape=()):
         """core.py:46-55: constrained samples as a pytree with leading ``sample_shape``."""
         shape = tuple(int(s) for s in ((sample_shape,) if isinstance(sample_shape, int) else sample_shape))

@@ -325,6 +325,30 @@ class ElboEngine:
             )
         return out_host
 
+    def host_stepper(self, X, y, ll_scale, n_samples, prior_weight=1.0, partitionable=None):
+        """``step_host`` with everything that does not change between steps resolved ONCE (argument block, kernel choice,
+        planes, workspace): returns ``call(key_host uint32[2] ndarray, params_host pinned f32, out_host pinned f32)`` whose only
+        work per step is the one C call ``bjx_elbo_step_host`` -- what a host-driven training loop pays per step."""
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
+        a.X = self._x_ptr(X)
+        a.y = y.data_ptr()
+        a.x_planes = self._x_planes(a, X)
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        n_params = self.D + self.P + self.K
+        fn, ref, dev = self.lib.bjx_elbo_step_host, C.byref(a), self.device
+        keep = (X, y, ws, a)  # everything the argument block points at stays alive with the closure
+
+        def call(key_host: np.ndarray, params_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+            assert key_host.dtype == np.uint32 and key_host.size == 2 and key_host.flags.c_contiguous
+            assert params_host.numel() == n_params and out_host.numel() == 1 + n_params and keep is not None
+            with torch.cuda.device(dev):
+                nv.check(fn(ref, key_host.ctypes.data, params_host.data_ptr(), out_host.data_ptr(), nv.current_stream_ptr()))
+            return out_host
+
+        return call
+
     def point_step(self, z, X, y, ll_scale, mode, out=None) -> torch.Tensor:
         """Point evaluation at the unconstrained value z [D] (BjxElboArgs.point_mode): packed [value | d value / d z | 0...],
         value = -(log prior + ll_scale * log likelihood) with or without the bijectors' log-det-Jacobian
