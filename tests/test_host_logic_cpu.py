@@ -43,6 +43,12 @@ def test_which_calls_run_as_the_device_resident_loop():
     m2 = _FakeModel()
     m2._group = object()  # row-sharded: host-driven step + all-reduce
     assert U._fused_loop_spec(partial(m2.loss_fn, outputs=[1.0], inputs=None, full_data_size=1), adam, object(), frozenset()) is None
+    m2b = _FakeModel()  # row-sharded WITH the peer-memory exchange: the all-reduce runs on the device too (bjx_train_steps_sharded)
+    m2b._group, m2b._shard, m2b._p2p = object(), "rows", True
+    assert U._fused_loop_spec(partial(m2b.loss_fn, outputs=[1.0], inputs=None, full_data_size=1), adam, object(), frozenset()) is not None
+    m2c = _FakeModel()  # sample sharding stays host-driven
+    m2c._group, m2c._shard, m2c._p2p = object(), "samples", True
+    assert U._fused_loop_spec(partial(m2c.loss_fn, outputs=[1.0], inputs=None, full_data_size=1), adam, object(), frozenset()) is None
     m3 = _FakeModel()
     m3.packed_tril = True
     assert U._fused_loop_spec(partial(m3.loss_fn, outputs=[1.0], inputs=None, full_data_size=1), adam, object(), frozenset()) is None
