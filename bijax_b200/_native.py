@@ -23,7 +23,7 @@ PRIOR_NORMAL, PRIOR_BETA, PRIOR_GAMMA = 0, 1, 2
 LIK_BERNOULLI_LOGITS, LIK_GAUSSIAN, LIK_BERNOULLI_PROBS = 0, 1, 2
 NOISE_CONST, NOISE_KWARG, NOISE_LATENT = 0, 1, 2
 PREC_AUTO, PREC_FP32, PREC_BF16X3, PREC_BF16X2 = 0, 1, 2, 3
-POINT_OFF, POINT_LOG_JOINT, POINT_MAP = 0, 1, 2
+POINT_OFF, POINT_LOG_JOINT, POINT_MAP, POINT_LOGLIK = 0, 1, 2, 3
 KERNEL_NAMES = {0: "fp32_tiled", 1: "fp32_smalld", 2: "tcgen05_bf16_split", 3: "coin", 4: "tcgen05_gemm_two_pass"}
 KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 

@@ -79,7 +79,7 @@ int make_plan(const BjxElboArgs& a, Plan& p) {
               a.scale_bijector);
   BJX_REQUIRE(a.threefry_layout == BJX_LAYOUT_LEGACY || a.threefry_layout == BJX_LAYOUT_PARTITIONABLE,
               "unknown threefry layout %d", a.threefry_layout);
-  BJX_REQUIRE(a.point_mode >= BJX_POINT_OFF && a.point_mode <= BJX_POINT_MAP, "unknown point_mode %d", a.point_mode);
+  BJX_REQUIRE(a.point_mode >= BJX_POINT_OFF && a.point_mode <= BJX_POINT_LOGLIK, "unknown point_mode %d", a.point_mode);
   BJX_REQUIRE(a.point_mode == BJX_POINT_OFF || (a.S == 1 && a.S_total == 0 && a.vi_type == BJX_VI_MEAN_FIELD),
               "point evaluation needs S == 1, no sample sharding and vi_type = mean field (raw_scale is ignored)");
   BJX_REQUIRE(a.S_total == 0 || (a.s_offset >= 0 && a.s_offset + a.S <= a.S_total), "sample shard [s_offset, s_offset+S) must lie in [0, S_total)");
@@ -269,7 +269,19 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
       logsig = scale_bij == BJX_SCALE_EXP ? rho : logf(sc.sigma);
     }
     if (eps_out) eps_out[i] = eps;
-    const CoordEval ce = eval_coord(z, coords[d]);
+    CoordEval ce;
+    if (point_mode == BJX_POINT_LOGLIK) {
+      // loc IS the constrained value: no bijector, no prior; derivatives are with respect to theta itself
+      ce.theta = z;
+      ce.dtheta = 1.0f;
+      ce.logp = ce.dlogp = ce.ldj = ce.dldj = 0.0f;
+      ce.lt = logf(z);
+      ce.l1t = log1pf(-z);
+      ce.dlt = 1.0f / z;
+      ce.dl1t = -1.0f / (1.0f - z);
+    } else {
+      ce = eval_coord(z, coords[d]);
+    }
     theta[i] = ce.theta;
     bprime[i] = ce.dtheta;
     gprior[i] = point_mode == BJX_POINT_MAP ? -(ce.dlogp - ce.dldj) : -ce.dlogp;
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(256) k_prologue(const uint32_t* __restrict__ k
     term = (-0.5f * eps * eps - logsig - BJX_HALF_LOG_2PI) - ce.logp;
     if (point_mode == BJX_POINT_LOG_JOINT) term = -ce.logp;               // no variational term
     if (point_mode == BJX_POINT_MAP) term = -(ce.logp - ce.ldj);          // prior density of theta = b(z), map.py:30
+    if (point_mode == BJX_POINT_LOGLIK) term = 0.0f;                      // the likelihood alone
   }
   const float t = block_sum(term, red);
   if (threadIdx.x == 0) qp_part[blockIdx.x] = t;

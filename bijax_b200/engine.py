@@ -349,12 +349,13 @@ class ElboEngine:
 
         return call
 
-    def point_step(self, z, X, y, ll_scale, mode, out=None) -> torch.Tensor:
-        """Point evaluation at the unconstrained value z [D] (BjxElboArgs.point_mode): packed [value | d value / d z | 0...],
-        value = -(log prior + ll_scale * log likelihood) with or without the bijectors' log-det-Jacobian
-        (MCMC.log_joint, mcmc.py:30-34 / MAP.neg_log_joint, map.py:27-33)."""
-        if self.vi_type != nv.VI_MEAN_FIELD or self.K:
-            raise NotImplementedError("point evaluation runs on a mean-field engine without trainable kwargs")
+    def point_step(self, z, X, y, ll_scale, mode, out=None, kwargs_vec=None) -> torch.Tensor:
+        """Point evaluation at the unconstrained value z [D] (BjxElboArgs.point_mode): packed [value | d value / d z | 0... |
+        d kwargs], value = -(log prior + ll_scale * log likelihood) with or without the bijectors' log-det-Jacobian
+        (MCMC.log_joint, mcmc.py:30-34 / MAP.neg_log_joint, map.py:27-33), or -ll_scale * log likelihood at the CONSTRAINED
+        value z itself (POINT_LOGLIK: the user-facing log_likelihood_fn, README.md:81-106)."""
+        if self.vi_type != nv.VI_MEAN_FIELD or (self.K and kwargs_vec is None):
+            raise NotImplementedError("point evaluation runs on a mean-field engine; trainable kwargs must be passed as kwargs_vec")
         dev = self.device
         z = self._f32(z, dev).reshape(-1)
         if z.numel() != self.D:
@@ -365,10 +366,16 @@ class ElboEngine:
         if self._point_key is None:
             self._point_key = torch.zeros(2, dtype=torch.uint32, device=dev)
         a.key, a.loc, a.raw_scale = self._point_key.data_ptr(), z.data_ptr(), z.data_ptr()  # raw_scale is ignored
+        kw = None
+        if self.K:
+            kw = self._f32(kwargs_vec, dev).reshape(-1)
+            if kw.numel() != self.K:
+                raise ValueError(f"expected {self.K} kwarg values")
+            a.kwargs = kw.data_ptr()
         a.X = self._x_ptr(X)
         a.y = y.data_ptr()
         if out is None:
-            out = torch.empty(1 + 2 * self.D, dtype=torch.float32, device=dev)
+            out = torch.empty(1 + 2 * self.D + self.K, dtype=torch.float32, device=dev)
         a.out = out.data_ptr()
         a.x_planes = self._x_planes(a, X)
         ws = self._workspace(a)

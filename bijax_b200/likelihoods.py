@@ -15,12 +15,33 @@ from typing import Optional
 
 
 class Likelihood:
-    pass
+    """Base of the recognised families.  Besides describing the likelihood to the engine, an instance IS the callable of
+    the reference's contract (README.md:81-106):
+
+        log_likelihood_fn(latent_sample, outputs, inputs, **kwargs) -> scalar log-likelihood
+
+    with ``latent_sample`` a dict of CONSTRAINED latent values (e.g. one posterior sample, ``{"weights": w}``) and ``kwargs`` the
+    trainable likelihood parameters (e.g. ``log_noise_scale=...``).  The call runs on the same CUDA kernels as the ELBO step
+    (a point evaluation, ``BJX_POINT_LOGLIK``) and is differentiable with respect to the latent leaves and the kwargs."""
+
+    def latent_names(self):
+        raise NotImplementedError
+
+    def kwarg_names(self):
+        return ()
+
+    def __call__(self, latent_sample, outputs, inputs=None, **kwargs):
+        from .point import log_likelihood
+
+        return log_likelihood(self, latent_sample, outputs, inputs, kwargs)
 
 
 class BernoulliLogits(Likelihood):
     def __init__(self, weights: str = "weights", X: str = "X"):
         self.weights, self.X = weights, X
+
+    def latent_names(self):
+        return (self.weights,)
 
 
 class GaussianLinear(Likelihood):
@@ -37,7 +58,16 @@ class GaussianLinear(Likelihood):
         self.weights, self.X = weights, X
         self.log_noise_scale, self.noise_latent, self.noise_scale = log_noise_scale, noise_latent, noise_scale
 
+    def latent_names(self):
+        return (self.weights,) + ((self.noise_latent,) if self.noise_latent is not None else ())
+
+    def kwarg_names(self):
+        return (self.log_noise_scale,) if self.log_noise_scale is not None else ()
+
 
 class BernoulliProbs(Likelihood):
     def __init__(self, probs: str):
         self.probs = probs
+
+    def latent_names(self):
+        return (self.probs,)

@@ -144,3 +144,60 @@ class MCMC(_PointModel):
 
     def transform(self, params):
         return self._transform(params)
+
+
+# ---- the likelihood object as the reference's callable (README.md:81-106) ------------------------------------------------------
+class _LogLikFunction(torch.autograd.Function):
+    """custom_vjp of log_likelihood_fn(latent_sample, outputs, inputs, **kwargs): one point evaluation gives the value and the
+    derivatives with respect to the constrained latent vector and the trainable kwargs."""
+
+    @staticmethod
+    def forward(ctx, theta, kw, run):
+        out = run(theta.detach(), None if kw is None else kw.detach())
+        ctx.save_for_backward(out)
+        ctx.n, ctx.k = theta.numel(), 0 if kw is None else kw.numel()
+        return -out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        n, k = ctx.n, ctx.k
+        return -g * out[1 : 1 + n], (-g * out[1 + 2 * n : 1 + 2 * n + k]) if k else None, None
+
+
+_LOGLIK_ENGINES: Dict[Any, Any] = {}
+
+
+def log_likelihood(L, latent_sample, outputs, inputs, kwargs) -> torch.Tensor:
+    """The scalar log-likelihood of ``outputs`` at the constrained ``latent_sample`` (see likelihoods.Likelihood.__call__)."""
+    import numpy as np
+
+    from . import distributions as tfd
+
+    names = sorted(L.latent_names())
+    missing = [n for n in names if n not in latent_sample]
+    if missing:
+        raise KeyError(f"latent_sample has no entry {missing[0]!r}")
+    knames = sorted(L.kwarg_names())
+    for n in knames:
+        if n not in kwargs:
+            raise KeyError(f"the likelihood needs the keyword argument {n!r}")
+    leaves = [torch.as_tensor(latent_sample[n]) for n in names]
+    dev = next((l.device for l in leaves if l.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+    sig = (id(L), tuple((n, tuple(l.shape)) for n, l in zip(names, leaves)), tuple(knames), str(dev))
+    if sig not in _LOGLIK_ENGINES:
+        # only the leaves the likelihood reads, in the flat layout of core.py:168-176; the priors are placeholders (never evaluated)
+        prior = {n: tfd.Normal(np.zeros(tuple(l.shape), np.float32), 1.0) for n, l in zip(names, leaves)}
+        latents = compile_latents(prior, fill_in_bijector({}, prior))
+        _LOGLIK_ENGINES[sig] = ElboEngine(latents, L, "mean_field", None, [(n, 1) for n in knames], device=dev)
+    eng = _LOGLIK_ENGINES[sig]
+    X = None
+    if eng.lik_id != nv.LIK_BERNOULLI_PROBS:
+        X = inputs[eng.x_name] if isinstance(inputs, dict) else inputs
+    theta = torch.cat([l.to(dev, torch.float32).reshape(-1) for l in leaves])
+    kw = torch.cat([torch.as_tensor(kwargs[n]).to(dev, torch.float32).reshape(-1) for n in knames]) if knames else None
+
+    def run(t, k):
+        return eng.point_step(t, X, outputs, 1.0, nv.POINT_LOGLIK, kwargs_vec=k)
+
+    return _LogLikFunction.apply(theta, kw, run)

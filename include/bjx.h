@@ -171,6 +171,9 @@ typedef struct BjxElboArgs {
    *   BJX_POINT_LOG_JOINT : out = -(log p~(z) + ll_scale * ll(b(z)))   = -MCMC.log_joint    (mcmc.py:30-34)
    *   BJX_POINT_MAP       : out = -(log p(b(z)) + ll_scale * ll(b(z))) = MAP.neg_log_joint  (map.py:27-33; prior density
    *                         of the constrained value, no log-det-Jacobian)
+   *   BJX_POINT_LOGLIK    : out = -ll_scale * ll(theta) with theta = loc ITSELF (the constrained value; no bijector, no prior)
+   *                         = minus what the user-facing log_likelihood_fn(latent_sample, outputs, inputs, **kwargs) returns
+   *                         (README.md:81-106), with d out / d theta in the `d loc` block and d kwargs in theirs (ABI 4)
    * and d out / d z in the `d loc` block. */
   int32_t point_mode;
   int32_t reserved3;
@@ -194,6 +197,7 @@ typedef struct BjxElboArgs {
 #define BJX_POINT_OFF 0
 #define BJX_POINT_LOG_JOINT 1
 #define BJX_POINT_MAP 2
+#define BJX_POINT_LOGLIK 3
 
 
 /* ---- library ------------------------------------------------------------ */

@@ -353,3 +353,53 @@ def test_row_sharded_device_resident_loop_on_a_world_of_one(tmp_path):
         model._p2p_op.close()
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["bernoulli_logits_d128", "gaussian_kwarg_d5", "gaussian_latent_noise_d40", "coin"])
+def test_likelihood_objects_are_the_reference_callable(case):
+    """README.md:81-106: ``log_likelihood_fn(latent_sample, outputs, inputs, **kwargs) -> scalar``.  The declarative objects
+    ARE that callable (a point evaluation on the same CUDA kernels, BJX_POINT_LOGLIK): value and gradients with respect to the
+    constrained latent leaves and the trainable kwargs against the float64 restatement of the same exemplar."""
+    from oracle import advi_ref as R
+    from tests import cases as C
+
+    dev = torch.device("cuda")
+    kwargs, okw = {}, {}
+    if case == "coin":
+        L, ofn = lk.BernoulliProbs("p"), R.bernoulli_probs_loglik("p")
+        y = np.array([1.0 if n % 10 < 7 else 0.0 for n in range(777)], dtype=np.float32)
+        X, latent = None, {"p": np.float32(0.37)}
+    else:
+        D = {"bernoulli_logits_d128": 128, "gaussian_kwarg_d5": 5, "gaussian_latent_noise_d40": 40}[case]
+        N = 3001
+        w = (0.3 * tf.normal(tf.prng_key(4), (D,), 1)).astype(np.float32)
+        if case == "bernoulli_logits_d128":
+            X, y = C.synth_logistic(N, D)
+            L, ofn, latent = lk.BernoulliLogits(), R.bernoulli_logits_loglik(), {"weights": w}
+        elif case == "gaussian_kwarg_d5":
+            X, y = C.synth_linear(N, D)
+            L, ofn, latent = lk.GaussianLinear(), R.gaussian_linear_loglik(), {"weights": w}
+            kwargs = {"log_noise_scale": np.float32(-0.4)}
+        else:
+            X, y = C.synth_linear(N, D)
+            L = lk.GaussianLinear(noise_latent="noise")
+            ofn, latent = C.oracle_likelihood(L), {"weights": w, "noise": np.float32(0.8), "unused": np.float32(3.0)}
+    t = lambda a, req=True: torch.tensor(np.asarray(a, dtype=np.float32), device=dev, requires_grad=req)
+    lat_t = {k: t(v, k != "unused") for k, v in latent.items()}
+    kw_t = {k: t(v) for k, v in kwargs.items()}
+    inputs = {"X": torch.tensor(X, device=dev)} if X is not None else None
+    got = L(lat_t, torch.tensor(y, device=dev), inputs, **kw_t)
+    assert got.shape == ()
+    got.backward()
+    t64 = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)
+    lat_o = {k: t64(v) for k, v in latent.items() if k != "unused"}
+    kw_o = {k: t64(v) for k, v in kwargs.items()}
+    want = ofn(lat_o, torch.tensor(y, dtype=torch.float64), {"X": torch.tensor(X, dtype=torch.float64)} if X is not None else None, **kw_o)
+    want.backward()
+    C.assert_close(got.item(), want.item(), what="log-likelihood")
+    for k in lat_o:
+        C.assert_close(lat_t[k].grad.cpu().numpy(), lat_o[k].grad.numpy(), what=f"d / d {k}")
+    for k in kw_o:
+        C.assert_close(kw_t[k].grad.cpu().numpy(), kw_o[k].grad.numpy(), what=f"d / d {k}")
+    with pytest.raises(KeyError):
+        L({}, torch.tensor(y, device=dev), inputs, **kw_t)
