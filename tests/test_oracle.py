@@ -388,3 +388,19 @@ def test_float_spec_building_blocks():
     for other in (b, c):
         d = np.abs(a.view(np.int32).astype(np.int64) - other.view(np.int32).astype(np.int64))
         assert d.max() <= 4 and 0.0 < (d > 0).mean() < 0.05
+
+
+def test_values_published_in_the_jax_documentation():
+    """tests/golden/threefry_kat.json "jax_docs": split chains, normals of subkeys, a (3,) draw and a uniform printed in JAX's
+    public docs, for both counter layouts -- all exact."""
+    for name, layout in (("legacy", tf.LAYOUT_LEGACY), ("partitionable", tf.LAYOUT_PARTITIONABLE)):
+        for v in KAT["jax_docs"][name]:
+            key = tf.prng_key(v["seed"]) if "seed" in v else np.array(v["key"], dtype=np.uint32)
+            if "split" in v:
+                assert tf.split(key, len(v["split"]), layout).tolist() == v["split"], v["what"]
+            if "normal" in v:
+                got = tf.normal(key, tuple(v["shape"]), layout).ravel()
+                assert np.array_equal(got, np.array(v["normal"], dtype=np.float32)), (v["what"], got)
+            if "uniform" in v:
+                got = tf.uniform(key, tuple(v["shape"]), layout).ravel()
+                assert np.array_equal(got, np.array(v["uniform"], dtype=np.float32)), (v["what"], got)

@@ -39,6 +39,33 @@ def test_known_answers_on_device():
     assert br.normal(br.PRNGKey(42), (), partitionable=False).item() == np.float32(-0.18471177)
     assert br.normal(br.PRNGKey(42), (), partitionable=True).item() == np.float32(-0.028304616)
     assert br.uniform(k0, (), partitionable=False).item() == np.float32(0.41845703)
+    assert br.normal(k0, (1,), partitionable=True).item() == np.float32(1.6226422)  # exact under the XLA Log1p / Cephes logf spec
+
+
+def test_values_published_in_the_jax_documentation_on_device():
+    """tests/golden/threefry_kat.json "jax_docs" on the CUDA generator: split chains, normals of subkeys, a (3,) draw, a uniform."""
+    import json
+    from pathlib import Path
+
+    import torch
+
+    from bijax_b200 import random as br
+
+    kat = json.loads((Path(__file__).parent / "golden" / "threefry_kat.json").read_text())["jax_docs"]
+    for name, part in (("legacy", False), ("partitionable", True)):
+        for v in kat[name]:
+            if "seed" in v:
+                key = br.PRNGKey(v["seed"])
+            else:
+                key = torch.tensor(np.array(v["key"], dtype=np.int64), dtype=torch.int64).to(torch.uint32).cuda()
+            if "split" in v:
+                assert br.split(key, len(v["split"]), partitionable=part).cpu().numpy().tolist() == v["split"], v["what"]
+            if "normal" in v:
+                got = br.normal(key, tuple(v["shape"]), partitionable=part).cpu().numpy().ravel()
+                assert np.array_equal(got, np.array(v["normal"], dtype=np.float32)), (v["what"], got)
+            if "uniform" in v:
+                got = br.uniform(key, tuple(v["shape"]), partitionable=part).cpu().numpy().ravel()
+                assert np.array_equal(got, np.array(v["uniform"], dtype=np.float32)), (v["what"], got)
 
 
 @pytest.mark.parametrize("layout", [0, 1])
