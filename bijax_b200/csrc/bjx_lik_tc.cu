@@ -680,7 +680,6 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         issue(sx, &bars->x_full[0], 0, cur);
       }
       for (int64_t it = 0; it < my_tiles; ++it) {
-        prefetch_rows(it + 2);
         load_rows(it + 1, nxt);
         if constexpr (RING) {
           const int q0 = (int)(it % R) * NBLK;
@@ -703,6 +702,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
             }
           }
         }
+        prefetch_rows(it + 2);  // AFTER this tile's copies: touches issued first would queue ahead of the copies GEMM1 is waiting for
 #pragma unroll
         for (int g = 0; g < 16; ++g) cur[g] = nxt[g];
         park_idx(it + 3);   // fetched during the previous iteration; its ring slot held tile it - 1
