@@ -771,16 +771,27 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
       } else if (p.kernel == KERNEL_TC_GEMM) {
         rc = launch_lik_gemm(a, p, ws, st);
       } else {
-        rc = launch_lik_tc(a, p, ws, st);
+        // the fused single pass takes 32 samples at a time: one launch per slice, each with its own block of the partials
+        for (int64_t s0 = 0; s0 < a.S && rc == BJX_OK; s0 += 32) rc = launch_lik_tc(a, p, ws, st, s0, a.S - s0 < 32 ? a.S - s0 : 32);
       }
       prof_mark(st, 1);
     }
     if (rc) return rc;
-    const int64_t SDw = a.S * Dw;
-    k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
-                                                                          (const float*)(ws + p.o_statpart), p.PS, SDw,
-                                                                          a.S, G, stat);
-    BJX_LAUNCH_CHECK("k_reduce_partials");
+    if (p.kernel == KERNEL_TC_BF16 && a.S > 32 && a.N > 0) {
+      for (int64_t s0 = 0; s0 < a.S; s0 += 32) {  // partials are laid out [slice][CTA][S_slice, Dw]
+        const int64_t Ss = a.S - s0 < 32 ? a.S - s0 : 32;
+        k_reduce_partials<<<(unsigned)((Ss * Dw + Ss + 31) / 32), 256, 0, st>>>(
+            (const float*)(ws + p.o_Gpart) + (size_t)p.PG * s0 * Dw, p.PG, (const float*)(ws + p.o_statpart) + (size_t)p.PS * s0, p.PS,
+            Ss * Dw, Ss, G + s0 * Dw, stat + s0);
+        BJX_LAUNCH_CHECK("k_reduce_partials");
+      }
+    } else {
+      const int64_t SDw = a.S * Dw;
+      k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
+                                                                            (const float*)(ws + p.o_statpart), p.PS, SDw,
+                                                                            a.S, G, stat);
+      BJX_LAUNCH_CHECK("k_reduce_partials");
+    }
   }
 
   TailArgs t;

@@ -39,7 +39,7 @@ int make_plan(const BjxElboArgs& a, Plan& p);
 int smalld_occupancy(int rec4);  // resident CTAs per SM of k_lik_smalld<rec4>
 int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
 int launch_lik_tiled(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
-int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st);
+int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st, int64_t s0, int64_t S_slice);
 bool tc_eligible(const BjxElboArgs& a);
 int tc_plan(const BjxElboArgs& a, Plan& p);          // fills tc_ctas / tc_terms
 size_t tc_theta_bytes(const BjxElboArgs& a, const Plan& p);

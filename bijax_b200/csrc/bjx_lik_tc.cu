@@ -1100,7 +1100,14 @@ static bool tc_exact_width(const BjxElboArgs& a) { return a.Dw >= 128 && a.Dw <=
 
 bool tc_eligible(const BjxElboArgs& a) {
   if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
-  if (a.S < 1 || a.S > tc::NS) return false;
+  if (a.S < 1) return false;
+  if (a.S > tc::NS) {
+    // More than 32 samples: TMEM holds G^T for 32 samples x 512 columns, so the single pass runs once per slice of 32 samples
+    // (X is read once per slice).  That beats the two-pass GEMM path -- X read twice plus the round trip of g through HBM,
+    // 8 * pad64(S) bytes per row -- only for a few slices of a narrow X: k * Dp * 1.15 <= 2 * Dp + 2 * Sp, Dp >= 128, k <= 3.
+    const int64_t k = (a.S + tc::NS - 1) / tc::NS, Dp = pad64(a.Dw), Sp = pad64(a.S);
+    if (k > 3 || Dp < 128 || 115 * k * Dp > 100 * (2 * Dp + 2 * Sp)) return false;
+  }
   if (a.precision == BJX_PREC_BF16X3) return false;  // the three-term split runs on the two-pass GEMM path
   // rows read through an index (minibatches): either the register-converting kernel on raw fp32 X, or -- with the FULL
   // dataset's planes and its row count -- the TMA-fed kernel gathering plane rows (tile::gather4)
@@ -1134,7 +1141,10 @@ size_t tc_theta_bytes(const BjxElboArgs& a, const Plan&) {
   return (!tc_exact_width(a) && a.x_planes == nullptr && a.row_index == nullptr) ? x_planes_bytes(a.N, a.Dw) : 0;
 }
 
-int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st) {
+int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t st, int64_t s0, int64_t S_slice) {
+  // one sample slice [s0, s0 + S_slice) of the step (S_slice <= 32): its theta rows, and its own block of the partial buffers
+  BjxElboArgs a = a_in;
+  a.S = S_slice;
   static bool env_read = false;
   if (!env_read) {
     if (const char* e = getenv("BJX_TC_STAGGER")) g_stagger = atoi(e);
@@ -1144,16 +1154,18 @@ int launch_lik_tc(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t st
     if (const char* e = getenv("BJX_TC_FLUSH")) g_flush = atoi(e) > 0 ? atoi(e) : 1;
     env_read = true;
   }
-  const float* theta = (const float*)(ws + p.o_theta);
-  float* Gpart = (float*)(ws + p.o_Gpart);
-  float* statpart = (float*)(ws + p.o_statpart);
+  const float* theta = (const float*)(ws + p.o_theta) + s0 * a.D;
+  float* Gpart = (float*)(ws + p.o_Gpart) + (size_t)p.PG * s0 * a.Dw;
+  float* statpart = (float*)(ws + p.o_statpart) + (size_t)p.PS * s0;
   const int64_t Dp = pad64(a.Dw);
   const int nblk = (int)(((Dp / tc::BLK_COLS) + 1) & ~1ll);  // even: GEMM2 works on 128-column chunks
   const size_t smem = tc_smem_bytes(nblk);
   const void* x_planes = a.x_planes;
   if (x_planes == nullptr && !tc_exact_width(a)) {
-    int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, ws + p.o_tc_theta, st);
-    if (rc) return rc;
+    if (s0 == 0) {  // the in-step split is made once, by the first slice
+      int rc = split_x_planes(a.X, a.N, a.Dw, a.ldx, ws + p.o_tc_theta, st);
+      if (rc) return rc;
+    }
     x_planes = ws + p.o_tc_theta;
   }
   if (x_planes != nullptr) {

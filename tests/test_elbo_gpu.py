@@ -238,7 +238,9 @@ def test_error_paths():
      (40000, 128, 32, "logit"), (30000, 384, 20, "gauss"), (50000, 256, 32, "logit"),  # several tiles per CTA for every block count
      # widths that are not a multiple of 128: planes padded to 64 columns, the missing blocks are TMA zero fill
      (20000, 500, 32, "logit"), (3000, 16, 32, "gauss"), (9000, 50, 5, "logit"), (4097, 64, 32, "logit"), (12000, 100, 17, "gauss"),
-     (30000, 200, 32, "logit"), (25000, 320, 32, "gauss"), (15000, 448, 9, "logit"), (777, 511, 32, "gauss"), (20000, 129, 32, "logit")],
+     (30000, 200, 32, "logit"), (25000, 320, 32, "gauss"), (15000, 448, 9, "logit"), (777, 511, 32, "gauss"), (20000, 129, 32, "logit"),
+     # more than 32 samples on a narrow X: the single pass once per slice of 32 samples (each slice its own block of partials)
+     (5000, 128, 64, "logit"), (3000, 256, 50, "gauss"), (20000, 384, 64, "logit"), (9000, 128, 96, "gauss"), (4000, 200, 40, "logit")],
 )
 @pytest.mark.parametrize("prepared", [True, False])
 def test_tensor_core_path(N, D, S, lik, prepared):

@@ -259,10 +259,10 @@ def test_step_gathering_plane_rows_equals_the_step_on_gathered_rows(D, S, N, B):
 
 
 def test_minibatch_on_the_two_pass_gemm_path():
-    """A batch step outside the fused kernel's envelope (S = 64 > 32) runs the TMA-fed two-pass GEMM on gathered plane rows:
+    """A batch step outside the fused kernel's envelope (S = 128: four slices of 32 samples would cost more than two passes) runs the TMA-fed two-pass GEMM on gathered plane rows:
     same numbers (to the rounding of its atomic reduction order) as loss_fn on host-indexed rows."""
     dev = torch.device("cuda")
-    N, D, B, S = 40000, 192, 16384, 64
+    N, D, B, S = 40000, 192, 16384, 128
     X, y = C.synth_logistic(N, D)
     Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
