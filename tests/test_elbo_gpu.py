@@ -782,3 +782,31 @@ def test_dataset_held_only_as_planes():
         half = bj.PreparedX(10, D)
         half.append(torch.zeros(4, D))
         eng.step(key, loc, raw, None, half, yd[:10], 1.0, S)
+
+
+def test_sample_slices_under_sample_sharding():
+    """Two sample shards of 48 + 48 samples (each more than one slice of 32) at D = 128 sum to the unsharded 96-sample step, and
+    the unsharded step matches the float64 oracle: the per-slice partial blocks, the global eps index and the sharding weights
+    compose."""
+    from bijax_b200 import random as br
+
+    N, D, S = 6000, 128, 96
+    X, y = C.synth_logistic(N, D)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.BernoulliLogits())
+    eng = model._engine_for({})[0]
+    assert eng.kernel_choice(S, N) == "tcgen05_bf16_split" and eng.kernel_choice(48, N) == "tcgen05_bf16_split"
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    loc = 0.05 * tf.normal(tf.prng_key(5), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    lt, rt = torch.tensor(loc, device="cuda"), torch.tensor(raw, device="cuda")
+    key = br.PRNGKey(13)
+    full = eng.step(key, lt, rt, None, Xd, yd, 1.0, S, partitionable=True).clone()
+    a = eng.step(key, lt, rt, None, Xd, yd, 1.0, 48, prior_weight=1.0, sample_shard=(0, S, 1.0), partitionable=True).clone()
+    b = eng.step(key, lt, rt, None, Xd, yd, 1.0, 48, prior_weight=1.0, sample_shard=(48, S, 0.0), partitionable=True).clone()
+    C.assert_close((a + b).cpu().numpy(), full.cpu().numpy(), rtol=2e-6, atol_scale=2e-6, what="sample shards")
+    (wl, wgl, wgr, _), _ = C.oracle_step(ref, loc, raw, {}, y, X, N, tf.prng_key(13), S, 1)
+    got = full.cpu().numpy()
+    C.assert_close(got[0], wl.item(), what="loss")
+    C.assert_close(got[1 : 1 + D], wgl.numpy(), what="d loc")
+    C.assert_close(got[1 + D :], wgr.numpy(), what="d raw scale")

@@ -292,3 +292,41 @@ def test_randint_against_the_committed_vectors():
     for c in fx["cases"]:
         got = br.randint(br.PRNGKey(c["seed"]), (c["n"],), c["minval"], c["maxval"], partitionable=bool(c["layout"]))
         assert got.cpu().tolist() == c["values"], c
+
+
+@pytest.mark.parametrize("D", [128, 200])
+def test_more_than_32_samples_through_the_index(D):
+    """S = 64 on a narrow X runs the fused single pass once per slice of 32 samples; through a row index every slice gathers the
+    batch's rows again (raw fp32 X at D = 128, the dataset's planes at D = 200).  Loss and gradients equal the step on rows gathered
+    by torch bit for bit, and the float64 oracle to rtol 1e-5; the device-resident loop equals the host-driven one."""
+    from bijax_b200 import utils as U
+
+    dev = torch.device("cuda")
+    N, B, S = 20000, 4097, 64
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device=dev), torch.tensor(y, device=dev)
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    model, ref = C.build_pair(prior, {}, lk.BernoulliLogits())
+    params = model.init(br.PRNGKey(0), initializer=lambda k, s: 0.05 * br.normal(k, s))
+    loss = model.minibatch_loss_fn(yd, {"X": Xd}, batch_size=B, n_samples=S, copy_free=True)
+    seed = br.PRNGKey(31)
+    got, g_got = bj.value_and_grad(loss)(params, seed)
+    st = loss._state
+    assert st["indexed"] and st["engine"].kernel_choice(S, B) == "tcgen05_bf16_split"
+    kb, ke = tf.split(tf.prng_key(31), 2, 0)
+    idx = tf.randint(kb, B, 0, N, 0)
+    li = torch.as_tensor(idx, device=dev).long()
+    ke_t = torch.tensor(ke.astype(np.int64), dtype=torch.int64).to(torch.uint32).to(dev)
+    same_route = model if st["planes_full"] is not None else bj.ADVI(prior, {}, lk.BernoulliLogits(), prepare_dataset=False)
+    want, g_want = same_route.value_and_grad(params, yd[li].contiguous(), {"X": Xd[li].contiguous()}, N, ke_t, S)
+    assert got.item() == want.item() and torch.equal(g_got["posterior"]["loc"], g_want["posterior"]["loc"])
+    loc, raw = params["posterior"]["loc"].cpu().numpy(), params["posterior"]["scale_diag"].cpu().numpy()
+    (wl, wgl, wgr, _), _ = C.oracle_step(ref, loc, raw, {}, y[idx], X[idx], N, ke, S, 0)
+    C.assert_close(got.item(), wl.item(), what="loss")
+    C.assert_close(g_got["posterior"]["loc"].cpu().numpy(), wgl.numpy(), what="d loc")
+    C.assert_close(g_got["posterior"]["scale_diag"].cpu().numpy(), wgr.numpy(), what="d raw scale")
+    n = 2 * U.GRAPH_STEPS + 1
+    fresh = lambda: model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.01 * br.normal(k, shape))
+    fused = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3))
+    host = bj.train(loss, fresh(), optim.adam(0.02), n_epochs=n, seed=br.PRNGKey(3), fused=False)
+    assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-5)
