@@ -526,15 +526,18 @@ def run_c3(args):
             stage = torch.empty_like(out)
             keys_host = np.ascontiguousarray(keys_host, dtype=np.uint32)
             host_step = engine.host_stepper(X, y, ll_scale, S, prior_weight, partitionable=False) if world == 1 else None
+            keys_pinned = torch.from_numpy(keys_host.astype(np.int64)).to(torch.uint32).pin_memory()
+            kdev, pdev = torch.zeros(2, dtype=torch.uint32, device=dev), torch.zeros(2 * D, device=dev)
+            dev_step = engine.stepper(kdev, pdev[:D], pdev[D:], None, X, y, ll_scale, S, stage, prior_weight, partitionable=False) if world > 1 else None
 
             def e2e_step(i):
                 if world == 1:
                     # the reference-facing C-ABI call (bjx_elbo_step_host): host key/params in, packed loss+grads out, synchronous
                     host_step(keys_host[i], params_host, out_host)
-                else:
-                    p = params_host.to(dev, non_blocking=True)
-                    k = torch.from_numpy(keys_host[i].astype(np.int64)).to(torch.uint32).to(dev, non_blocking=True)
-                    engine.step(k, p[:D], p[D:], None, X, y, ll_scale, S, prior_weight, out=stage, partitionable=False)
+                else:  # pinned key + params -> device, one C call for the step, the exchange kernel, packed result -> pinned host
+                    kdev.copy_(keys_pinned[i], non_blocking=True)
+                    pdev.copy_(params_host, non_blocking=True)
+                    dev_step()
                     allreduce(stage)
                     out_host.copy_(stage, non_blocking=False)
 

@@ -325,6 +325,36 @@ class ElboEngine:
             )
         return out_host
 
+    def stepper(self, key, loc, raw_scale, kwargs_vec, X, y, ll_scale, n_samples, out, prior_weight=1.0, partitionable=None):
+        """``step`` with fixed device buffers resolved ONCE: returns ``call()`` that enqueues one ELBO+grad step reading the
+        CURRENT contents of ``key`` / ``loc`` / ``raw_scale`` / ``kwargs_vec`` and writing ``out`` -- one C call per step (what a
+        host loop that refreshes those buffers with small copies pays)."""
+        dev = self.device
+        key = brandom._check_key(key)
+        for t in (loc, raw_scale, out):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        X, y, N, ldx = self._data(X, y)
+        a = self._args(n_samples, N, ldx if ldx else max(self.Dw, 1), ll_scale, prior_weight, brandom._layout(partitionable))
+        a.key, a.loc, a.raw_scale = key.data_ptr(), loc.data_ptr(), raw_scale.data_ptr()
+        if self.K:
+            a.kwargs = kwargs_vec.data_ptr()
+        a.X = self._x_ptr(X)
+        a.y = y.data_ptr()
+        a.out = out.data_ptr()
+        a.x_planes = self._x_planes(a, X)
+        ws = self._workspace(a)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        fn, ref = self.lib.bjx_elbo_step, C.byref(a)
+        keep = (key, loc, raw_scale, kwargs_vec, X, y, out, ws, a)
+
+        def call():
+            assert keep is not None
+            with torch.cuda.device(dev):
+                nv.check(fn(ref, nv.current_stream_ptr()))
+            return out
+
+        return call
+
     def host_stepper(self, X, y, ll_scale, n_samples, prior_weight=1.0, partitionable=None):
         """``step_host`` with everything that does not change between steps resolved ONCE (argument block, kernel choice,
         planes, workspace): returns ``call(key_host uint32[2] ndarray, params_host pinned f32, out_host pinned f32)`` whose only
