@@ -544,7 +544,7 @@ def run_c3(args):
             # same starting point as the device-timed region: a 1 kW part drops its clocks some 100 ms into a burst, and this
             # region would otherwise inherit the previous one's power state -- let the device idle, then warm up again
             barrier()
-            time.sleep(float(os.environ.get("BJX_BENCH_IDLE_S", "0.5")))
+            time.sleep(float(os.environ.get("BJX_BENCH_IDLE_S", "1.0")))
             for i in range(W + int(os.environ.get("BJX_BENCH_EXTRA_WARMUP", "0"))):
                 e2e_step(i % W)
             barrier()
@@ -553,13 +553,16 @@ def run_c3(args):
             for i in range(W, W + K):
                 e2e_step(i)
             barrier()
-            tt = torch.tensor([time.perf_counter() - tt0], dtype=torch.float64, device=dev)
+            tt1 = time.perf_counter()
+            tt = torch.tensor([tt1 - tt0], dtype=torch.float64, device=dev)
             e2e_kms = collect_kernel_ms(lib, nv, K)
+            e2e_clocks = sampler.window(tt0, tt1) if rank == 0 else None
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             r["e2e"] = {"value": K / float(tt[0]) * n_total_ / N_C3, "unit": UNIT, "h2d_bytes_per_step": 8 + params_host.numel() * 4,
                         "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * float(tt[0]) / K,
                         "kernel_ms": (sum(e2e_kms) / len(e2e_kms)) if e2e_kms else None,
+                        "kernel_ms_min_max": [min(e2e_kms), max(e2e_kms)] if e2e_kms else None, "clocks": e2e_clocks,
                         "note": "host key+params -> device, loss+grads -> host every step (bjx_elbo_step_host at N=1, wall clock); X, y are "
                                 "the device-resident dataset, as they are for the reference's jitted scan (utils.py:22-31); kernel_ms = the "
                                 "likelihood kernel inside THIS region (this rank), so ms_per_step - kernel_ms is the whole host + copy + small-kernel share"}
