@@ -165,9 +165,6 @@ class _LogLikFunction(torch.autograd.Function):
         return -g * out[1 : 1 + n], (-g * out[1 + 2 * n : 1 + 2 * n + k]) if k else None, None
 
 
-_LOGLIK_ENGINES: Dict[Any, Any] = {}
-
-
 def log_likelihood(L, latent_sample, outputs, inputs, kwargs) -> torch.Tensor:
     """The scalar log-likelihood of ``outputs`` at the constrained ``latent_sample`` (see likelihoods.Likelihood.__call__)."""
     import numpy as np
@@ -184,13 +181,14 @@ def log_likelihood(L, latent_sample, outputs, inputs, kwargs) -> torch.Tensor:
             raise KeyError(f"the likelihood needs the keyword argument {n!r}")
     leaves = [torch.as_tensor(latent_sample[n]) for n in names]
     dev = next((l.device for l in leaves if l.is_cuda), torch.device("cuda", torch.cuda.current_device()))
-    sig = (id(L), tuple((n, tuple(l.shape)) for n, l in zip(names, leaves)), tuple(knames), str(dev))
-    if sig not in _LOGLIK_ENGINES:
+    sig = (tuple((n, tuple(l.shape)) for n, l in zip(names, leaves)), tuple(knames), str(dev))
+    cache = L.__dict__.setdefault("_point_engines", {})  # lives and dies with the likelihood object
+    if sig not in cache:
         # only the leaves the likelihood reads, in the flat layout of core.py:168-176; the priors are placeholders (never evaluated)
         prior = {n: tfd.Normal(np.zeros(tuple(l.shape), np.float32), 1.0) for n, l in zip(names, leaves)}
         latents = compile_latents(prior, fill_in_bijector({}, prior))
-        _LOGLIK_ENGINES[sig] = ElboEngine(latents, L, "mean_field", None, [(n, 1) for n in knames], device=dev)
-    eng = _LOGLIK_ENGINES[sig]
+        cache[sig] = ElboEngine(latents, L, "mean_field", None, [(n, 1) for n in knames], device=dev)
+    eng = cache[sig]
     X = None
     if eng.lik_id != nv.LIK_BERNOULLI_PROBS:
         X = inputs[eng.x_name] if isinstance(inputs, dict) else inputs
