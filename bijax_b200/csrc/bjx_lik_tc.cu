@@ -490,6 +490,7 @@ struct Maps {
 struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
   unsigned long long x_full[9], x_empty[9];
   unsigned long long acc1_full[2], dl_full, dl_empty, done;  // one logits barrier per accumulator (tile parity)
+  unsigned long long px_full[2];  // PAIR: the peer CTA's partial logits of a tile (by tile parity) have landed (transaction bytes)
   uint32_t tmem_base;
 };
 }  // namespace tcp
@@ -497,7 +498,14 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 // IDX: row r of the problem is row ridx[r] of the planes (a minibatch drawn on the device, BjxElboArgs.row_index + x_planes +
 // N_full): the producer warp gathers the batch's rows straight out of the FULL dataset's planes with 16-byte cp.async copies
 // into the swizzled image, so a batch costs one pass over its own rows and nothing else.
-template <int NBLK, int EW, bool IDX>  // D / 64; epilogue warps (8 or 16); IDX adds a second producer warp at the end
+//
+// PAIR: a cluster of two CTAs works on one 64-row tile, each on HALF of the columns (CTA rank r owns columns [r * 64 * NBLK,
+// (r + 1) * 64 * NBLK)): every CTA runs GEMM1 over its own K range, the epilogue warps send their partial logits to the same
+// thread of the peer CTA through distributed shared memory (st.async + the peer's transaction barrier) and add what they
+// receive, both CTAs evaluate the link function on the (bit-identical) sums, and each runs GEMM2 for its own columns.  This
+// doubles the width one pass can hold -- TMEM has room for G^T of 512 columns x 32 samples per SM -- to D <= 1024, and at
+// D <= 512 it halves the bytes of a tile per SM, so that two tiles fit the slots (the ring mode of the narrow widths).
+template <int NBLK, int EW, bool IDX, bool PAIR>  // per-CTA D / 64; epilogue warps (8 or 16); IDX adds a second producer warp
 __global__ void __launch_bounds__((tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
@@ -514,8 +522,14 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   constexpr int SG = NS / HG;   // samples whose partial logits a thread loads (16 or 8)
   constexpr int VPT = SG / 2;   // (row, sample) pairs a thread finishes after the swap with its partner (8 or 4)
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
-  constexpr int D = NBLK * BLK_COLS;
+  static_assert(!(PAIR && IDX), "the gather variant runs one CTA per tile");
+  constexpr int D = NBLK * BLK_COLS;  // columns of THIS CTA
   constexpr int NCH = NBLK / 2;
+  // PAIR: rank in the cluster, tile sequence of the cluster (both CTAs walk the same tiles), first column of this CTA
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ncl = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int col0 = rank * D;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // Block 0 of a tile alternates between its regular slot and a spare one (index 8) placed one block BEFORE it, so the
@@ -532,6 +546,9 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   constexpr int R = 8 / NBLK;
   constexpr bool RING = R > 1;
   constexpr int NSLOT = RING ? 8 : NBLK;
+  // the spare slot of block 0 exists outside ring mode, except for a pair of 512-column CTAs: there its 16 KB are the two
+  // receive buffers of the partial-logit exchange (shared memory is full: 128 KB tile + 64 KB theta + 8 KB g + 8 KB swap)
+  constexpr bool SPARE = !RING && !(PAIR && NBLK == 8);
   uint8_t* sx = smem + SLOT;
   uint8_t* sth = sx + NSLOT * SLOT;
   uint8_t* sdl = sth + NBLK * BLK_BYTES;
@@ -540,10 +557,12 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   float* xch = (float*)(((uintptr_t)(sred + 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
   constexpr int XCH_FLOATS = EW * VPT * 32;                                    // (two of them in ring mode, see the epilogue)
   int32_t* sidx = reinterpret_cast<int32_t*>(xch + (RING ? 2 : 1) * XCH_FLOATS);  // IDX only: [4 tiles][64] ring of row indices
+  // PAIR: [tile parity][VPT / 4][EW * 32 threads] float4 written by the peer CTA; in the unused spare slot where there is one
+  float* pxch = SPARE ? xch + (RING ? 2 : 1) * XCH_FLOATS : reinterpret_cast<float*>(smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (N + TILE_ROWS - 1) / TILE_ROWS;
-  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = (n_tiles > cid) ? (n_tiles - cid + ncl - 1) / ncl : 0;
 
   if (tid == 0) {
     for (int b = 0; b < 9; ++b) {
@@ -551,6 +570,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
                                                   // gather: one cp.async.mbarrier.arrive per lane of the two producer warps
       mbar_init(&bars->x_empty[b], 1);
     }
+    mbar_init(&bars->px_full[0], 1);
+    mbar_init(&bars->px_full[1], 1);
     mbar_init(&bars->acc1_full[0], 1);
     mbar_init(&bars->acc1_full[1], 1);
     mbar_init(&bars->dl_full, EW);
@@ -566,7 +587,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const int s = idx / (D / 8), d8 = idx % (D / 8);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (s < S && d8 * 8 + j < Dw) ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
+    for (int j = 0; j < 8; ++j) v[j] = (s < S && col0 + d8 * 8 + j < Dw) ? theta[(int64_t)s * Dtot + w_off + col0 + d8 * 8 + j] : 0.0f;
     uint32_t p1[4], p2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], p1[j], p2[j]);
@@ -580,6 +601,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any store of mine can reach them
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == tcp::PROD_WARP || (IDX && warp == PROD_WARP2)) {
@@ -717,25 +739,26 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         auto issue_block0 = [&](int64_t t) {
           const int alt = (int)(t & 1);
           const int idx = alt ? 8 : 0;
-          const int64_t row0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
+          const int64_t row0 = ((int64_t)cid + t * ncl) * TILE_ROWS;
           mbar_wait(&bars->x_empty[idx], (uint32_t)(((t >> 1) & 1) ^ 1));  // released by chunk 0 of GEMM2 two tiles ago
           BJX_TRACE(t, 0);
           mbar_expect_tx(&bars->x_full[idx], 2u * BLK_BYTES);
           uint8_t* slot = alt ? sx - SLOT : sx;
-          tma_load_2d(slot, &maps.x1, 0, (int32_t)row0, &bars->x_full[idx]);
-          tma_load_2d(slot + BLK_BYTES, &maps.x2, 0, (int32_t)row0, &bars->x_full[idx]);
+          tma_load_2d(slot, &maps.x1, col0, (int32_t)row0, &bars->x_full[idx]);
+          tma_load_2d(slot + BLK_BYTES, &maps.x2, col0, (int32_t)row0, &bars->x_full[idx]);
         };
         const int pf_ahead = pf_dist * R;  // the same distance in bytes for every D
-        if (!RING && my_tiles > 0) issue_block0(0);
+        if (SPARE && my_tiles > 0) issue_block0(0);
         for (int64_t it = 0; it < my_tiles; ++it) {
-          const int64_t row0 = (blockIdx.x + it * gridDim.x) * TILE_ROWS;
+          const int64_t row0 = ((int64_t)cid + it * ncl) * TILE_ROWS;
           auto bulk_pf = [&]() {
-            // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane)
-            const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * TILE_ROWS;
+            // pull a later tile of both planes into L2 (rows of a tile are contiguous: 64 KB per plane at D = 512); in a
+            // pair each CTA takes one plane of the whole tile
+            const int64_t rowp = ((int64_t)cid + (it + pf_ahead) * ncl) * TILE_ROWS;
             const int64_t rows = (N - rowp) < TILE_ROWS ? (N - rowp) : TILE_ROWS;
             const uint32_t bytes = (uint32_t)(rows * Dp * 2);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
+            if (!PAIR || rank == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
+            if (!PAIR || rank == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
           };
           if (pf_mode == 0 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
           if constexpr (RING) {
@@ -746,19 +769,19 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
               mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
               BJX_TRACE(it, b);
               mbar_expect_tx(&bars->x_full[q], 2u * BLK_BYTES);
-              tma_load_2d(sx + q * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
-              tma_load_2d(sx + q * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+              tma_load_2d(sx + q * SLOT, &maps.x1, col0 + b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+              tma_load_2d(sx + q * SLOT + BLK_BYTES, &maps.x2, col0 + b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
             }
           } else {
-            for (int b = 1; b < NBLK; ++b) {
+            for (int b = SPARE ? 1 : 0; b < NBLK; ++b) {
               mbar_wait(&bars->x_empty[b], (uint32_t)((it & 1) ^ 1));  // GEMM2 of the previous tile released this block
               BJX_TRACE(it, b);
               mbar_expect_tx(&bars->x_full[b], 2u * BLK_BYTES);
-              tma_load_2d(sx + b * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
-              tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+              tma_load_2d(sx + b * SLOT, &maps.x1, col0 + b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
+              tma_load_2d(sx + b * SLOT + BLK_BYTES, &maps.x2, col0 + b * BLK_COLS, (int32_t)row0, &bars->x_full[b]);
               // block 0 of the NEXT tile goes into the other slot, free since chunk 0 of GEMM2(it - 1) like block 1: issue
               // it now, so that it has landed when the MMA warp wants to run it under this tile's epilogue
-              if (b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
+              if (SPARE && b == 1 && it + 1 < my_tiles) issue_block0(it + 1);
             }
           }
           if (pf_mode == 1 && pf_dist > 0 && it + pf_ahead < my_tiles) bulk_pf();
@@ -783,7 +806,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     // GEMM1 of one block into the logits accumulator of tile t's parity (two accumulators: block 0 of the next tile is
     // issued right after this tile's logits are committed, so it runs while the epilogue warps work on them)
     auto gemm1_block = [&](int64_t t, int b) {
-      const bool alt = (t & 1) != 0;
+      const bool alt = SPARE && (t & 1) != 0;  // block 0 sits in the spare slot
+      const bool acc_b = (t & 1) != 0;         // which logits accumulator
       if constexpr (RING) {
         const int q = (int)(t % R) * NBLK + b;
         mbar_wait(&bars->x_full[q], (uint32_t)((t / R) & 1));
@@ -792,14 +816,14 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         if (!(ablate & 1) && elect_one()) {
           const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);
           const uint64_t boff = (uint64_t)((q * SLOT) >> 4);
-          const uint32_t acc = tmem + ACC1_COL + (alt ? NB : 0);
+          const uint32_t acc = tmem + ACC1_COL + (acc_b ? NB : 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(acc, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
         }
         __syncwarp();
         return;
       }
-      if (b == 0)
+      if (b == 0 && SPARE)
         mbar_wait(&bars->x_full[alt ? 8 : 0], (uint32_t)((t >> 1) & 1));
       else
         mbar_wait(&bars->x_full[b], (uint32_t)(t & 1));
@@ -808,7 +832,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if (!(ablate & 1) && elect_one()) {
         const uint64_t toff = (uint64_t)((b * BLK_BYTES) >> 4);  // theta block
         const uint64_t boff = (b == 0 && alt) ? (uint64_t)(-(int64_t)(SLOT >> 4)) : (uint64_t)((b * SLOT) >> 4);  // X slot
-        const uint32_t acc = tmem + ACC1_COL + (alt ? NB : 0);
+        const uint32_t acc = tmem + ACC1_COL + (acc_b ? NB : 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(acc, dxa + boff + 2 * k, dth + toff + 2 * k, ID_G1, (b | k) != 0);
       }
@@ -819,13 +843,13 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         for (int b = 0; b < NBLK; ++b) gemm1_block(0, b);
         if (elect_one()) umma_commit(&bars->acc1_full[0]);
         __syncwarp();
-      } else {
+      } else if (SPARE) {
         gemm1_block(0, 0);
       }
     }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      const bool alt = RING ? false : (it & 1) != 0;
+      const bool alt = SPARE ? (it & 1) != 0 : false;
       const int idx0 = alt ? 8 : 0;
       const int q0 = RING ? (int)(it % R) * NBLK : 0;  // first slot of this tile
       if constexpr (RING) {
@@ -840,11 +864,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           __syncwarp();
         }
       } else {
-        for (int b = 1; b < NBLK; ++b) gemm1_block(it, b);
+        for (int b = SPARE ? 1 : 0; b < NBLK; ++b) gemm1_block(it, b);
         if (elect_one()) umma_commit(&bars->acc1_full[it & 1]);
         __syncwarp();
         if (lane == 0) BJX_TRACE(it, 24);
-        if (it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
+        if (SPARE && it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
       }
       mbar_wait(&bars->dl_full, ph);
       tc_fence_after();
@@ -895,7 +919,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     }
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
     const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
-    float* gp = Gpart + (size_t)blockIdx.x * S * Dw;  // the partial keeps the caller's [S, Dw] layout (Dw <= D = NBLK * 64)
+    float* gp = Gpart + (size_t)cid * S * Dw;  // the partial keeps the caller's [S, Dw] layout; a pair shares one, by columns
     // The GEMM2 accumulators are folded every few tiles (the tensor core's fp32 accumulate truncates) into an fp32 partial
     // that lives in the 128 TMEM columns left over ([384, 512): 4 chunks x 32 samples, lane = weight column): registers
     // add, tcgen05.st writes back -- no global-memory traffic until the single store at the end of the kernel.
@@ -916,7 +940,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           fp[j] = __float_as_uint(val);
         }
         if (final) {
-          const int d = ch * 128 + 32 * q + lane;
+          const int d = col0 + ch * 128 + 32 * q + lane;
           float* base = gp + (size_t)sb * Dw + d;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -930,9 +954,17 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
     int phase = 0;
     uint32_t flushed = 0;
-    int64_t row = (int64_t)blockIdx.x * TILE_ROWS + r;
+    int64_t row = (int64_t)cid * TILE_ROWS + r;
     float yv = (my_tiles > 0 && row < N) ? y[row] : 0.0f;
     uint32_t va[SG], vb[SG];  // partial logits of one tile
+    // PAIR: my slot in the peer's receive buffers and the peer's transaction barriers (shared::cluster addresses)
+    const int te = tid - tcp::EPI_WARP0 * 32;
+    constexpr int PX_FLOATS = EW * 32 * VPT;
+    uint32_t px_remote = 0, px_rbar = 0;
+    if constexpr (PAIR) {
+      px_remote = mapa_cluster(smem_u32(pxch) + (uint32_t)te * 16u, (uint32_t)(rank ^ 1));
+      px_rbar = mapa_cluster(smem_u32(&bars->px_full[0]), (uint32_t)(rank ^ 1));
+    }
     auto load_logits = [&](int64_t t) {
       mbar_wait(&bars->acc1_full[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
@@ -959,8 +991,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       const bool row_ok = row < N;
       const float ycur = yv;
       // fetch the next tile's label now: its latency hides behind this tile's GEMM1
-      row += (int64_t)gridDim.x * TILE_ROWS;
+      row += (int64_t)ncl * TILE_ROWS;
       yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
+      if constexpr (PAIR) {  // this tile's receive phase: EW * 32 threads x VPT floats from the peer
+        if (te == 0) mbar_expect_tx(&bars->px_full[it & 1], (uint32_t)(PX_FLOATS * sizeof(float)));
+      }
       // (Loading the next tile's logits early, under this tile's link function, was tried in ring mode and lost 10 %: the
       // wait for GEMM1(t+1) -- queued behind GEMM2(t-1) on the tensor pipe -- then sits in front of this tile's hand-over.)
       load_logits(it);
@@ -981,10 +1016,30 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
 #pragma unroll
       for (int j = 0; j < VPT; ++j) eta[j] += xch_mine[xoff + j * 32 + lane];
+      if constexpr (PAIR) {
+        // eta holds the logits over THIS CTA's columns: send them to the same thread of the peer, add what it sent.  Two
+        // receive buffers by tile parity: the peer writes tile t + 2 only after it has received my tile t + 1, which every
+        // warp of mine sends after reading buffer t.  a + b == b + a exactly, so both CTAs get the same bits.
+        const uint32_t po = (uint32_t)(it & 1) * (uint32_t)(PX_FLOATS * sizeof(float));
+        const uint32_t rb = px_rbar + (uint32_t)(it & 1) * 8u;
+#pragma unroll
+        for (int j4 = 0; j4 < VPT / 4; ++j4)
+          st_async_v4(px_remote + po + (uint32_t)j4 * (EW * 32 * 16), eta[4 * j4], eta[4 * j4 + 1], eta[4 * j4 + 2], eta[4 * j4 + 3], rb);
+        mbar_wait_cluster(&bars->px_full[it & 1], (uint32_t)((it >> 1) & 1));
+        const float4* mine = reinterpret_cast<const float4*>(pxch + (it & 1) * PX_FLOATS) + te;
+#pragma unroll
+        for (int j4 = 0; j4 < VPT / 4; ++j4) {
+          const float4 o = mine[j4 * (EW * 32)];
+          eta[4 * j4] += o.x;
+          eta[4 * j4 + 1] += o.y;
+          eta[4 * j4 + 2] += o.z;
+          eta[4 * j4 + 3] += o.w;
+        }
+      }
       if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
       // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
       // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
-      const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
+      const bool all_ok = (S == NS) && (row - (int64_t)ncl * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
       // Only g is on the critical path (GEMM2 waits for it): the loss bookkeeping (stat, prod) is done after the hand-over.
       float ope[VPT];
       if (ablate & 4) {
@@ -1064,8 +1119,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if (lane == 0) sred[q * NS + s0 + j] = v;  // the other (q, sample) slots stay zero
     }
     asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
-    if (warp == tcp::EPI_WARP0 && lane < S) {
-      statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+    if (warp == tcp::EPI_WARP0 && lane < S && rank == 0) {  // both CTAs of a pair hold the same sums: one reports them
+      statpart[(size_t)cid * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
     }
     mbar_wait(&bars->done, 0);
     tc_fence_after();
@@ -1079,6 +1134,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   tc_fence_before();
   __syncthreads();
   if (warp == tcp::MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+  if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while the peer may still store into its shared memory
 #undef BJX_TRACE
 }
 
@@ -1097,6 +1153,22 @@ static size_t tc_smem_bytes(int nblk) {
 static int64_t pad64(int64_t v) { return (v + 63) / 64 * 64; }
 // columns are a multiple of 128 in [128, 512]: both variants of the kernel apply (raw fp32 X or prepared planes)
 static bool tc_exact_width(const BjxElboArgs& a) { return a.Dw >= 128 && a.Dw <= 512 && a.Dw % 128 == 0; }
+
+// Two CTAs per tile, each on half of the columns (k_lik_tc_tma<..., PAIR>): every width in (512, 1024]; BJX_TC_PAIR=1 also
+// sends 256 < D <= 512 that way (development switch: two half-width tiles in the slots instead of one full-width tile).
+static int tc_pair_forced() {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("BJX_TC_PAIR");
+    forced = e ? atoi(e) : 0;
+  }
+  return forced;
+}
+static bool tc_pair(const BjxElboArgs& a) {
+  if (a.row_index != nullptr) return false;
+  return a.Dw > 512 || (tc_pair_forced() == 1 && a.Dw > 256 && a.x_planes != nullptr);
+}
+static int tc_max_clusters();
 
 bool tc_eligible(const BjxElboArgs& a) {
   if (a.likelihood != BJX_LIK_BERNOULLI_LOGITS && a.likelihood != BJX_LIK_GAUSSIAN) return false;
@@ -1120,7 +1192,8 @@ bool tc_eligible(const BjxElboArgs& a) {
   // bjx_prepare_x_planes): the kernel is instantiated for the next even number of 64-column blocks, and the blocks beyond
   // the plane's extent are zero-filled by the copy engine (out-of-bounds TMA boxes cost no HBM traffic).  The raw-fp32 /
   // row-index variant has no such fill, so a step without prepared planes splits X into the workspace first.
-  if (a.Dw < 16 || a.Dw > 512) return false;
+  if (a.Dw < 16 || a.Dw > 1024) return false;
+  if (a.Dw > 512 && (a.row_index != nullptr || tc_pair_forced() < 0)) return false;  // the pair kernel has no gather variant (BJX_TC_PAIR=-1: off)
   if (a.row_index != nullptr && a.x_planes == nullptr) return false;  // no planes to gather from, and no in-step split of a full dataset
   return true;
 }
@@ -1130,6 +1203,11 @@ int tc_plan(const BjxElboArgs& a, Plan& p) {
   if (sms <= 0) return fail(BJX_ERR_CUDA, "no CUDA device");
   const int64_t tiles = (a.N + tc::TILE_ROWS - 1) / tc::TILE_ROWS;
   int64_t g = tiles < sms ? tiles : sms;
+  if (tc_pair(a)) {  // one partial slot per CLUSTER of two CTAs
+    const int mc = tc_max_clusters();
+    if (mc <= 0) return fail(BJX_ERR_CUDA, "no cluster of two CTAs can be resident");
+    g = tiles < mc ? tiles : mc;
+  }
   if (g < 1) g = 1;
   p.tc_ctas = (int)g;
   p.tc_terms = 2;
@@ -1139,6 +1217,37 @@ int tc_plan(const BjxElboArgs& a, Plan& p) {
 // workspace for the operand planes when a width outside {128, 256, 384, 512} arrives without prepared planes
 size_t tc_theta_bytes(const BjxElboArgs& a, const Plan&) {
   return (!tc_exact_width(a) && a.x_planes == nullptr && a.row_index == nullptr) ? x_planes_bytes(a.N, a.Dw) : 0;
+}
+
+// how many clusters of two CTAs of the paired kernel can be resident at once (the largest instance: 227 KB, 320 threads)
+static int tc_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  const int smem = 227 * 1024;
+  if (cudaFuncSetAttribute(k_lik_tc_tma<8, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2u * 148u);
+  cfg.blockDim = dim3((tcp::EPI_WARP0 + 8) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_lik_tc_tma<8, 8, false, true>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  const int sms = sm_count();
+  if (n > sms / 2) n = sms / 2;
+  cached = n;
+  return n;
 }
 
 int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t st, int64_t s0, int64_t S_slice) {
@@ -1158,7 +1267,9 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
   float* Gpart = (float*)(ws + p.o_Gpart) + (size_t)p.PG * s0 * a.Dw;
   float* statpart = (float*)(ws + p.o_statpart) + (size_t)p.PS * s0;
   const int64_t Dp = pad64(a.Dw);
-  const int nblk = (int)(((Dp / tc::BLK_COLS) + 1) & ~1ll);  // even: GEMM2 works on 128-column chunks
+  const bool pair = tc_pair(a);
+  // 64-column blocks per CTA, even (GEMM2 works on 128-column chunks); a pair splits the blocks in two halves
+  const int nblk = pair ? (int)((((Dp / tc::BLK_COLS + 1) / 2) + 1) & ~1ll) : (int)(((Dp / tc::BLK_COLS) + 1) & ~1ll);
   const size_t smem = tc_smem_bytes(nblk);
   const void* x_planes = a.x_planes;
   if (x_planes == nullptr && !tc_exact_width(a)) {
@@ -1173,7 +1284,8 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
     const int nslot = 8 / nblk > 1 ? 8 : nblk;  // D = 128, 256: the eight slots are a ring of tiles (see the kernel)
     const size_t smem = (size_t)(2 * nslot + nblk + 3) * tc::BLK_BYTES + sizeof(tcp::BarsP) + 4 * tc::NS * sizeof(float) + 16 +
                         (nslot > nblk ? 2 : 1) * 8 * 256 * sizeof(float) + 1024 +
-                        (a.row_index != nullptr ? 4 * tc::TILE_ROWS * sizeof(int32_t) : 0);  // + the gather variant's index ring
+                        (a.row_index != nullptr ? 4 * tc::TILE_ROWS * sizeof(int32_t) : 0) +  // + the gather variant's index ring
+                        (pair && nblk == 6 ? 2 * 8 * 256 * sizeof(float) : 0);  // + a pair's receive buffers where no spare slot is left over
     static int pf_tiles = -1;
     if (pf_tiles < 0) {
       const char* e = getenv("BJX_TC_PF_TILES");
@@ -1198,11 +1310,44 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
   do {                                                                                                                    \
     static DeviceOnce attr_set;                                                                                         \
     if (!attr_set.test_and_set()) {                                                                                                      \
-      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW, IDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW, IDX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK, EW, IDX><<<p.tc_ctas, (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
+    k_lik_tc_tma<NBLK, EW, IDX, false><<<p.tc_ctas, (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
                                                               a.likelihood, Gpart, statpart, idx ? pf_idx : pf_tiles, flush_tma, g_ablate, g_trace, a.row_index, plane_rows); \
   } while (0)
+    // a pair of CTAs per tile: p.tc_ctas counts clusters
+#define BJX_TCP_LAUNCH_PAIR(NBLK)                                                                                                \
+  do {                                                                                                                            \
+    static DeviceOnce attr_set;                                                                                                   \
+    if (!attr_set.test_and_set()) {                                                                                               \
+      BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    }                                                                                                                             \
+    cudaLaunchConfig_t cfg = {};                                                                                                  \
+    cfg.gridDim = dim3(2u * (unsigned)p.tc_ctas);                                                                                 \
+    cfg.blockDim = dim3((tcp::EPI_WARP0 + 8) * 32);                                                                               \
+    cfg.dynamicSmemBytes = smem;                                                                                                  \
+    cfg.stream = st;                                                                                                              \
+    cudaLaunchAttribute attr[1];                                                                                                  \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                             \
+    attr[0].val.clusterDim.x = 2;                                                                                                 \
+    attr[0].val.clusterDim.y = 1;                                                                                                 \
+    attr[0].val.clusterDim.z = 1;                                                                                                 \
+    cfg.attrs = attr;                                                                                                             \
+    cfg.numAttrs = 1;                                                                                                             \
+    BJX_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_lik_tc_tma<NBLK, 8, false, true>, maps, planes, a.y, a.N, theta, a.D, a.w_offset,     \
+                                    (int)a.Dw, (int)Dp, (int)a.S, (int)a.likelihood, Gpart, statpart, pf_tiles, flush_tma, g_ablate,   \
+                                    g_trace, (const int32_t*)nullptr, plane_rows));                                               \
+  } while (0)
+    if (pair) {
+      switch (nblk) {
+        case 4: BJX_TCP_LAUNCH_PAIR(4); break;
+        case 6: BJX_TCP_LAUNCH_PAIR(6); break;
+        case 8: BJX_TCP_LAUNCH_PAIR(8); break;
+        default: return fail(BJX_ERR_UNSUPPORTED, "paired tcgen05 kernel needs 256 < D <= 1024");
+      }
+      BJX_LAUNCH_CHECK("k_lik_tc_tma<pair>");
+      return BJX_OK;
+    }
 #define BJX_TCP_LAUNCH(NBLK, EW)                  \
   do {                                            \
     if (idx) BJX_TCP_LAUNCH_I(NBLK, EW, true);    \
@@ -1232,6 +1377,7 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
 #undef BJX_TCP_LAUNCH_EW
 #undef BJX_TCP_LAUNCH
 #undef BJX_TCP_LAUNCH_I
+#undef BJX_TCP_LAUNCH_PAIR
     BJX_LAUNCH_CHECK("k_lik_tc_tma");
     return BJX_OK;
   }

@@ -181,6 +181,34 @@ __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr, uint32_t ncols) 
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
 
+// ---- plain clusters (no cta_group::2): two CTAs that exchange small vectors through distributed shared memory ------------
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// asynchronous 16-byte store into a peer CTA's shared memory; the peer's mbarrier `rbar` (a shared::cluster address in the
+// same CTA) counts the 16 bytes as a transaction, so the receiver's wait orders the data like a TMA completion
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "f"(a),
+               "f"(b), "f"(c), "f"(d), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(void* bar, uint32_t parity) {  // acquire at cluster scope: data came from the peer
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

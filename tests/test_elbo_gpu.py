@@ -240,7 +240,10 @@ def test_error_paths():
      (20000, 500, 32, "logit"), (3000, 16, 32, "gauss"), (9000, 50, 5, "logit"), (4097, 64, 32, "logit"), (12000, 100, 17, "gauss"),
      (30000, 200, 32, "logit"), (25000, 320, 32, "gauss"), (15000, 448, 9, "logit"), (777, 511, 32, "gauss"), (20000, 129, 32, "logit"),
      # more than 32 samples on a narrow X: the single pass once per slice of 32 samples (each slice its own block of partials)
-     (5000, 128, 64, "logit"), (3000, 256, 50, "gauss"), (20000, 384, 64, "logit"), (9000, 128, 96, "gauss"), (4000, 200, 40, "logit")],
+     (5000, 128, 64, "logit"), (3000, 256, 50, "gauss"), (20000, 384, 64, "logit"), (9000, 128, 96, "gauss"), (4000, 200, 40, "logit"),
+     # 512 < D <= 1024: a cluster of two CTAs per tile, half of the columns each, partial logits exchanged through DSMEM
+     (20000, 1024, 32, "logit"), (9000, 768, 32, "gauss"), (5000, 640, 20, "logit"), (12000, 1000, 32, "gauss"), (1, 1024, 32, "logit"),
+     (65, 600, 8, "gauss"), (30000, 1024, 16, "logit"), (40000, 513, 32, "gauss"), (26000, 896, 32, "logit")],
 )
 @pytest.mark.parametrize("prepared", [True, False])
 def test_tensor_core_path(N, D, S, lik, prepared):
