@@ -489,7 +489,7 @@ struct Maps {
 };
 struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
   unsigned long long x_full[9], x_empty[9];
-  unsigned long long acc1_full[2], dl_full, dl_empty, done;  // one logits barrier per accumulator (tile parity)
+  unsigned long long acc1_full[2], dl_full[2], dl_empty[2], done;  // one logits barrier per accumulator (tile parity); g hand-over per epilogue group
   unsigned long long px_full[2];  // PAIR: the peer CTA's partial logits of a tile (by tile parity) have landed (transaction bytes)
   uint32_t tmem_base;
 };
@@ -505,7 +505,12 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 // receive, both CTAs evaluate the link function on the (bit-identical) sums, and each runs GEMM2 for its own columns.  This
 // doubles the width one pass can hold -- TMEM has room for G^T of 512 columns x 32 samples per SM -- to D <= 1024, and at
 // D <= 512 it halves the bytes of a tile per SM, so that two tiles fit the slots (the ring mode of the narrow widths).
-template <int NBLK, int EW, bool IDX, bool PAIR>  // per-CTA D / 64; epilogue warps (8 or 16); IDX adds a second producer warp
+//
+// NG = 2 (D <= 128 only: the ring holds four tiles): the sixteen epilogue warps form TWO groups that work on alternate tiles,
+// each with its own logits accumulator, g buffer and hand-over barriers.  A tile of 64 rows x 128 columns is 32 KB -- 1360
+// cycles of HBM time per SM -- while one tile's epilogue is a dependent chain of ~1250 cycles (tcgen05.ld, partner swap,
+// MUFU, g store, fence, arrive): with one group the chain is exposed on every tile, with two it overlaps the other group's.
+template <int NBLK, int EW, bool IDX, bool PAIR, int NG = 1>  // per-CTA D / 64; epilogue warps (8 or 16); IDX adds a second producer warp
 __global__ void __launch_bounds__((tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
@@ -518,7 +523,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   using namespace tc;
   constexpr int NTHREADS = (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32;
   constexpr int PROD_WARP2 = tcp::EPI_WARP0 + EW;  // IDX only: the second producer warp (one per operand plane)
-  constexpr int HG = EW / 4;    // groups of samples among the epilogue warps of one TMEM sub-partition
+  constexpr int EWG = EW / NG;  // epilogue warps that work on one tile
+  constexpr int HG = EWG / 4;   // groups of samples among the epilogue warps of one TMEM sub-partition
   constexpr int SG = NS / HG;   // samples whose partial logits a thread loads (16 or 8)
   constexpr int VPT = SG / 2;   // (row, sample) pairs a thread finishes after the swap with its partner (8 or 4)
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
@@ -549,13 +555,14 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   // the spare slot of block 0 exists outside ring mode, except for a pair of 512-column CTAs: there its 16 KB are the two
   // receive buffers of the partial-logit exchange (shared memory is full: 128 KB tile + 64 KB theta + 8 KB g + 8 KB swap)
   constexpr bool SPARE = !RING && !(PAIR && NBLK == 8);
+  static_assert(NG == 1 || (NG == 2 && EW == 16 && R >= 4 && !IDX && !PAIR), "two epilogue groups need a ring of four tiles");
   uint8_t* sx = smem + SLOT;
   uint8_t* sth = sx + NSLOT * SLOT;
-  uint8_t* sdl = sth + NBLK * BLK_BYTES;
-  tcp::BarsP* bars = (tcp::BarsP*)(sdl + BLK_BYTES);
-  float* sred = (float*)(bars + 1);
-  float* xch = (float*)(((uintptr_t)(sred + 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
-  constexpr int XCH_FLOATS = EW * VPT * 32;                                    // (two of them in ring mode, see the epilogue)
+  uint8_t* sdl = sth + NBLK * BLK_BYTES;  // NG buffers of g
+  tcp::BarsP* bars = (tcp::BarsP*)(sdl + NG * BLK_BYTES);
+  float* sred = (float*)(bars + 1);       // [NG][4][NS]
+  float* xch = (float*)(((uintptr_t)(sred + NG * 4 * NS) + 15) & ~(uintptr_t)15);  // [8 warps][8][32 lanes] partial-logit exchange
+  constexpr int XCH_FLOATS = EWG * VPT * 32;                                   // (two of them in ring mode, see the epilogue)
   int32_t* sidx = reinterpret_cast<int32_t*>(xch + (RING ? 2 : 1) * XCH_FLOATS);  // IDX only: [4 tiles][64] ring of row indices
   // PAIR: [tile parity][VPT / 4][EW * 32 threads] float4 written by the peer CTA; in the unused spare slot where there is one
   float* pxch = SPARE ? xch + (RING ? 2 : 1) * XCH_FLOATS : reinterpret_cast<float*>(smem);
@@ -574,14 +581,16 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     mbar_init(&bars->px_full[1], 1);
     mbar_init(&bars->acc1_full[0], 1);
     mbar_init(&bars->acc1_full[1], 1);
-    mbar_init(&bars->dl_full, EW);
-    mbar_init(&bars->dl_empty, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bars->dl_full[g], EWG);
+      mbar_init(&bars->dl_empty[g], 1);
+    }
     mbar_init(&bars->done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.x1);
     tma_prefetch_desc(&maps.x2);
   }
-  if (tid < 4 * NS) sred[tid] = 0.0f;
+  if (tid < NG * 4 * NS) sred[tid] = 0.0f;
   if (warp == tcp::MMA_WARP) tmem_alloc(&bars->tmem_base, TMEM_COLS);
   for (int idx = tid; idx < NS * (D / 8); idx += NTHREADS) {
     const int s = idx / (D / 8), d8 = idx % (D / 8);
@@ -840,9 +849,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     };
     if (my_tiles > 0) {
       if constexpr (RING) {
-        for (int b = 0; b < NBLK; ++b) gemm1_block(0, b);
-        if (elect_one()) umma_commit(&bars->acc1_full[0]);
-        __syncwarp();
+        for (int64_t t = 0; t < NG && t < my_tiles; ++t) {  // one tile per epilogue group
+          for (int b = 0; b < NBLK; ++b) gemm1_block(t, b);
+          if (elect_one()) umma_commit(&bars->acc1_full[t & 1]);
+          __syncwarp();
+        }
       } else if (SPARE) {
         gemm1_block(0, 0);
       }
@@ -852,7 +863,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       const bool alt = SPARE ? (it & 1) != 0 : false;
       const int idx0 = alt ? 8 : 0;
       const int q0 = RING ? (int)(it % R) * NBLK : 0;  // first slot of this tile
-      if constexpr (RING) {
+      const int eg = NG == 2 ? (int)(it & 1) : 0;       // the epilogue group of this tile
+      if constexpr (NG == 2) {
+        // two groups: GEMM1 of tiles it and it + 1 are already issued (one logits accumulator each); GEMM1(it + 2) follows
+        // this tile's GEMM2 below -- the same event (dl_full of this group) frees its accumulator
+      } else if constexpr (RING) {
         // the whole GEMM1 of the next tile (other logits accumulator, slots already in the ring) under this tile's epilogue
         // Its barrier is the OTHER one (one per accumulator): the previous phase of that barrier was tile it - 1, which
         // every epilogue warp consumed before dl_full(it - 1) -- so it may complete right away, and the epilogue goes from
@@ -870,9 +885,10 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         if (lane == 0) BJX_TRACE(it, 24);
         if (SPARE && it + 1 < my_tiles) gemm1_block(it + 1, 0);  // its slot (the other one) was filled a tile ago
       }
-      mbar_wait(&bars->dl_full, ph);
+      mbar_wait(&bars->dl_full[eg], NG == 2 ? (uint32_t)((it >> 1) & 1) : ph);
       tc_fence_after();
       if (lane == 0) BJX_TRACE(it, 25);
+      const uint64_t tdl_g = tdl + (uint64_t)((eg * BLK_BYTES) >> 4);
       for (int ch = 0; ch < NCH; ++ch) {
         if (elect_one()) {
           const uint64_t coff = (uint64_t)(((q0 + 2 * ch) * SLOT) >> 4);
@@ -881,18 +897,26 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (ablate & 2) continue;
-            umma_bf16(tmem + ACC2_COL + ch * NB, a1 + 128 * k, tdl + 128 * k, ID_G2,
+            umma_bf16(tmem + ACC2_COL + ch * NB, a1 + 128 * k, tdl_g + 128 * k, ID_G2,
                       (k != 0) || !(it == 0 || phase == ch * flush_step));
-            umma_bf16(tmem + ACC2_COL + ch * NB, a2 + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
+            umma_bf16(tmem + ACC2_COL + ch * NB, a2 + 128 * k, tdl_g + 128 * k, ID_G2_N32, 1);
           }
           umma_commit(&bars->x_empty[(ch == 0 && !RING) ? idx0 : q0 + 2 * ch]);
           umma_commit(&bars->x_empty[q0 + 2 * ch + 1]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&bars->dl_empty);
+      if (elect_one()) umma_commit(&bars->dl_empty[eg]);
       __syncwarp();
       if (lane == 0) BJX_TRACE(it, 26);
+      if constexpr (NG == 2) {
+        if (it + 2 < my_tiles) {
+          for (int b = 0; b < NBLK; ++b) gemm1_block(it + 2, b);
+          if (elect_one()) umma_commit(&bars->acc1_full[eg]);
+          __syncwarp();
+          if (lane == 0) BJX_TRACE(it + 2, 24);
+        }
+      }
       if (++phase == NCH * flush_step) phase = 0;
     }
     if (elect_one()) umma_commit(&bars->done);
@@ -904,13 +928,16 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     // 32q..32q+31) and its partner in sub-partition q ^ 2 hold the two parts of the same 32 rows; they swap halves of
     // their 16 samples through shared memory, so that every thread finishes 8 (row, sample) pairs.
     const int q = warp & 3;
-    const int h = (warp - tcp::EPI_WARP0) >> 2;
+    const int eg = (warp - tcp::EPI_WARP0) / EWG;      // epilogue group (NG = 2: this group takes the tiles of parity eg)
+    const int wg = (warp - tcp::EPI_WARP0) - eg * EWG;  // warp within the group
+    const int h = wg >> 2;
     const int part = q >> 1;
     const int r = 32 * (q & 1) + lane;
     const int s0 = h * SG + part * VPT;
-    float* xch_mine = xch + (size_t)(warp - tcp::EPI_WARP0) * (VPT * 32);             // what the partner wrote for me
-    float* xch_peer = xch + (size_t)((warp - tcp::EPI_WARP0) ^ 2) * (VPT * 32);       // (warp index ^ 2 flips q's high bit)
-    const int pair_bar = 2 + HG * (q & 1) + h;                                        // named barriers 2.., 64 threads each
+    float* xch_mine = xch + (size_t)wg * (VPT * 32);             // what the partner wrote for me
+    float* xch_peer = xch + (size_t)(wg ^ 2) * (VPT * 32);       // (warp index ^ 2 flips q's high bit)
+    const int pair_bar = 2 + 2 * HG * eg + HG * (q & 1) + h;     // named barriers 2.., 64 threads each
+    uint8_t* sdl_g = sdl + eg * BLK_BYTES;
     float stat[VPT], prod[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
@@ -952,10 +979,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       if (!final) tmem_st_wait();
     };
     const int flush_step = flush_tiles / NCH > 0 ? flush_tiles / NCH : 1;
-    int phase = 0;
-    uint32_t flushed = 0;
-    int64_t row = (int64_t)cid * TILE_ROWS + r;
-    float yv = (my_tiles > 0 && row < N) ? y[row] : 0.0f;
+    const int flush_period = NCH * flush_step;
+    // chunk ch is folded for the first time at tile ch * flush_step (chunk 0: one period in), then once per period
+    auto first_fold = [&](int ch) { return (int64_t)(ch == 0 ? flush_period : ch * flush_step); };
+    int64_t row = ((int64_t)cid + (int64_t)eg * ncl) * TILE_ROWS + r;
+    float yv = (my_tiles > eg && row < N) ? y[row] : 0.0f;
     uint32_t va[SG], vb[SG];  // partial logits of one tile
     // PAIR: my slot in the peer's receive buffers and the peer's transaction barriers (shared::cluster addresses)
     const int te = tid - tcp::EPI_WARP0 * 32;
@@ -977,29 +1005,33 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         tmem_ld8(acc1 + NS + h * SG, vb);
       }
     };
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    for (int64_t it = eg; it < my_tiles; it += NG) {
       const uint32_t ph = (uint32_t)(it & 1);
+      const int phase = (int)(it % flush_period);
       if (it > 0 && phase % flush_step == 0 && phase / flush_step < NCH) {
+        // GEMM2 of the previous tile (the other group's, with two groups) has retired and this tile's cannot start before
+        // this group hands over g: nobody touches the accumulators now
         const int ch = phase / flush_step;
-        mbar_wait(&bars->dl_empty, ph ^ 1);
+        if constexpr (NG == 2)
+          mbar_wait(&bars->dl_empty[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+        else
+          mbar_wait(&bars->dl_empty[0], ph ^ 1);
         tc_fence_after();
-        drain_chunk(ch, !((flushed >> ch) & 1u), false);
+        drain_chunk(ch, it == first_fold(ch), false);
         tc_fence_before();
-        flushed |= 1u << ch;
       }
-      if (++phase == NCH * flush_step) phase = 0;
       const bool row_ok = row < N;
       const float ycur = yv;
       // fetch the next tile's label now: its latency hides behind this tile's GEMM1
-      row += (int64_t)ncl * TILE_ROWS;
-      yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
+      row += (int64_t)NG * ncl * TILE_ROWS;
+      yv = (it + NG < my_tiles && row < N) ? y[row] : 0.0f;
       if constexpr (PAIR) {  // this tile's receive phase: EW * 32 threads x VPT floats from the peer
         if (te == 0) mbar_expect_tx(&bars->px_full[it & 1], (uint32_t)(PX_FLOATS * sizeof(float)));
       }
       // (Loading the next tile's logits early, under this tile's link function, was tried in ring mode and lost 10 %: the
       // wait for GEMM1(t+1) -- queued behind GEMM2(t-1) on the tensor pipe -- then sits in front of this tile's hand-over.)
       load_logits(it);
-      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 32);
+      if (tid == (tcp::EPI_WARP0 + eg * EWG) * 32) BJX_TRACE(it, 32);
       tmem_ld_wait();
       // ring mode: the exchange buffers alternate with the tile (nothing orders my write for tile t+1 after the partner's
       // read for tile t any more, now that the next logits do not wait for this tile's hand-over)
@@ -1036,10 +1068,10 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           eta[4 * j4 + 3] += o.w;
         }
       }
-      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 33);
+      if (tid == (tcp::EPI_WARP0 + eg * EWG) * 32) BJX_TRACE(it, 33);
       // This stage is bound by instruction issue (2048 values per tile over four schedulers), so the common case -- a full
       // tile and S = 32 -- runs without the validity selects, and the reciprocal goes to the special-function pipe.
-      const bool all_ok = (S == NS) && (row - (int64_t)ncl * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
+      const bool all_ok = (S == NS) && (row - (int64_t)NG * ncl * TILE_ROWS - r + TILE_ROWS <= N);  // warp-uniform
       // Only g is on the critical path (GEMM2 waits for it): the loss bookkeeping (stat, prod) is done after the hand-over.
       float ope[VPT];
       if (ablate & 4) {
@@ -1070,10 +1102,11 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       uint32_t e1[VPT / 2], e2[VPT / 2];
 #pragma unroll
       for (int j = 0; j < VPT / 2; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
-      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 34);
-      mbar_wait(&bars->dl_empty, ph ^ 1);
+      if (tid == (tcp::EPI_WARP0 + eg * EWG) * 32) BJX_TRACE(it, 34);
+      // GEMM2 of this group's previous tile has consumed its g buffer
+      mbar_wait(&bars->dl_empty[eg], NG == 2 ? (uint32_t)(((it >> 1) & 1) ^ 1) : (ph ^ 1));
       {
-        uint8_t* rowp = sdl + r * 128;
+        uint8_t* rowp = sdl_g + r * 128;
         const int sw = r & 7;
         // row layout: [e1: 32 samples x 2 B | e2: 32 x 2 B], 16-byte chunks XOR-swizzled by the row
         if constexpr (VPT == 8) {
@@ -1087,7 +1120,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->dl_full);
+      if (lane == 0) mbar_arrive(&bars->dl_full[eg]);
       // ---- off the critical path: log-likelihood bookkeeping
       if (!(ablate & 4)) {
         if (logit) {
@@ -1097,7 +1130,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
             stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
             prod[j] *= ok ? ope[j] : 1.0f;
           }
-          if ((it & 31) == 31) {
+          if (((it / NG) & 31) == 31) {
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
               stat[j] -= logf(prod[j]);
@@ -1109,23 +1142,26 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           for (int j = 0; j < VPT; ++j) stat[j] = fmaf(g[j], g[j], stat[j]);  // g = y - eta, already masked
         }
       }
-      if (tid == tcp::EPI_WARP0 * 32) BJX_TRACE(it, 35);
+      if (tid == (tcp::EPI_WARP0 + eg * EWG) * 32) BJX_TRACE(it, 35);
     }
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
       float v = stat[j] - logf(prod[j]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) sred[q * NS + s0 + j] = v;  // the other (q, sample) slots stay zero
+      if (lane == 0) sred[eg * 4 * NS + q * NS + s0 + j] = v;  // the other (q, sample) slots stay zero
     }
     asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
     if (warp == tcp::EPI_WARP0 && lane < S && rank == 0) {  // both CTAs of a pair hold the same sums: one reports them
-      statpart[(size_t)cid * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+      float v = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+      if constexpr (NG == 2) v += sred[4 * NS + lane] + sred[5 * NS + lane] + sred[6 * NS + lane] + sred[7 * NS + lane];
+      statpart[(size_t)cid * S + lane] = v;
     }
     mbar_wait(&bars->done, 0);
     tc_fence_after();
     if (my_tiles > 0) {
-      for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, !((flushed >> ch) & 1u), true);
+      if (eg == 0)
+        for (int ch = 0; ch < NCH; ++ch) drain_chunk(ch, my_tiles <= first_fold(ch), true);
     } else {
       for (int i = (warp - tcp::EPI_WARP0) * 32 + lane; i < S * Dw; i += EW * 32) gp[i] = 0.0f;
     }
@@ -1367,6 +1403,27 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
     if (epi_warps == 16) BJX_TCP_LAUNCH(NBLK, 16); \
     else BJX_TCP_LAUNCH(NBLK, 8);               \
   } while (0)
+    // D <= 128: two epilogue groups on alternate tiles (see the kernel).  A/B on one box (profiles/r02_envelope_narrow_groups.json):
+    // the Gaussian link gains (0.71-0.72 -> 0.75-0.77 of the roofline at D = 128), the Bernoulli-logit link does not (0.70 either
+    // way: sixteen warps on ONE tile shorten its longer MUFU chain just as much), so it keeps one group.  BJX_TC_EPI_GROUPS=1 / 2 forces.
+    static int groups = -1;
+    if (groups < 0) {
+      const char* e = getenv("BJX_TC_EPI_GROUPS");
+      groups = e ? atoi(e) : 0;
+    }
+    const bool two_groups = groups ? groups == 2 : a.likelihood == BJX_LIK_GAUSSIAN;
+    if (nblk == 2 && !idx && two_groups && !forced_ew) {
+      const size_t smem2 = smem + tc::BLK_BYTES + 4 * tc::NS * sizeof(float);
+      static DeviceOnce attr_set;
+      if (!attr_set.test_and_set()) {
+        BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<2, 16, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      }
+      k_lik_tc_tma<2, 16, false, false, 2><<<p.tc_ctas, (tcp::EPI_WARP0 + 16) * 32, smem2, st>>>(
+          maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, a.likelihood, Gpart, statpart, pf_tiles, flush_tma,
+          g_ablate, g_trace, a.row_index, plane_rows);
+      BJX_LAUNCH_CHECK("k_lik_tc_tma<two groups>");
+      return BJX_OK;
+    }
     switch (nblk) {
       case 2: BJX_TCP_LAUNCH_EW(2); break;
       case 4: BJX_TCP_LAUNCH_EW(4); break;

@@ -1,6 +1,7 @@
-"""Three steps of the fused kernel at D = 128 and D = 256 (S = 32, Bernoulli-logit, 4 GB of X each, prepared planes) for an
-ncu capture of k_lik_tc_tma<2, 8> / <4, 8> (the slot-ring variants); no timing here."""
-import math, sys
+"""Three steps of the fused kernel at D = 128 and D = 256 (ENV_D overrides; S = 32, Bernoulli-logit, 4 GB of X each, prepared
+planes) for an ncu capture of k_lik_tc_tma<2, 8> / <4, 8> (the slot-ring variants) or, at D > 512, of the paired variant; no
+timing here."""
+import math, os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import bijax_b200 as bj
@@ -8,7 +9,7 @@ from bijax_b200 import bijectors as tfb, distributions as tfd, likelihoods as lk
 
 dev = torch.device("cuda")
 keys = br.split(br.PRNGKey(0), 8)
-for D in (128, 256):
+for D in tuple(int(v) for v in os.environ.get("ENV_D", "128,256").split(",")):
     N = int(4e9 / (4 * D)) // 64 * 64
     X = br.normal(br.PRNGKey(1234), (N, D), partitionable=True); X.mul_(1 / math.sqrt(D))
     w = br.normal(br.PRNGKey(1235), (D,), partitionable=True)

@@ -1,11 +1,11 @@
 """Dump the per-tile pipeline timeline of the tcgen05 likelihood kernel (CTA 0, tiles 16..23), in SM cycles."""
-import math, sys
+import math, os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import bijax_b200 as bj
 from bijax_b200 import _native as nv, distributions as tfd, likelihoods as lk, random as br
 
-D, S, N = 512, 32, int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+D, S, N = int(os.environ.get("TRACE_D", 512)), int(os.environ.get("TRACE_S", 32)), int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 dev = torch.device("cuda")
 X = br.normal(br.PRNGKey(1), (N, D), partitionable=True) / math.sqrt(D)
 y = (torch.rand(N, device=dev) < 0.5).float()
@@ -29,7 +29,7 @@ names = {**{b: f"ld wait_empty b{b}" for b in range(8)}, **{8 + b: f"ld stored b
          **{44 + w: f"ld stored b1 quarter {w}" for w in range(4)},
          48: "ld b4 loads issued", 49: "ld b4 data arrived",
          32: "epi acc1_full", 33: "epi tmem loaded", 34: "epi math done", 35: "epi dl stored"}
-for it in range(1, 3):
+for it in range(1, int(os.environ.get("TRACE_TILES", 3))):
     ev = sorted((int(t[it, k] - t0), names[k]) for k in names if t[it, k])
     print(f"--- tile {16 + it} (tile period {int(t[it,0]-t[it-1,0])} cycles)")
     base = ev[0][0]
