@@ -780,6 +780,9 @@ def run_small(args):
                     "algorithmic_bytes": 4.0 * N * D + 4.0 * N,
                     "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: cuBLAS bf16 back to back for 4 s; the kernel is timed inside a long step)"
                                     if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s")}
+        if "bf16_tflops" in peaks:  # the 20-step region is ~0.1 s, between the two cuBLAS figures: say both
+            roofline["frac_of_burst_peak"] = issued / float(peaks["bf16_tflops"])
+            roofline["burst_peak"] = float(peaks["bf16_tflops"])
     elif cfg == "c2":
         mhz = float(peaks.get("sm_max_mhz", 1965.0))
         peak = 148 * 128 * 2 * mhz * 1e6 / 1e12

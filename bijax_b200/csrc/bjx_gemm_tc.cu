@@ -32,8 +32,11 @@ namespace gemm {
 constexpr int BM = 128;            // UMMA M
 constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_PLANE = BM * 128;  // bytes of one A plane tile
-constexpr int THREADS = 192;
 constexpr int NACC = 2;            // accumulator stages in TMEM
+// Epilogue warps: four (one per TMEM sub-partition), except the transposed contraction on 256-wide tiles, which keeps its
+// 128 x 256 fp32 partial of a whole K split in REGISTERS -- 128 values per thread need two warps per sub-partition.
+__host__ __device__ constexpr int epi_warps(int epi, int bn) { return (epi == 1 /* EPI_LIK2 */ && bn == 256) ? 8 : 4; }
+__host__ __device__ constexpr int threads_of(int epi, int bn) { return (2 + epi_warps(epi, bn)) * 32; }
 
 enum { EPI_LIK1 = 0, EPI_LIK2 = 1, EPI_Z = 2, EPI_DM = 3 };
 
@@ -115,7 +118,7 @@ __device__ __forceinline__ void for_each_vtile(const Sched& sc, F&& f) {
     do {
       int kb1 = kb0 + sc.kb_per_vtile;
       if (kb1 > kb_hi) kb1 = kb_hi;
-      f(m_blk, n_blk, split, kb0, kb1);
+      f(m_blk, n_blk, split, kb0, kb1, kb0 == kb_lo, kb1 >= kb_hi);  // + first / last virtual tile of this output unit
       kb0 = kb1;
     } while (kb0 < kb_hi);
   }
@@ -137,7 +140,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 }
 
 template <int BN, int NT, bool A_MN, bool B_MN, int EPI, int CG>
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(threads_of(EPI, BN), 1) k_gemm_tc(const __grid_constant__ Params P) {
   using namespace tc;
   using C = Cfg<BN, NT, CG>;
   constexpr int BMC = BM * CG;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4 * CG);
+      mbar_init(&bars->tmem_empty[s], epi_warps(EPI, BN) * CG);
     }
     fence_mbar_init();
   }
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       auto load = [&](void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, void* bar) {
         if (CG == 2) tma_load_2d_cg2(dst, map, c0, c1, bar); else tma_load_2d(dst, map, c0, c1, bar);
       };
-      for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int, int kb0, int kb1) {
+      for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int, int kb0, int kb1, bool, bool) {
         const int m0 = m_blk * BMC + rank * BM, n0 = n_blk * BN + rank * (BN / CG);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     constexpr uint64_t A_KADV = A_MN ? 128 : 2, B_KADV = B_MN ? 128 : 2;  // in 16-byte units
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
-    for_each_vtile<BN, CG>(sc, [&](int, int, int, int kb0, int kb1) {
+    for_each_vtile<BN, CG>(sc, [&](int, int, int, int kb0, int kb1, bool, bool) {
       mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)(as * BN);
@@ -278,7 +281,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     const EpiArgs& e = P.epi;
     int as = 0;
     uint32_t aphase = 0;
-    for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int split, int kb0, int kb1) {
+    // EPI_LIK2: the partial of this thread's accumulator row over the K split (CW columns: the whole tile, or half of a
+    // 256-wide one -- warps 6-9 take columns [128, 256))
+    constexpr int CW = EPI == EPI_LIK2 ? BN / (epi_warps(EPI, BN) / 4) : 1;
+    const int cw0 = EPI == EPI_LIK2 ? ((warp - 2) >> 2) * CW : 0;
+    float part[CW];
+    for_each_vtile<BN, CG>(sc, [&](int m_blk, int n_blk, int split, int kb0, int kb1, bool first_vt, bool last_vt) {
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem + (uint32_t)(as * BN) + ((uint32_t)(32 * q) << 16);
@@ -343,22 +351,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           if (s0 + lane < e.S) atomicAdd(statp + s0 + lane, tot);
         }
       } else if (EPI == EPI_LIK2) {
-        // accumulator rows = weight column d, columns = sample s:  Gpart[split][s][d] += acc  (lanes contiguous in d: coalesced)
-        if (!empty) {  // warp-uniform; tcgen05.ld is warp-collective, only the reductions are predicated per lane
-          const bool r_ok = r < e.Dw;
-          float* gp = e.Gpart + (size_t)split * e.S * e.Dw + (r_ok ? r : 0);
-#pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const int s0 = n_blk * BN + c * 32;
-            if (s0 >= e.S) break;
-            uint32_t v[32];
-            tmem_ld32(t_acc + c * 32, v);
-            tmem_ld_wait();
-            if (r_ok) {
+        // accumulator rows = weight column d, columns = sample s.  The accumulator of every virtual tile (the tensor core's
+        // fp32 accumulate truncates, so the chain is cut every kb_per_vtile k-blocks) is added into a partial that stays in
+        // REGISTERS for the whole K split and is stored once: Gpart[split][s][d] = partial (lanes contiguous in d: coalesced).
+        // The same fp32 additions in the same order as the red.global.add updates this replaces (bit-identical), without
+        // their DRAM traffic -- 1.7 GB of writes and 3.7 GB of extra reads per c4 step.
+        if (first_vt) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (s0 + j < e.S) atomicAdd(gp + (size_t)(s0 + j) * e.Dw, __uint_as_float(v[j]));  // RED.ADD, same thread per address
+          for (int j = 0; j < CW; ++j) part[j] = 0.0f;
+        }
+        if (!empty) {  // warp-uniform; tcgen05.ld is warp-collective
+#pragma unroll
+          for (int c = 0; c < CW / 32; ++c) {
+            if (n_blk * BN + cw0 + c * 32 < e.S) {  // warp-uniform
+              uint32_t v[32];
+              tmem_ld32(t_acc + cw0 + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) part[c * 32 + j] += __uint_as_float(v[j]);
             }
+          }
+        }
+        if (last_vt && r < e.Dw) {
+          float* gp = e.Gpart + (size_t)split * e.S * e.Dw + r;
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int sj = n_blk * BN + cw0 + j;
+            if (sj < e.S) gp[(size_t)sj * e.Dw] = part[j];
           }
         }
       } else if (EPI == EPI_Z) {
@@ -559,12 +578,12 @@ static int launch(const Params& P, int grid, cudaStream_t st) {
   if (!attr_set.test_and_set())
     BJX_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   if (CG == 1) {
-    k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG><<<grid, THREADS, C::SMEM_BYTES, st>>>(P);
+    k_gemm_tc<BN, NT, A_MN, B_MN, EPI, CG><<<grid, threads_of(EPI, BN), C::SMEM_BYTES, st>>>(P);
   } else {
     // CTA pairs: a cluster of two CTAs (same TPC) per 256-row tile
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(threads_of(EPI, BN));
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -715,7 +734,7 @@ int launch_lik_gemm(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_t 
     BJX_LAUNCH_CHECK("k_split_planes(theta)");
   }
   BJX_CUDA_TRY(cudaMemsetAsync(statpart, 0, (size_t)p.PS * a.S * sizeof(float), st));
-  BJX_CUDA_TRY(cudaMemsetAsync(Gpart, 0, (size_t)p.PG * a.S * a.Dw * sizeof(float), st));
+  // (Gpart needs no clearing: every [split][s][d] entry is stored exactly once by the unit that owns it)
   const int bn = lik1_bn(a.S, nt);
   const int cg = p.gm_cg, bmc = 128 * cg;
 

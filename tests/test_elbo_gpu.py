@@ -682,7 +682,8 @@ def test_large_shape_properties_of_the_tensor_core_path():
     C.assert_close(full[1 + D :].cpu().numpy(), other[1 + D :].cpu().numpy(), what="d rho vs fp32 kernel")
 
 
-@pytest.mark.parametrize("D,prepared", [(128, True), (384, True), (256, True), (128, False), (384, False)])
+@pytest.mark.parametrize("D,prepared", [(128, True), (384, True), (256, True), (128, False), (384, False),
+                                        (768, True), (1024, True), (640, False)])  # > 512: a pair of CTAs per tile, 3-4 chunks each
 def test_accumulator_folding_with_few_blocks_per_tile(D, prepared):
     """Enough tiles per CTA (21+) that the periodic folding of the GEMM2 accumulators runs for every block count
     (D = 128, 256, 384 have 1, 2, 3 chunks, so a different folding rotation than D = 512): the fused tensor-core kernels

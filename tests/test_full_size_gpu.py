@@ -54,14 +54,17 @@ def _check(packed, want, D, P, names):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("rows,row0,n_total", [(10_000_000, 0, 10_000_000), (12_500_000, 37_500_000, 100_000_000)],
-                         ids=["c3_10M_rows", "c5_shard_3_of_8"])
-def test_logistic_d512_s32_full_size_against_the_float64_oracle(rows, row0, n_total):
+@pytest.mark.parametrize("rows,row0,n_total,D", [(10_000_000, 0, 10_000_000, 512), (12_500_000, 37_500_000, 100_000_000, 512),
+                                                  (5_000_000, 0, 5_000_000, 1024), (6_000_000, 0, 6_000_000, 768)],
+                         ids=["c3_10M_rows", "c5_shard_3_of_8", "d1024_5M_rows_cta_pairs", "d768_6M_rows_cta_pairs"])
+def test_logistic_d512_s32_full_size_against_the_float64_oracle(rows, row0, n_total, D):
     """c3 (N=10M on one GPU) and one c5 shard (rows [37.5M, 50M) of the 100M-row dataset, ``ll_scale`` from the global
-    length): default precision, prepared planes = the exact kernel and layout bench.py times."""
+    length): default precision, prepared planes = the exact kernel and layout bench.py times.  The same at D = 1024 and
+    D = 768 (20 GB / 18 GB of X): the single pass with a cluster of two CTAs per tile (each CTA half of the columns, ~1000
+    tiles per cluster, partial logits summed across the pair on every tile)."""
     from bijax_b200 import random as br
 
-    D, S = 512, 32
+    S = 32
     X = _device_X(rows, D, row0, n_total)
     y = _logistic_y(X, row0, n_total)
     prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
