@@ -828,7 +828,7 @@ def run_small(args):
         "metric": METRIC, "value": value, "unit": unit, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": small_config(cfg), "impl_detail": {"precision": args.precision, "kernel": kernel},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (14 if cfg == "c4" else launches_per_step(kernel)) * K,  # c4: prologue, 4 operand splits, 4 GEMMs (L.eps, pass 1, pass 2, dM), tail kernels
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (15 if cfg == "c4" else launches_per_step(kernel)) * K,  # c4: prologue, k_eps, 5 operand splits, 4 GEMMs (L.eps, pass 1, pass 2, dM), two partial reductions, tail, scalars
         "roofline": roofline, "cpu_baseline": cpu, "snd_per_s": value * S * N * D, "loss_last_step": float(out[0]),
     }
     line.update(extra)

@@ -456,6 +456,17 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
   }
 }
 
+// Few partial slots and many outputs (the two-pass GEMM path: 9 K splits x S x Dw, 0.5 M outputs at c4): one thread per output
+// walks the slots in order -- eight warps striding over nine slots leave most of a block idle (30 us at c4 against 6 us here).
+// The stat partials of that path have many slots (4 per pass-1 CTA) and few outputs: they keep the block-per-32-outputs kernel.
+__global__ void __launch_bounds__(256) k_reduce_partials_few(const float* __restrict__ Gpart, int PG, int64_t SDw, float* __restrict__ G) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= SDw) return;
+  float t = 0.0f;
+  for (int p = 0; p < PG; ++p) t += Gpart[(size_t)p * SDw + i];
+  G[i] = t;
+}
+
 struct TailArgs {
   int64_t S, D, Dw, w_off, N;
   int vi_type, scale_bij, likelihood, noise_src, noise_index;
@@ -787,9 +798,15 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
       }
     } else {
       const int64_t SDw = a.S * Dw;
-      k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
-                                                                            (const float*)(ws + p.o_statpart), p.PS, SDw,
-                                                                            a.S, G, stat);
+      if (p.PG <= 16 && SDw >= 65536) {
+        k_reduce_partials_few<<<(unsigned)((SDw + 255) / 256), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG, SDw, G);
+        // the stat partials alone: outputs [SDw, SDw + S) of the general kernel, i.e. an empty G range
+        k_reduce_partials<<<(unsigned)((a.S + 31) / 32), 256, 0, st>>>(nullptr, 0, (const float*)(ws + p.o_statpart), p.PS, 0, a.S, G, stat);
+      } else {
+        k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
+                                                                              (const float*)(ws + p.o_statpart), p.PS, SDw,
+                                                                              a.S, G, stat);
+      }
       BJX_LAUNCH_CHECK("k_reduce_partials");
     }
   }

@@ -413,12 +413,17 @@ __global__ void __launch_bounds__(threads_of(EPI, BN), 1) k_gemm_tc(const __grid
               tmem_ld_wait();
             }
             if (r < e.D) {
-              // all 32 loads of M first (independent, in flight together): the stores below may alias them for the compiler
+              // The raw scale enters only through d sigma / d raw (1 for the Identity bijector of get_full_rank's default:
+              // M is then read on the diagonal alone) and, on the diagonal, through d log sigma / d raw.  With four warps
+              // per SM this loop is a latency chain, so the division stays off the 16383 off-diagonal entries of a tile.
+              const bool need_m = e.scale_bij != BJX_SCALE_IDENTITY;
               float mv[32];
+              if (need_m) {  // all 32 loads first (independent, in flight together): the stores below may alias them for the compiler
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t i = i0 + j;
-                mv[j] = (i < e.D && r <= i) ? __ldg(e.M + i * e.D + r) : 0.0f;
+                for (int j = 0; j < 32; ++j) {
+                  const int64_t i = i0 + j;
+                  mv[j] = (i < e.D && r <= i) ? __ldg(e.M + i * e.D + r) : 0.0f;
+                }
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -426,9 +431,12 @@ __global__ void __launch_bounds__(threads_of(EPI, BN), 1) k_gemm_tc(const __grid
                 if (i < e.D) {
                   float val = 0.0f;
                   if (r <= i) {
-                    const ScaleEval se = eval_scale(mv[j], e.scale_bij);
-                    val = (empty ? 0.0f : __uint_as_float(v[j])) * se.dsigma;
-                    if (r == i) val -= e.prior_weight * se.dlogsigma;
+                    val = empty ? 0.0f : __uint_as_float(v[j]);
+                    if (need_m) val *= eval_scale(mv[j], e.scale_bij).dsigma;
+                    if (r == i) {
+                      const ScaleEval se = eval_scale(need_m ? mv[j] : __ldg(e.M + i * e.D + r), e.scale_bij);
+                      val -= e.prior_weight * se.dlogsigma;
+                    }
                   }
                   e.out[i * e.D + r] = val;
                 }
