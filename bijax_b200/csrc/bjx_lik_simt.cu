@@ -4,6 +4,9 @@
 //   G[s, d]   = sum_n g(y_n, eta[n, s]) X[n, d]   (the transposed dot_general of the VJP, utils.py:7)
 // Two kernels: a single-pass register-resident one for a handful of columns (config c2: D = 5), and a generic
 // two-pass tiled fallback for any shape the tensor-core kernel (bjx_lik_tc.cu) does not take.
+#include <cstdlib>
+#include <type_traits>
+
 #include "bjx_elbo.cuh"
 #include "bjx_sgemm.cuh"
 
@@ -16,102 +19,145 @@ namespace bjx {
 // =====================================================================================================================
 constexpr int SD_CHUNK = SD_CHUNK_ROWS;
 
-template <int REC4, int DWT>  // DWT = the column count as a compile-time constant: the padding slots cost no FMAs
-__global__ void __launch_bounds__(256) k_lik_smalld(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y,
+// SPT = Monte-Carlo samples per thread.  With two, a record read from shared memory (LDS.128 broadcast) and its address
+// arithmetic serve two samples: 21 -> ~15 instructions per (row, sample) pair of which 12 are the arithmetic itself (config c2 is
+// bound by instruction issue, profiles/r01_k_lik_smalld_c2_ncu_full.txt).  Rows per inner iteration shrink to two, so the
+// register count -- and with it the number of resident blocks -- stays where it was.
+template <int REC4, int DWT, int SPT>  // DWT = the column count as a compile-time constant: the padding slots cost no FMAs
+__global__ void __launch_bounds__(256, REC4 <= 2 ? 4 : 1) k_lik_smalld(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y,
                                                     int64_t N, int Dw, const float* __restrict__ theta, int64_t D,
                                                     int64_t w_off, int S, int family, int SB, int64_t rows_per_cta,
                                                     float* __restrict__ Gpart, float* __restrict__ statpart) {
-  constexpr int REC = REC4 * 4;  // record = [y, x_0 .. x_{Dw-1}, 0 ...]: y sits at a fixed slot
-  constexpr int ROWS = 4;        // rows per inner iteration: independent eta chains give the FMA pipe some ILP
+  constexpr int REC = REC4 * 4;    // record = [y, x_0 .. x_{Dw-1}, 0 ...]: y sits at a fixed slot
+  constexpr int ROWS = 4 / SPT;    // rows per inner iteration: ROWS * SPT independent eta chains give the FMA pipe its ILP
   __shared__ __align__(16) float sm[256 * (REC + 1)];
   const int tid = threadIdx.x;
-  const int RL = 256 / SB;
-  const int sl = tid % SB, rl = tid / SB;
-  const int s = blockIdx.y * SB + sl;
-  const bool s_ok = s < S;
-
-  float th[REC], G[REC];  // th[0] = 0 (the y slot), th[1 + d] = theta[s, d]
+  const int SBT = SB / SPT;        // threads along the samples of this block (SB samples)
+  const int RL = 256 / SBT;
+  const int sl = tid % SBT, rl = tid / SBT;
+  int sidx[SPT];
+  bool s_ok[SPT];
 #pragma unroll
-  for (int d = 0; d < REC; ++d) {
-    th[d] = (s_ok && d >= 1 && d <= Dw) ? theta[(int64_t)s * D + w_off + d - 1] : 0.0f;
-    G[d] = 0.0f;
+  for (int k = 0; k < SPT; ++k) {
+    sidx[k] = blockIdx.y * SB + sl + k * SBT;
+    s_ok[k] = sidx[k] < S;
   }
-  float stat = 0.0f;
+
+  float th[SPT][REC], G[SPT][REC];  // th[.][0] = 0 (the y slot), th[.][1 + d] = theta[s, d]
+  float stat[SPT];
+#pragma unroll
+  for (int k = 0; k < SPT; ++k) {
+#pragma unroll
+    for (int d = 0; d < REC; ++d) {
+      th[k][d] = (s_ok[k] && d >= 1 && d <= Dw) ? theta[(int64_t)sidx[k] * D + w_off + d - 1] : 0.0f;
+      G[k][d] = 0.0f;
+    }
+    stat[k] = 0.0f;
+  }
+
+  // ROWS rows x SPT samples; MASKED: rows past nvalid contribute nothing (only the last group of a chunk can hold such rows)
+  auto group = [&](int r0, int nvalid, auto masked_tag) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
+    float rec[ROWS][REC];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const int r = MASKED ? min(r0 + u * RL, SD_CHUNK - 1) : r0 + u * RL;
+      const float4* rp = reinterpret_cast<const float4*>(sm + r * REC);
+#pragma unroll
+      for (int q = 0; q < REC4; ++q) {
+        const float4 v = rp[q];
+        rec[u][4 * q + 0] = v.x;
+        rec[u][4 * q + 1] = v.y;
+        rec[u][4 * q + 2] = v.z;
+        rec[u][4 * q + 3] = v.w;
+      }
+    }
+    float eta[ROWS][SPT];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u)
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) eta[u][k] = 0.0f;
+#pragma unroll
+    for (int d = 1; d <= DWT; ++d)
+#pragma unroll
+      for (int u = 0; u < ROWS; ++u)
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) eta[u][k] = fmaf(rec[u][d], th[k][d], eta[u][k]);
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const bool ok = !MASKED || (r0 + u * RL < nvalid);
+#pragma unroll
+      for (int k = 0; k < SPT; ++k) {
+        float f, g;
+        link_eval(family, rec[u][0], eta[u][k], f, g);
+        if (MASKED) {
+          f = ok ? f : 0.0f;
+          g = ok ? g : 0.0f;
+        }
+        stat[k] += f;
+#pragma unroll
+        for (int d = 1; d <= DWT; ++d) G[k][d] = fmaf(g, rec[u][d], G[k][d]);
+      }
+    }
+  };
 
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_end = min(N, row_begin + rows_per_cta);
+  // this thread's row of a chunk, fetched into registers one chunk ahead: the global-load latency of chunk c + 1 runs under
+  // the arithmetic of chunk c instead of in front of a barrier
+  float nx[REC];
+  auto fetch = [&](int64_t base) {
+    const int64_t row = base + tid;
+    if (row < row_end) {
+      const float* xr = X + row * ldx;
+      nx[0] = y[row];
+#pragma unroll
+      for (int d = 1; d < REC; ++d) nx[d] = d <= Dw ? xr[d - 1] : 0.0f;
+    } else {  // rows past the end: eta = 0 and y = 0 would still contribute f(0, 0); they are masked below
+#pragma unroll
+      for (int d = 0; d < REC; ++d) nx[d] = 0.0f;
+    }
+  };
+  if (row_begin < row_end) fetch(row_begin);
   for (int64_t base = row_begin; base < row_end; base += SD_CHUNK) {
     const int nvalid = (int)min((int64_t)SD_CHUNK, row_end - base);
     __syncthreads();  // previous chunk fully consumed
     {
-      float* rec = sm + tid * REC;
-      if (tid < nvalid) {
-        const float* xr = X + (base + tid) * ldx;
-        rec[0] = y[base + tid];
+      float4* rec = reinterpret_cast<float4*>(sm + tid * REC);
 #pragma unroll
-        for (int d = 1; d < REC; ++d) rec[d] = d <= Dw ? xr[d - 1] : 0.0f;
-      } else {  // rows past the end: eta = 0 and y = 0 would still contribute f(0, 0); they are masked below
-#pragma unroll
-        for (int d = 0; d < REC; ++d) rec[d] = 0.0f;
-      }
+      for (int q = 0; q < REC4; ++q) rec[q] = make_float4(nx[4 * q], nx[4 * q + 1], nx[4 * q + 2], nx[4 * q + 3]);
     }
     __syncthreads();
-    for (int r0 = rl; r0 < nvalid; r0 += ROWS * RL) {
-      float rec[ROWS][REC];
-#pragma unroll
-      for (int u = 0; u < ROWS; ++u) {
-        const int r = min(r0 + u * RL, SD_CHUNK - 1);
-        const float4* rp = reinterpret_cast<const float4*>(sm + r * REC);
-#pragma unroll
-        for (int q = 0; q < REC4; ++q) {
-          const float4 v = rp[q];
-          rec[u][4 * q + 0] = v.x;
-          rec[u][4 * q + 1] = v.y;
-          rec[u][4 * q + 2] = v.z;
-          rec[u][4 * q + 3] = v.w;
-        }
-      }
-      float eta[ROWS];
-#pragma unroll
-      for (int u = 0; u < ROWS; ++u) eta[u] = 0.0f;
-#pragma unroll
-      for (int d = 1; d <= DWT; ++d)
-#pragma unroll
-        for (int u = 0; u < ROWS; ++u) eta[u] = fmaf(rec[u][d], th[d], eta[u]);
-#pragma unroll
-      for (int u = 0; u < ROWS; ++u) {
-        float f, g;
-        link_eval(family, rec[u][0], eta[u], f, g);
-        const bool ok = r0 + u * RL < nvalid;
-        stat += ok ? f : 0.0f;
-        g = ok ? g : 0.0f;
-#pragma unroll
-        for (int d = 1; d <= DWT; ++d) G[d] = fmaf(g, rec[u][d], G[d]);
-      }
-    }
+    if (base + SD_CHUNK < row_end) fetch(base + SD_CHUNK);
+    int r0 = rl;
+    for (; r0 + (ROWS - 1) * RL < nvalid; r0 += ROWS * RL) group(r0, nvalid, std::false_type{});  // every row of the group is valid
+    if (r0 < nvalid) group(r0, nvalid, std::true_type{});
   }
 
-  // deterministic reduction over the RL row lanes of this CTA
-  __syncthreads();
-  float* red = sm + (size_t)(rl * SB + sl) * (REC + 1);
+  // deterministic reduction over the RL row lanes of this CTA, one sample slot of the threads at a time (RL * SBT = 256 entries)
 #pragma unroll
-  for (int d = 0; d < REC; ++d) red[d] = G[d];
-  red[REC] = stat;
-  __syncthreads();
-  if (rl == 0 && s_ok) {
-    float acc[REC + 1];
+  for (int k = 0; k < SPT; ++k) {
+    __syncthreads();
+    float* red = sm + (size_t)(rl * SBT + sl) * (REC + 1);
 #pragma unroll
-    for (int d = 0; d <= REC; ++d) acc[d] = 0.0f;
-    for (int l = 0; l < RL; ++l) {
-      const float* rr = sm + (size_t)(l * SB + sl) * (REC + 1);
+    for (int d = 0; d < REC; ++d) red[d] = G[k][d];
+    red[REC] = stat[k];
+    __syncthreads();
+    if (rl == 0 && s_ok[k]) {
+      float acc[REC + 1];
 #pragma unroll
-      for (int d = 0; d <= REC; ++d) acc[d] += rr[d];
+      for (int d = 0; d <= REC; ++d) acc[d] = 0.0f;
+      for (int l = 0; l < RL; ++l) {
+        const float* rr = sm + (size_t)(l * SBT + sl) * (REC + 1);
+#pragma unroll
+        for (int d = 0; d <= REC; ++d) acc[d] += rr[d];
+      }
+      float* gp = Gpart + ((size_t)blockIdx.x * S + sidx[k]) * Dw;
+#pragma unroll
+      for (int d = 1; d < REC; ++d)
+        if (d <= Dw) gp[d - 1] = acc[d];
+      statpart[(size_t)blockIdx.x * S + sidx[k]] = acc[REC];
     }
-    float* gp = Gpart + ((size_t)blockIdx.x * S + s) * Dw;
-#pragma unroll
-    for (int d = 1; d < REC; ++d)
-      if (d <= Dw) gp[d - 1] = acc[d];
-    statpart[(size_t)blockIdx.x * S + s] = acc[REC];
   }
 }
 
@@ -120,10 +166,10 @@ int smalld_occupancy(int rec4) {
   cudaError_t e = cudaErrorInvalidValue;
   switch (rec4) {
     // (the widest column count of each record width: the most registers, a safe lower bound for the others)
-    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<1, 3>, 256, 0); break;
-    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<2, 7>, 256, 0); break;
-    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<3, 11>, 256, 0); break;
-    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<4, 15>, 256, 0); break;
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<1, 3, 2>, 256, 0); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<2, 7, 2>, 256, 0); break;
+    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<3, 11, 2>, 256, 0); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lik_smalld<4, 15, 2>, 256, 0); break;
     default: break;
   }
   return (e == cudaSuccess && occ > 0) ? occ : 1;
@@ -135,9 +181,22 @@ int launch_lik_smalld(const BjxElboArgs& a, const Plan& p, char* ws, cudaStream_
   float* statpart = (float*)(ws + p.o_statpart);
   const int64_t rows_per_cta = (a.N + p.sd_grid_x - 1) / p.sd_grid_x;
   dim3 grid(p.sd_grid_x, p.sd_grid_y);
-#define BJX_SD_LAUNCH(R4, DW)                                                                                      \
-  k_lik_smalld<R4, DW><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,   \
-                                             a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart)
+  // two samples per thread whenever the block has at least two (BJX_SD_SPT=1 keeps one: development switch)
+  static int spt_env = -1;
+  if (spt_env < 0) {
+    const char* e = getenv("BJX_SD_SPT");
+    spt_env = e ? atoi(e) : 2;
+  }
+  const bool two = p.sd_SB >= 2 && spt_env == 2;
+#define BJX_SD_LAUNCH(R4, DW)                                                                                            \
+  do {                                                                                                                   \
+    if (two)                                                                                                             \
+      k_lik_smalld<R4, DW, 2><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,   \
+                                                    a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart);               \
+    else                                                                                                                 \
+      k_lik_smalld<R4, DW, 1><<<grid, 256, 0, st>>>(a.X, a.ldx, a.y, a.N, (int)a.Dw, theta, a.D, a.w_offset, (int)a.S,   \
+                                                    a.likelihood, p.sd_SB, rows_per_cta, Gpart, statpart);               \
+  } while (0)
   switch ((int)a.Dw) {
     case 1: BJX_SD_LAUNCH(1, 1); break;
     case 2: BJX_SD_LAUNCH(1, 2); break;
