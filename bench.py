@@ -312,9 +312,10 @@ def small_config(cfg: str):
 
 
 def launches_per_step(kernel: str) -> int:
-    # k_prologue + likelihood + k_reduce_partials + k_tail + k_scalars (mean field); the tiny coin-toss step is one launch
-    # (two-pass GEMM path: + operand split of theta, pass 1, pass 2 instead of one likelihood launch)
-    return {"tcgen05_bf16_split": 5, "fp32_smalld": 5, "fp32_tiled": 6, "coin": 1, "tcgen05_gemm_two_pass": 7}[kernel]
+    # k_prologue + likelihood + k_reduce_partials + k_tail (mean field: its last block computes the loss and d kwargs, the former
+    # k_scalars launch); the tiny coin-toss step is one launch
+    # (two-pass GEMM path: + operand split of theta, pass 1, pass 2 instead of one likelihood launch, two partial reductions)
+    return {"tcgen05_bf16_split": 4, "fp32_smalld": 4, "fp32_tiled": 5, "coin": 1, "tcgen05_gemm_two_pass": 7}[kernel]
 
 
 def collect_kernel_ms(lib, nv, K):

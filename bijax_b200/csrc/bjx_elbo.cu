@@ -482,6 +482,45 @@ __device__ __forceinline__ float tau_of(const TailArgs& t, const float* kwargs, 
   return t.noise_value;
 }
 
+// loss = prior_weight * mean_s(q_s - p~_s) - ll_scale * mean_s ll_s ;  d kwargs          (one block of 256 threads)
+__device__ __forceinline__ void scalars_body(const TailArgs& t, int64_t K, int64_t Pn, const float* __restrict__ kwargs,
+                                             const float* __restrict__ theta, const float* __restrict__ qp_part, int n_qp,
+                                             const float* __restrict__ stat, const float* __restrict__ logdet,
+                                             float* __restrict__ out) {
+  __shared__ float red[32];
+  float qp = 0.0f;
+  for (int i = threadIdx.x; i < n_qp; i += 256) qp += qp_part[i];
+  qp = block_sum(qp, red);
+  float ll = 0.0f, dk = 0.0f;
+  for (int64_t s = threadIdx.x; s < t.S; s += 256) {
+    if (t.likelihood == BJX_LIK_GAUSSIAN) {
+      const float tau = tau_of(t, kwargs, theta, s);
+      const float q = stat[s] / (tau * tau);
+      ll += -0.5f * q - (float)t.N * (logf(tau) + BJX_HALF_LOG_2PI);
+      dk += q - (float)t.N;  // d ll_s / d log tau
+    } else {
+      ll += stat[s];
+    }
+  }
+  ll = block_sum(ll, red);
+  dk = block_sum(dk, red);
+  if (threadIdx.x == 0) {
+    const float invS = 1.0f / (float)t.S_total;
+    // low rank: q.log_prob carries -log|det A| once per sample of this call
+    const float qextra = logdet ? -logdet[0] * (float)t.S : 0.0f;
+    out[0] = t.prior_weight * (qp + qextra) * invS - t.ll_scale * ll * invS;
+    float* dkw = out + 1 + t.D + Pn;
+    for (int64_t k = 0; k < K; ++k) dkw[k] = 0.0f;
+    if (t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_KWARG) dkw[t.noise_index] = -t.ll_scale * dk * invS;
+  }
+}
+__global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t Pn, const float* __restrict__ kwargs,
+                                                 const float* __restrict__ theta, const float* __restrict__ qp_part,
+                                                 int n_qp, const float* __restrict__ stat, const float* __restrict__ logdet,
+                                                 float* __restrict__ out) {
+  scalars_body(t, K, Pn, kwargs, theta, qp_part, n_qp, stat, logdet, out);
+}
+
 // One WARP per latent coordinate d; lanes stride over the S samples, fixed-shape shuffle reduction (deterministic).
 //   gz[s,d] = prior_weight * (-d log p~ / dz) / S  -  (ll_scale / S) * dll_s/dtheta_d * b'(z)
 //   d loc[d] = sum_s gz;   d rho[d] = sigma'(rho) * sum_s gz * eps  -  prior_weight * dlog sigma / d rho     (mean field)
@@ -489,7 +528,14 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
                                               const float* __restrict__ eps, const float* __restrict__ theta,
                                               const float* __restrict__ bprime, const float* __restrict__ gprior,
                                               const float* __restrict__ G, const float* __restrict__ stat,
-                                              float* __restrict__ gz_out, float* __restrict__ out) {
+                                              float* __restrict__ gz_out, float* __restrict__ out,
+                                              int fuse_scalars, int64_t K, int64_t Pn, const float* __restrict__ qp_part, int n_qp) {
+  // fuse_scalars (mean field): one extra block at the end of the grid computes the loss and d kwargs -- they depend on the
+  // same reduced partials as this kernel, not on its results -- which saves the k_scalars launch
+  if (fuse_scalars && blockIdx.x == gridDim.x - 1) {
+    scalars_body(t, K, Pn, kwargs, theta, qp_part, n_qp, stat, nullptr, out);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t d = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (d >= t.D) return;
@@ -527,39 +573,6 @@ __global__ void __launch_bounds__(256) k_tail(TailArgs t, const float* __restric
       const ScaleEval sc = eval_scale(raw[d], t.scale_bij);
       out[1 + t.D + d] = t.point_mode ? 0.0f : acc_rho * sc.dsigma - t.entropy_weight * sc.dlogsigma;
     }
-  }
-}
-
-// loss = prior_weight * mean_s(q_s - p~_s) - ll_scale * mean_s ll_s ;  d kwargs
-__global__ void __launch_bounds__(256) k_scalars(TailArgs t, int64_t K, int64_t Pn, const float* __restrict__ kwargs,
-                                                 const float* __restrict__ theta, const float* __restrict__ qp_part,
-                                                 int n_qp, const float* __restrict__ stat, const float* __restrict__ logdet,
-                                                 float* __restrict__ out) {
-  __shared__ float red[32];
-  float qp = 0.0f;
-  for (int i = threadIdx.x; i < n_qp; i += 256) qp += qp_part[i];
-  qp = block_sum(qp, red);
-  float ll = 0.0f, dk = 0.0f;
-  for (int64_t s = threadIdx.x; s < t.S; s += 256) {
-    if (t.likelihood == BJX_LIK_GAUSSIAN) {
-      const float tau = tau_of(t, kwargs, theta, s);
-      const float q = stat[s] / (tau * tau);
-      ll += -0.5f * q - (float)t.N * (logf(tau) + BJX_HALF_LOG_2PI);
-      dk += q - (float)t.N;  // d ll_s / d log tau
-    } else {
-      ll += stat[s];
-    }
-  }
-  ll = block_sum(ll, red);
-  dk = block_sum(dk, red);
-  if (threadIdx.x == 0) {
-    const float invS = 1.0f / (float)t.S_total;
-    // low rank: q.log_prob carries -log|det A| once per sample of this call
-    const float qextra = logdet ? -logdet[0] * (float)t.S : 0.0f;
-    out[0] = t.prior_weight * (qp + qextra) * invS - t.ll_scale * ll * invS;
-    float* dkw = out + 1 + t.D + Pn;
-    for (int64_t k = 0; k < K; ++k) dkw[k] = 0.0f;
-    if (t.likelihood == BJX_LIK_GAUSSIAN && t.noise_src == BJX_NOISE_KWARG) dkw[t.noise_index] = -t.ll_scale * dk * invS;
   }
 }
 
@@ -820,10 +833,13 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
   t.point_mode = a.point_mode;
   t.S_total = a.S_total ? a.S_total : a.S;
   float* gz = a.vi_type != BJX_VI_MEAN_FIELD ? (float*)(ws + p.o_gz) : nullptr;
-  k_tail<<<(unsigned)((a.D + 7) / 8), 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
-                                                       (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
-                                                       (const float*)(ws + p.o_gprior), G, stat, gz, a.out);
+  const int fuse_scalars = a.vi_type == BJX_VI_MEAN_FIELD ? 1 : 0;
+  k_tail<<<(unsigned)((a.D + 7) / 8) + fuse_scalars, 256, 0, st>>>(t, a.raw_scale, a.kwargs, (const float*)(ws + p.o_eps),
+                                                                      (const float*)(ws + p.o_theta), (const float*)(ws + p.o_bprime),
+                                                                      (const float*)(ws + p.o_gprior), G, stat, gz, a.out, fuse_scalars,
+                                                                      a.K, p.Pn, (const float*)(ws + p.o_qp), p.n_qp_blocks);
   BJX_LAUNCH_CHECK("k_tail");
+  if (fuse_scalars) return BJX_OK;
   if (a.vi_type == BJX_VI_FULL_RANK) {
     if (p.fr_tc) {
       rc = launch_fullrank_dM_tc(a, gz, a.out + 1 + a.D, ws + p.o_fr_tc, t.entropy_weight, st);
