@@ -1175,6 +1175,337 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 }
 
 // =========================================================================================================================
+// Narrow problems (D <= 128) on TALL tiles: 128 data rows per tile instead of 64.
+//
+// At D = 128 a 64-row tile is only 32 KB -- 1360 cycles of HBM time per SM -- while the fixed costs of a tile (barrier
+// hand-overs, tcgen05.ld, the partner swap, the proxy fence in front of GEMM2) add up to a dependent chain of ~2000 cycles
+// (profiles/r02_envelope_narrow_groups.json), so the 64-row kernel stops at 0.70-0.77 of the roofline there however the
+// epilogue warps are arranged.  With 128 rows per tile the same fixed costs buy twice the bytes, and the accumulator layout
+// gets simpler: GEMM1 is  x1[128 rows] * [t1 | t2]  (M = 128, N = 64)  +  x2[128 rows] * t1  (M = 128, N = 32) into the SAME
+// TMEM columns, so TMEM lane r holds data row r completely (eta = acc[s] + acc[32 + s]) and the partner swap through
+// shared memory is gone, together with the wasted x2 * t2 quarter of the stacked M = 128 form.
+//   shared memory: 6 slots of 32 KB ([x1 block | x2 block], 128 rows x 64 columns each) = a ring of three tiles,
+//                  theta 16 KB, g 16 KB ([128 rows][e1 (32 samples) | e2 (32)], MN-major B of GEMM2 with K = 128 rows)
+//   TMEM: two logits accumulators (2 x 64 columns), G^T of the one 128-column chunk (64), its folded partial (32)
+//   warps: producer, MMA issuer, sixteen epilogue warps (sub-partition q = warp % 4, sample group h: 8 samples per thread)
+namespace tct {
+constexpr int ROWS = 128;
+constexpr int XBLK = ROWS * 128;  // one plane block: 16 KB
+constexpr int SLOT = 2 * XBLK;    // 32 KB
+constexpr int NBLK = 2, R = 3, NSLOT = NBLK * R;
+constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, EW = 16;
+constexpr int NTHREADS = (EPI_WARP0 + EW) * 32;
+constexpr int TMEM_COLS = 256, ACC1_COL = 0, ACC2_COL = 128, PART_COL = 192;
+struct Bars {
+  unsigned long long x_full[NSLOT], x_empty[NSLOT];
+  unsigned long long acc1_full[2], dl_full, dl_empty, done;
+  uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = (size_t)NSLOT * SLOT + NBLK * tc::BLK_BYTES + XBLK + sizeof(Bars) + 4 * tc::NS * sizeof(float) + 1024;
+}  // namespace tct
+
+__global__ void __launch_bounds__(tct::NTHREADS, 1)
+k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y, int64_t N,
+              const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
+              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
+              long long* __restrict__ trace) {
+#define BJX_TRACE(it_, slot_)                                                                 \
+  do {                                                                                        \
+    if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
+  } while (0)
+  using namespace tc;
+  using namespace tct;
+  constexpr int D = tct::NBLK * BLK_COLS;  // 128
+  constexpr int SG = NS / (EW / 4);        // samples per thread: 8
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx = smem;
+  uint8_t* sth = sx + NSLOT * SLOT;            // 2 blocks of [64 rows: t1 (32) | t2 (32)][64 bf16]
+  uint8_t* sdl = sth + tct::NBLK * BLK_BYTES;  // [128 rows][64 bf16: e1 (32 samples) | e2 (32)]
+  tct::Bars* bars = (tct::Bars*)(sdl + XBLK);
+  float* sred = (float*)(bars + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (N + ROWS - 1) / ROWS;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int b = 0; b < NSLOT; ++b) {
+      mbar_init(&bars->x_full[b], 1);
+      mbar_init(&bars->x_empty[b], 1);
+    }
+    mbar_init(&bars->acc1_full[0], 1);
+    mbar_init(&bars->acc1_full[1], 1);
+    mbar_init(&bars->dl_full, EW);
+    mbar_init(&bars->dl_empty, 1);
+    mbar_init(&bars->done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.x1);
+    tma_prefetch_desc(&maps.x2);
+  }
+  if (tid < 4 * NS) sred[tid] = 0.0f;
+  if (warp == tct::MMA_WARP) tmem_alloc(&bars->tmem_base, tct::TMEM_COLS);
+  for (int idx = tid; idx < NS * (D / 8); idx += NTHREADS) {
+    const int s = idx / (D / 8), d8 = idx % (D / 8);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (s < S && d8 * 8 + j < Dw) ? theta[(int64_t)s * Dtot + w_off + d8 * 8 + j] : 0.0f;
+    uint32_t p1[4], p2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], p1[j], p2[j]);
+    const int b = d8 / 8, c = d8 % 8;
+    uint8_t* blk = sth + b * BLK_BYTES;
+    *reinterpret_cast<uint4*>(blk + s * 128 + ((c ^ (s & 7)) << 4)) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    const int n2 = 32 + s;
+    *reinterpret_cast<uint4*>(blk + n2 * 128 + ((c ^ (n2 & 7)) << 4)) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == tct::PROD_WARP) {
+    // ===================================================== TMA producer ================================================
+    if (lane == 0) {
+      const __nv_bfloat16* p1 = planes;
+      const __nv_bfloat16* p2 = planes + (size_t)N * Dp;
+      const int pf_mode = pf_tiles >> 8, pf_ahead = (pf_tiles & 255) * R;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t row0 = (blockIdx.x + it * gridDim.x) * ROWS;
+        auto bulk_pf = [&]() {
+          const int64_t rowp = (blockIdx.x + (it + pf_ahead) * gridDim.x) * ROWS;
+          const int64_t rows = (N - rowp) < ROWS ? (N - rowp) : ROWS;
+          const uint32_t bytes = (uint32_t)(rows * Dp * 2);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p1 + rowp * Dp), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
+        };
+        if (pf_mode == 0 && pf_ahead > 0 && it + pf_ahead < my_tiles) bulk_pf();
+        const int q0 = (int)(it % R) * tct::NBLK;
+        const uint32_t use = (uint32_t)((it / R) & 1);
+        for (int b = 0; b < tct::NBLK; ++b) {
+          const int q = q0 + b;
+          mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
+          BJX_TRACE(it, b);
+          mbar_expect_tx(&bars->x_full[q], (uint32_t)SLOT);
+          tma_load_2d(sx + q * SLOT, &maps.x1, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+          tma_load_2d(sx + q * SLOT + XBLK, &maps.x2, b * BLK_COLS, (int32_t)row0, &bars->x_full[q]);
+        }
+        if (pf_mode == 1 && pf_ahead > 0 && it + pf_ahead < my_tiles) bulk_pf();
+      }
+    }
+  } else if (warp == tct::MMA_WARP) {
+    // ===================================================== MMA issuer ==================================================
+    constexpr uint32_t ID_G1_N64 = make_idesc(128, NB, 0, 0);   // x1 * [t1 | t2]
+    constexpr uint32_t ID_G1_N32 = make_idesc(128, NS, 0, 0);   // x2 * t1 into the first 32 columns
+    constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);       // x1^T * [e1 | e2]
+    constexpr uint32_t ID_G2_N32 = make_idesc(128, NS, 1, 1);   // x2^T * e1
+    const uint64_t dx1 = make_desc(smem_u32(sx), 16, 1024), dx2 = make_desc(smem_u32(sx + XBLK), 16, 1024);
+    const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
+    // GEMM2 (MN-major A): the two 64-column blocks of the chunk are one slot apart
+    const uint64_t tx1 = make_desc(smem_u32(sx), SLOT, 1024), tx2 = make_desc(smem_u32(sx + XBLK), SLOT, 1024);
+    const uint64_t tdl = make_desc(smem_u32(sdl), XBLK, 1024);
+    auto gemm1 = [&](int64_t t) {
+      const uint32_t acc = tmem + tct::ACC1_COL + ((t & 1) ? NB : 0);
+      for (int b = 0; b < tct::NBLK; ++b) {
+        const int q = (int)(t % R) * tct::NBLK + b;
+        mbar_wait(&bars->x_full[q], (uint32_t)((t / R) & 1));
+        if (lane == 0) BJX_TRACE(t, 16 + b);
+        if (!(ablate & 1) && elect_one()) {
+          const uint64_t xoff = (uint64_t)((q * SLOT) >> 4), toff = (uint64_t)((b * BLK_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(acc, dx1 + xoff + 2 * k, dth + toff + 2 * k, ID_G1_N64, (b | k) != 0);
+            umma_bf16(acc, dx2 + xoff + 2 * k, dth + toff + 2 * k, ID_G1_N32, 1);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bars->acc1_full[t & 1]);
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(t, 24);
+    };
+    int phase = 0;
+    if (my_tiles > 0) gemm1(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) gemm1(it + 1);  // other logits accumulator, slots already in the ring: runs under this tile's epilogue
+      mbar_wait(&bars->dl_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      if (lane == 0) BJX_TRACE(it, 25);
+      if (elect_one()) {
+        const int q0 = (int)(it % R) * tct::NBLK;
+        const uint64_t coff = (uint64_t)((q0 * SLOT) >> 4);
+#pragma unroll
+        for (int k = 0; k < ROWS / 16; ++k) {  // K = 16 rows = two 8-row swizzle atoms, 2048 bytes
+          if (ablate & 2) continue;
+          umma_bf16(tmem + tct::ACC2_COL, tx1 + coff + 128 * k, tdl + 128 * k, ID_G2, (k != 0) || !(it == 0 || phase == 0));
+          umma_bf16(tmem + tct::ACC2_COL, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
+        }
+        umma_commit(&bars->x_empty[q0]);
+        umma_commit(&bars->x_empty[q0 + 1]);
+        umma_commit(&bars->dl_empty);
+      }
+      __syncwarp();
+      if (lane == 0) BJX_TRACE(it, 26);
+      if (++phase == flush_tiles) phase = 0;
+    }
+    if (elect_one()) umma_commit(&bars->done);
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue =====================================================
+    const int q = warp & 3;                       // TMEM sub-partition: data rows 32q .. 32q + 31 of the tile
+    const int h = (warp - tct::EPI_WARP0) >> 2;   // sample group: samples 8h .. 8h + 7
+    const int r = 32 * q + lane;
+    const int s0 = h * SG;
+    float stat[SG], prod[SG];
+#pragma unroll
+    for (int j = 0; j < SG; ++j) {
+      stat[j] = 0.0f;
+      prod[j] = 1.0f;
+    }
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const bool logit = family == BJX_LIK_BERNOULLI_LOGITS;
+    float* gp = Gpart + (size_t)blockIdx.x * S * Dw;
+    // fold the GEMM2 accumulator (lanes = weight column d, columns [x*e1 (32) | x1*e2 (32)]) into the TMEM-resident partial
+    auto drain = [&](bool first, bool final) {
+      uint32_t fa[8], fb[8], fp[8];
+      tmem_ld8(t_lane + tct::ACC2_COL + s0, fa);
+      tmem_ld8(t_lane + tct::ACC2_COL + NS + s0, fb);
+      if (!first) tmem_ld8(t_lane + tct::PART_COL + s0, fp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float val = __uint_as_float(fa[j]) + __uint_as_float(fb[j]);
+        if (!first) val += __uint_as_float(fp[j]);
+        fp[j] = __float_as_uint(val);
+      }
+      if (final) {
+        const int d = r;  // lane of the accumulator = weight column
+        float* base = gp + (size_t)s0 * Dw + d;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (s0 + j < S && d < Dw) __stcg(base + (size_t)j * Dw, __uint_as_float(fp[j]));
+      } else {
+        tmem_st8(t_lane + tct::PART_COL + s0, fp);
+        tmem_st_wait();
+      }
+    };
+    int64_t row = (int64_t)blockIdx.x * ROWS + r;
+    float yv = (my_tiles > 0 && row < N) ? y[row] : 0.0f;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      if (it > 0 && it % flush_tiles == 0) {
+        mbar_wait(&bars->dl_empty, ph ^ 1);  // GEMM2 of the previous tile has retired; this tile's restarts the chain
+        tc_fence_after();
+        drain(it == flush_tiles, false);
+        tc_fence_before();
+      }
+      const bool row_ok = row < N;
+      const float ycur = yv;
+      row += (int64_t)gridDim.x * ROWS;
+      yv = (it + 1 < my_tiles && row < N) ? y[row] : 0.0f;
+      mbar_wait(&bars->acc1_full[it & 1], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (tid == tct::EPI_WARP0 * 32) BJX_TRACE(it, 32);
+      uint32_t va[SG], vb[SG];
+      const uint32_t acc1 = t_lane + tct::ACC1_COL + ((it & 1) ? NB : 0);
+      tmem_ld8(acc1 + s0, va);
+      tmem_ld8(acc1 + NS + s0, vb);
+      tmem_ld_wait();
+      if (tid == tct::EPI_WARP0 * 32) BJX_TRACE(it, 33);
+      float eta[SG], g[SG], ope[SG];
+#pragma unroll
+      for (int j = 0; j < SG; ++j) eta[j] = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+      const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * ROWS - r + ROWS <= N);  // warp-uniform
+      if (ablate & 4) {
+#pragma unroll
+        for (int j = 0; j < SG; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
+      } else if (logit) {
+        float e[SG], rc[SG];
+#pragma unroll
+        for (int j = 0; j < SG; ++j) e[j] = __expf(-fabsf(eta[j]));
+#pragma unroll
+        for (int j = 0; j < SG; ++j) ope[j] = 1.0f + e[j];
+#pragma unroll
+        for (int j = 0; j < SG; ++j) rc[j] = __fdividef(1.0f, ope[j]);
+#pragma unroll
+        for (int j = 0; j < SG; ++j) {
+          const float gj = ycur - (eta[j] >= 0.0f ? rc[j] : e[j] * rc[j]);
+          g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? gj : 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SG; ++j) {
+          const float rr = ycur - eta[j];
+          g[j] = (all_ok || (row_ok && (s0 + j) < S)) ? rr : 0.0f;
+        }
+      }
+      uint32_t e1[SG / 2], e2[SG / 2];
+#pragma unroll
+      for (int j = 0; j < SG / 2; ++j) split2(g[2 * j], g[2 * j + 1], e1[j], e2[j]);
+      if (tid == tct::EPI_WARP0 * 32) BJX_TRACE(it, 34);
+      mbar_wait(&bars->dl_empty, ph ^ 1);  // GEMM2 of the previous tile has consumed the g buffer
+      {
+        uint8_t* rowp = sdl + r * 128;
+        const int sw = r & 7;
+        // row layout: [e1: 32 samples x 2 B | e2: 32 x 2 B]; this thread's 8 samples are one 16-byte chunk of each half
+        *reinterpret_cast<uint4*>(rowp + ((h ^ sw) << 4)) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        *reinterpret_cast<uint4*>(rowp + (((4 + h) ^ sw) << 4)) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dl_full);
+      // ---- off the critical path: log-likelihood bookkeeping
+      if (!(ablate & 4)) {
+        if (logit) {
+#pragma unroll
+          for (int j = 0; j < SG; ++j) {
+            const bool ok = all_ok || (row_ok && (s0 + j) < S);
+            stat[j] += ok ? (ycur * eta[j] - fmaxf(eta[j], 0.0f)) : 0.0f;
+            prod[j] *= ok ? ope[j] : 1.0f;
+          }
+          if ((it & 31) == 31) {
+#pragma unroll
+            for (int j = 0; j < SG; ++j) {
+              stat[j] -= logf(prod[j]);
+              prod[j] = 1.0f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < SG; ++j) stat[j] = fmaf(g[j], g[j], stat[j]);  // g = y - eta, already masked
+        }
+      }
+      if (tid == tct::EPI_WARP0 * 32) BJX_TRACE(it, 35);
+    }
+#pragma unroll
+    for (int j = 0; j < SG; ++j) {
+      float v = stat[j] - logf(prod[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sred[q * NS + s0 + j] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
+    if (warp == tct::EPI_WARP0 && lane < S) {
+      statpart[(size_t)blockIdx.x * S + lane] = sred[lane] + sred[NS + lane] + sred[2 * NS + lane] + sred[3 * NS + lane];
+    }
+    mbar_wait(&bars->done, 0);
+    tc_fence_after();
+    if (my_tiles > 0) {
+      drain(my_tiles <= flush_tiles, true);
+    } else {
+      for (int i = (warp - tct::EPI_WARP0) * 32 + lane; i < S * Dw; i += EW * 32) gp[i] = 0.0f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == tct::MMA_WARP) tmem_dealloc(tmem, tct::TMEM_COLS);
+#undef BJX_TRACE
+}
+
+// =========================================================================================================================
 static int g_stagger = 600;          // start-up skew per phase group in SM cycles (BJX_TC_STAGGER overrides)
 static int g_ablate = 0;             // timing experiments only (BJX_TC_ABLATE bitmask: 1 no GEMM1, 2 no GEMM2, 4 no link math, 8 no convert/store)
 static int g_pf_mode = 0;            // 0 per-lane line prefetch by the loaders, 1 per-sector, 2 bulk prefetch by the MMA warp (BJX_TC_PFMODE)
@@ -1403,6 +1734,26 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
     if (epi_warps == 16) BJX_TCP_LAUNCH(NBLK, 16); \
     else BJX_TCP_LAUNCH(NBLK, 8);               \
   } while (0)
+    // D <= 128: tall tiles (128 rows, no partner swap; see k_lik_tc_tall).  BJX_TC_TALL=0 keeps the 64-row kernel.
+    static int tall = -1;
+    if (tall < 0) {
+      const char* e = getenv("BJX_TC_TALL");
+      tall = e ? atoi(e) : 1;
+    }
+    if (nblk == 2 && !idx && tall && !forced_ew) {
+      tcp::Maps mt;
+      if ((rc = make_bf16_tensor_map(&mt.x1, planes, plane_rows, Dp, Dp, tc::BLK_COLS, tct::ROWS))) return rc;
+      if ((rc = make_bf16_tensor_map(&mt.x2, planes + (size_t)plane_rows * Dp, plane_rows, Dp, Dp, tc::BLK_COLS, tct::ROWS))) return rc;
+      static DeviceOnce attr_set;
+      if (!attr_set.test_and_set()) {
+        BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::SMEM_BYTES));
+      }
+      const int flush_tall = getenv("BJX_TC_FLUSH") ? g_flush : 4;  // 4 tiles of 128 rows = the chain length of 8 tiles of 64
+      k_lik_tc_tall<<<p.tc_ctas, tct::NTHREADS, tct::SMEM_BYTES, st>>>(mt, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S,
+                                                                       a.likelihood, Gpart, statpart, pf_tiles, flush_tall, g_ablate, g_trace);
+      BJX_LAUNCH_CHECK("k_lik_tc_tall");
+      return BJX_OK;
+    }
     // D <= 128: two epilogue groups on alternate tiles (see the kernel).  A/B on one box (profiles/r02_envelope_narrow_groups.json):
     // the Gaussian link gains (0.71-0.72 -> 0.75-0.77 of the roofline at D = 128), the Bernoulli-logit link does not (0.70 either
     // way: sixteen warps on ONE tile shorten its longer MUFU chain just as much), so it keeps one group.  BJX_TC_EPI_GROUPS=1 / 2 forces.
