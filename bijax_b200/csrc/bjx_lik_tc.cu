@@ -1192,7 +1192,7 @@ namespace tct {
 constexpr int ROWS = 128;
 constexpr int XBLK = ROWS * 128;  // one plane block: 16 KB
 constexpr int SLOT = 2 * XBLK;    // 32 KB
-constexpr int NBLK = 2, R = 3, NSLOT = NBLK * R;
+constexpr int NSLOT = 6;  // a ring of three tiles of two blocks (64 < D <= 128) or of six tiles of one block (D <= 64)
 constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, EW = 16;
 constexpr int NTHREADS = (EPI_WARP0 + EW) * 32;
 constexpr int TMEM_COLS = 256, ACC1_COL = 0, ACC2_COL = 128, PART_COL = 192;
@@ -1201,9 +1201,13 @@ struct Bars {
   unsigned long long acc1_full[2], dl_full, dl_empty, done;
   uint32_t tmem_base;
 };
-constexpr size_t SMEM_BYTES = (size_t)NSLOT * SLOT + NBLK * tc::BLK_BYTES + XBLK + sizeof(Bars) + 4 * tc::NS * sizeof(float) + 1024;
+constexpr size_t smem_bytes(int nblk) { return (size_t)NSLOT * SLOT + nblk * tc::BLK_BYTES + XBLK + sizeof(Bars) + 4 * tc::NS * sizeof(float) + 1024; }
 }  // namespace tct
 
+// NBLK = 1 (D <= 64): the planes are 64 columns wide, so a tile is ONE block; GEMM2 then runs as M = 64 UMMAs (accumulator row d
+// in lane d % 16 of sub-partition d / 16) instead of dragging a zero block through shared memory and the tensor pipe -- at
+// 32 KB per tile the MMA time of two blocks alone (1408 cycles) exceeded the tile's HBM time (1360).
+template <int NBLK>
 __global__ void __launch_bounds__(tct::NTHREADS, 1)
 k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y, int64_t N,
               const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
@@ -1215,13 +1219,14 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
   } while (0)
   using namespace tc;
   using namespace tct;
-  constexpr int D = tct::NBLK * BLK_COLS;  // 128
+  constexpr int R = NSLOT / NBLK;
+  constexpr int D = NBLK * BLK_COLS;       // 128 or 64
   constexpr int SG = NS / (EW / 4);        // samples per thread: 8
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sx = smem;
   uint8_t* sth = sx + NSLOT * SLOT;            // 2 blocks of [64 rows: t1 (32) | t2 (32)][64 bf16]
-  uint8_t* sdl = sth + tct::NBLK * BLK_BYTES;  // [128 rows][64 bf16: e1 (32 samples) | e2 (32)]
+  uint8_t* sdl = sth + NBLK * BLK_BYTES;  // [128 rows][64 bf16: e1 (32 samples) | e2 (32)]
   tct::Bars* bars = (tct::Bars*)(sdl + XBLK);
   float* sred = (float*)(bars + 1);
 
@@ -1281,9 +1286,9 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2 + rowp * Dp), "r"(bytes) : "memory");
         };
         if (pf_mode == 0 && pf_ahead > 0 && it + pf_ahead < my_tiles) bulk_pf();
-        const int q0 = (int)(it % R) * tct::NBLK;
+        const int q0 = (int)(it % R) * NBLK;
         const uint32_t use = (uint32_t)((it / R) & 1);
-        for (int b = 0; b < tct::NBLK; ++b) {
+        for (int b = 0; b < NBLK; ++b) {
           const int q = q0 + b;
           mbar_wait(&bars->x_empty[q], use ^ 1);  // GEMM2 of tile it - R released this slot
           BJX_TRACE(it, b);
@@ -1298,8 +1303,8 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
     // ===================================================== MMA issuer ==================================================
     constexpr uint32_t ID_G1_N64 = make_idesc(128, NB, 0, 0);   // x1 * [t1 | t2]
     constexpr uint32_t ID_G1_N32 = make_idesc(128, NS, 0, 0);   // x2 * t1 into the first 32 columns
-    constexpr uint32_t ID_G2 = make_idesc(128, NB, 1, 1);       // x1^T * [e1 | e2]
-    constexpr uint32_t ID_G2_N32 = make_idesc(128, NS, 1, 1);   // x2^T * e1
+    constexpr uint32_t ID_G2 = make_idesc(64 * NBLK, NB, 1, 1);       // x1^T * [e1 | e2]
+    constexpr uint32_t ID_G2_N32 = make_idesc(64 * NBLK, NS, 1, 1);   // x2^T * e1
     const uint64_t dx1 = make_desc(smem_u32(sx), 16, 1024), dx2 = make_desc(smem_u32(sx + XBLK), 16, 1024);
     const uint64_t dth = make_desc(smem_u32(sth), 16, 1024);
     // GEMM2 (MN-major A): the two 64-column blocks of the chunk are one slot apart
@@ -1307,8 +1312,8 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
     const uint64_t tdl = make_desc(smem_u32(sdl), XBLK, 1024);
     auto gemm1 = [&](int64_t t) {
       const uint32_t acc = tmem + tct::ACC1_COL + ((t & 1) ? NB : 0);
-      for (int b = 0; b < tct::NBLK; ++b) {
-        const int q = (int)(t % R) * tct::NBLK + b;
+      for (int b = 0; b < NBLK; ++b) {
+        const int q = (int)(t % R) * NBLK + b;
         mbar_wait(&bars->x_full[q], (uint32_t)((t / R) & 1));
         if (lane == 0) BJX_TRACE(t, 16 + b);
         if (!(ablate & 1) && elect_one()) {
@@ -1333,7 +1338,7 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
       tc_fence_after();
       if (lane == 0) BJX_TRACE(it, 25);
       if (elect_one()) {
-        const int q0 = (int)(it % R) * tct::NBLK;
+        const int q0 = (int)(it % R) * NBLK;
         const uint64_t coff = (uint64_t)((q0 * SLOT) >> 4);
 #pragma unroll
         for (int k = 0; k < ROWS / 16; ++k) {  // K = 16 rows = two 8-row swizzle atoms, 2048 bytes
@@ -1342,7 +1347,7 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
           umma_bf16(tmem + tct::ACC2_COL, tx2 + coff + 128 * k, tdl + 128 * k, ID_G2_N32, 1);
         }
         umma_commit(&bars->x_empty[q0]);
-        umma_commit(&bars->x_empty[q0 + 1]);
+        if (NBLK == 2) umma_commit(&bars->x_empty[q0 + 1]);
         umma_commit(&bars->dl_empty);
       }
       __syncwarp();
@@ -1380,11 +1385,13 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
         fp[j] = __float_as_uint(val);
       }
       if (final) {
-        const int d = r;  // lane of the accumulator = weight column
+        // lane of the accumulator = weight column (M = 128), or lanes 0-15 of each sub-partition hold columns 16q .. 16q + 15 (M = 64)
+        const int d = NBLK == 2 ? r : 16 * q + (lane & 15);
+        const bool lane_ok = NBLK == 2 || lane < 16;
         float* base = gp + (size_t)s0 * Dw + d;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (s0 + j < S && d < Dw) __stcg(base + (size_t)j * Dw, __uint_as_float(fp[j]));
+          if (lane_ok && s0 + j < S && d < Dw) __stcg(base + (size_t)j * Dw, __uint_as_float(fp[j]));
       } else {
         tmem_st8(t_lane + tct::PART_COL + s0, fp);
         tmem_st_wait();
@@ -1417,7 +1424,13 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
 #pragma unroll
       for (int j = 0; j < SG; ++j) eta[j] = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
       const bool all_ok = (S == NS) && (row - (int64_t)gridDim.x * ROWS - r + ROWS <= N);  // warp-uniform
-      if (ablate & 4) {
+      if (s0 >= S) {  // warp-uniform: this sample group does not exist (S <= 24) -- its g is zero, no link maths
+#pragma unroll
+        for (int j = 0; j < SG; ++j) {
+          g[j] = 0.0f;
+          ope[j] = 1.0f;
+        }
+      } else if (ablate & 4) {
 #pragma unroll
         for (int j = 0; j < SG; ++j) g[j] = (row_ok && (s0 + j) < S) ? eta[j] : 0.0f;
       } else if (logit) {
@@ -1457,7 +1470,7 @@ k_lik_tc_tall(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __res
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dl_full);
       // ---- off the critical path: log-likelihood bookkeeping
-      if (!(ablate & 4)) {
+      if (!(ablate & 4) && s0 < S) {
         if (logit) {
 #pragma unroll
           for (int j = 0; j < SG; ++j) {
@@ -1741,16 +1754,23 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
       tall = e ? atoi(e) : 1;
     }
     if (nblk == 2 && !idx && tall && !forced_ew) {
+      const bool one_block = Dp <= tc::BLK_COLS;
+      const size_t smem_tall = tct::smem_bytes(one_block ? 1 : 2);
       tcp::Maps mt;
       if ((rc = make_bf16_tensor_map(&mt.x1, planes, plane_rows, Dp, Dp, tc::BLK_COLS, tct::ROWS))) return rc;
       if ((rc = make_bf16_tensor_map(&mt.x2, planes + (size_t)plane_rows * Dp, plane_rows, Dp, Dp, tc::BLK_COLS, tct::ROWS))) return rc;
       static DeviceOnce attr_set;
       if (!attr_set.test_and_set()) {
-        BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::SMEM_BYTES));
+        BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tall<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(1)));
+        BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tall<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(2)));
       }
       const int flush_tall = getenv("BJX_TC_FLUSH") ? g_flush : 4;  // 4 tiles of 128 rows = the chain length of 8 tiles of 64
-      k_lik_tc_tall<<<p.tc_ctas, tct::NTHREADS, tct::SMEM_BYTES, st>>>(mt, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S,
-                                                                       a.likelihood, Gpart, statpart, pf_tiles, flush_tall, g_ablate, g_trace);
+      if (one_block)
+        k_lik_tc_tall<1><<<p.tc_ctas, tct::NTHREADS, smem_tall, st>>>(mt, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S,
+                                                                      a.likelihood, Gpart, statpart, pf_tiles, flush_tall, g_ablate, g_trace);
+      else
+        k_lik_tc_tall<2><<<p.tc_ctas, tct::NTHREADS, smem_tall, st>>>(mt, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S,
+                                                                      a.likelihood, Gpart, statpart, pf_tiles, flush_tall, g_ablate, g_trace);
       BJX_LAUNCH_CHECK("k_lik_tc_tall");
       return BJX_OK;
     }

@@ -232,7 +232,7 @@ def test_step_through_a_row_index_equals_the_step_on_gathered_rows(D, S, N, B):
                                      (200, 32, 7000, 3333), (64, 16, 4000, 700), (500, 32, 6000, 6000)])
 def test_step_gathering_plane_rows_equals_the_step_on_gathered_rows(D, S, N, B):
     """BjxElboArgs.row_index + x_planes + N_full (ABI 4): the TMA-fed kernel gathering rows of the full dataset's planes with
-    16-byte cp.async copies gives, bit for bit, what it gives on the planes of the gathered rows -- repeated indices, B not a
+    16-byte cp.async copies gives, bit for bit (D > 128: the same tile schedule), what it gives on the planes of the gathered rows -- repeated indices, B not a
     multiple of the 64-row tile, every block count (ring and spare-slot schedules), widths padded by TMA zero fill."""
     dev = torch.device("cuda")
     X, y = C.synth_logistic(N, D)
@@ -253,7 +253,12 @@ def test_step_gathering_plane_rows_equals_the_step_on_gathered_rows(D, S, N, B):
     want = eng.step(key, loc, raw, None, Xg, yg, N / B, S).clone()  # prepares the planes of the gathered rows
     assert eng._planes is not None and eng.kernel_choice(S, B) == "tcgen05_bf16_split"
     got = eng.step(key, loc, raw, None, Xd, yg, N / B, S, row_index=idx, planes=full, n_full=N).clone()
-    assert torch.equal(got, want)
+    if D > 128:
+        assert torch.equal(got, want)
+    else:
+        # D <= 128: the contiguous step runs on 128-row tiles (k_lik_tc_tall), the gathering one on 64-row tiles -- the same
+        # products summed in a different order
+        C.assert_close(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol_scale=2e-6, what="gathered vs contiguous")
     with pytest.raises(nv.BjxError):  # planes of the full dataset without its row count
         eng.step(key, loc, raw, None, Xd, yg, N / B, S, row_index=idx, planes=full, n_full=0)
 
