@@ -330,7 +330,12 @@ def test_full_rank_contractions_on_the_tensor_cores(D, S, lik):
 
 
 @pytest.mark.parametrize("kernel,Dw,S,prepared", [("tcgen05_bf16_split", 256, 24, True), ("tcgen05_bf16_split", 256, 24, False),
-                                                  ("tcgen05_gemm_two_pass", 192, 70, True), ("tcgen05_gemm_two_pass", 192, 70, False)])
+                                                  ("tcgen05_gemm_two_pass", 192, 70, True), ("tcgen05_gemm_two_pass", 192, 70, False),
+                                                  # a pair of CTAs per tile (the second CTA's theta columns start at w_offset + 384),
+                                                  # 128-row tiles (two blocks / one block), each on prepared planes and on the in-step split
+                                                  ("tcgen05_bf16_split", 700, 32, True), ("tcgen05_bf16_split", 700, 12, False),
+                                                  ("tcgen05_bf16_split", 100, 32, True), ("tcgen05_bf16_split", 100, 9, False),
+                                                  ("tcgen05_bf16_split", 40, 32, True), ("tcgen05_bf16_split", 40, 17, False)])
 def test_tensor_core_paths_with_offset_weights_latent_noise_and_strided_X(kernel, Dw, S, prepared):
     """The weights are not the first latent (w_offset > 0: "a_first" sorts before "weights"), the Gaussian noise scale is a
     constrained latent (Gamma prior + Exp bijector), and X is a column slice of a wider matrix (row pitch ldx > Dw)."""
