@@ -484,6 +484,7 @@ k_lik_tc(const float* __restrict__ X, int64_t ldx, const float* __restrict__ y, 
 // on the shared-memory port: one producer thread, one MMA warp, eight epilogue warps (320 threads).
 namespace tcp {
 constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2;  // then EW (8 or 16) epilogue warps
+constexpr int GATHER_WARPS = 4;  // IDX: producer warps of the gather (warp 0 and GATHER_WARPS - 1 more after the epilogue warps)
 struct Maps {
   CUtensorMap x1, x2;
 };
@@ -511,7 +512,7 @@ struct BarsP {  // nine block slots: index 8 is the spare slot of block 0
 // cycles of HBM time per SM -- while one tile's epilogue is a dependent chain of ~1250 cycles (tcgen05.ld, partner swap,
 // MUFU, g store, fence, arrive): with one group the chain is exposed on every tile, with two it overlaps the other group's.
 template <int NBLK, int EW, bool IDX, bool PAIR, int NG = 1>  // per-CTA D / 64; epilogue warps (8 or 16); IDX adds a second producer warp
-__global__ void __launch_bounds__((tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, 1)
+__global__ void __launch_bounds__((tcp::EPI_WARP0 + EW + (IDX ? tcp::GATHER_WARPS - 1 : 0)) * 32, 1)
 k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __restrict__ planes, const float* __restrict__ y,
              int64_t N, const float* __restrict__ theta, int64_t Dtot, int64_t w_off, int Dw, int Dp, int S, int family,
              float* __restrict__ Gpart, float* __restrict__ statpart, int pf_tiles, int flush_tiles, int ablate,
@@ -521,8 +522,10 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
     if (trace != nullptr && blockIdx.x == 0 && (it_) >= 16 && (it_) < 24) trace[((it_)-16) * 64 + (slot_)] = clock64(); \
   } while (0)
   using namespace tc;
-  constexpr int NTHREADS = (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32;
-  constexpr int PROD_WARP2 = tcp::EPI_WARP0 + EW;  // IDX only: the second producer warp (one per operand plane)
+  constexpr int NTHREADS = (tcp::EPI_WARP0 + EW + (IDX ? tcp::GATHER_WARPS - 1 : 0)) * 32;
+  constexpr int PROD_WARP2 = tcp::EPI_WARP0 + EW;  // IDX only: the further producer warps start here
+  constexpr int GW = tcp::GATHER_WARPS;            // producer warps of the gather: (plane, group of rows) each
+  constexpr int GPW = 16 / (GW / 2);               // four-row groups per producer warp (16 groups = 64 rows per plane)
   constexpr int EWG = EW / NG;  // epilogue warps that work on one tile
   constexpr int HG = EWG / 4;   // groups of samples among the epilogue warps of one TMEM sub-partition
   constexpr int SG = NS / HG;   // samples whose partial logits a thread loads (16 or 8)
@@ -573,7 +576,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
 
   if (tid == 0) {
     for (int b = 0; b < 9; ++b) {
-      mbar_init(&bars->x_full[b], IDX ? 64 : 1);  // TMA: the producer's expect_tx arrival, completion counted in bytes;
+      mbar_init(&bars->x_full[b], IDX ? 32 * GW : 1);  // TMA: the producer's expect_tx arrival, completion counted in bytes;
                                                   // gather: one cp.async.mbarrier.arrive per lane of the two producer warps
       mbar_init(&bars->x_empty[b], 1);
     }
@@ -613,7 +616,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any store of mine can reach them
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == tcp::PROD_WARP || (IDX && warp == PROD_WARP2)) {
+  if (warp == tcp::PROD_WARP || (IDX && warp >= PROD_WARP2)) {
     // ===================================================== TMA producer ================================================
     if constexpr (IDX) {
       // Gather variant: TWO producer warps (one per operand plane: a single warp keeps only ~50 KB of copies in flight, 0.5
@@ -627,7 +630,10 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       // (tile::gather4 TMA loads were measured first: the copy engine retires one 512-byte gather4 per ~75 cycles, 0.27 of the
       // HBM roofline -- profiles/r02_minibatch_gather4_rejected.json.)
       const int r4 = lane >> 3, c = lane & 7;
-      const int pw = warp == tcp::PROD_WARP ? 0 : 1;  // which plane this warp copies
+      const int pwi = warp == tcp::PROD_WARP ? 0 : warp - PROD_WARP2 + 1;  // producer warp index 0 .. GW - 1
+      const int pw = pwi & 1;                                               // which plane this warp copies
+      const int g0 = (pwi >> 1) * GPW;                                      // its first four-row group
+      // (two warps, one per plane, keep ~100 KB of copies in flight; four were measured next -- profiles/r02_minibatch.json)
       const int64_t pitch = (int64_t)Dp * 2;
       const char* pl = reinterpret_cast<const char*>(planes) + (int64_t)pw * plane_rows * pitch;
       const int dst_plane = pw * BLK_BYTES;
@@ -636,24 +642,24 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
       // address -- the L2 touch two tiles ahead, the source rows one tile ahead -- reads the ring, never global memory, so
       // no dependent global load sits in front of a copy.
       int32_t stage0 = 0, stage1 = 0;
-      auto fetch_idx = [&](int64_t t) {  // -> registers (warp 0 of the pair)
-        if (pw != 0) return;
+      auto fetch_idx = [&](int64_t t) {  // -> registers (producer warp 0)
+        if (pwi != 0) return;
         const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS + 2 * lane;
         stage0 = (t < my_tiles && r0 < N) ? __ldg(ridx + r0) : 0;
         stage1 = (t < my_tiles && r0 + 1 < N) ? __ldg(ridx + r0 + 1) : 0;
       };
       auto park_idx = [&](int64_t t) {  // registers -> ring slot t % 4, visible to both producer warps
-        if (pw == 0) {
+        if (pwi == 0) {
           int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
           slot[2 * lane] = stage0;
           slot[2 * lane + 1] = stage1;
         }
-        asm volatile("bar.sync 14, 64;" ::: "memory");
+        asm volatile("bar.sync 14, %0;" ::"r"(32 * GW) : "memory");
       };
-      auto load_rows = [&](int64_t t, const char*(&rb)[16]) {
+      auto load_rows = [&](int64_t t, const char*(&rb)[GPW]) {
         const int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) rb[g] = pl + (int64_t)slot[4 * g + r4] * pitch + c * 16;
+        for (int g = 0; g < GPW; ++g) rb[g] = pl + (int64_t)slot[4 * (g0 + g) + r4] * pitch + c * 16;
       };
       // A row's eight 128-byte pieces (one per block) are copied at different times, and the X slots have no slack, so the
       // copies of tile t+1 can only be issued as GEMM2(t) releases its blocks: without help every tile pays a full random-
@@ -665,6 +671,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         const int32_t* slot = sidx + (int)(t & 3) * TILE_ROWS;
         const int64_t r0 = (blockIdx.x + t * gridDim.x) * TILE_ROWS;
         if (pf_kind == 3) {  // two rows per lane, the whole plane row (pitch bytes) in one request
+          if (pwi >= 2) return;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int r = 2 * lane + u;
@@ -675,7 +682,8 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         }
         if (c * 128 >= pitch) return;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
+        for (int gg = 0; gg < GPW; ++gg) {
+          const int g = g0 + gg;
           if (r0 + r4 + 4 * g < N) {
             const char* p = pl + (int64_t)slot[4 * g + r4] * pitch + c * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -687,12 +695,12 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
           }
         }
       };
-      auto issue = [&](uint8_t* slot, unsigned long long* bar, int b, const char* const(&rb)[16]) {
+      auto issue = [&](uint8_t* slot, unsigned long long* bar, int b, const char* const(&rb)[GPW]) {
         const uint32_t nbytes = (b * BLK_COLS < Dp) ? 16u : 0u;
         const int64_t boff = nbytes ? (int64_t)b * 128 : 0;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const int r = 4 * g + r4;
+        for (int g = 0; g < GPW; ++g) {
+          const int r = 4 * (g0 + g) + r4;
           cp_async16(slot + dst_plane + r * 128 + ((c ^ (r & 7)) << 4), rb[g] + boff, nbytes);
         }
         cp_async_mbar_arrive(bar);
@@ -702,7 +710,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         park_idx(t);
       }
       fetch_idx(3);
-      const char *cur[16], *nxt[16];
+      const char *cur[GPW], *nxt[GPW];
       load_rows(0, cur);
       prefetch_rows(0);
       prefetch_rows(1);
@@ -735,7 +743,7 @@ k_lik_tc_tma(const __grid_constant__ tcp::Maps maps, const __nv_bfloat16* __rest
         }
         prefetch_rows(it + 2);  // AFTER this tile's copies: touches issued first would queue ahead of the copies GEMM1 is waiting for
 #pragma unroll
-        for (int g = 0; g < 16; ++g) cur[g] = nxt[g];
+        for (int g = 0; g < GPW; ++g) cur[g] = nxt[g];
         park_idx(it + 3);   // fetched during the previous iteration; its ring slot held tile it - 1
         fetch_idx(it + 4);
       }
@@ -1692,7 +1700,7 @@ int launch_lik_tc(const BjxElboArgs& a_in, const Plan& p, char* ws, cudaStream_t
     if (!attr_set.test_and_set()) {                                                                                                      \
       BJX_CUDA_TRY(cudaFuncSetAttribute(k_lik_tc_tma<NBLK, EW, IDX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     }                                                                                                                     \
-    k_lik_tc_tma<NBLK, EW, IDX, false><<<p.tc_ctas, (tcp::EPI_WARP0 + EW + (IDX ? 1 : 0)) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
+    k_lik_tc_tma<NBLK, EW, IDX, false><<<p.tc_ctas, (tcp::EPI_WARP0 + EW + (IDX ? tcp::GATHER_WARPS - 1 : 0)) * 32, smem, st>>>(maps, planes, a.y, a.N, theta, a.D, a.w_offset, (int)a.Dw, (int)Dp, (int)a.S, \
                                                               a.likelihood, Gpart, statpart, idx ? pf_idx : pf_tiles, flush_tma, g_ablate, g_trace, a.row_index, plane_rows); \
   } while (0)
     // a pair of CTAs per tile: p.tc_ctas counts clusters
