@@ -130,6 +130,40 @@ def test_device_resident_training_loop_matches_the_host_driven_loop():
     assert torch.equal(eager["params"]["posterior"]["loc"], fused["params"]["posterior"]["loc"])
 
 
+@pytest.mark.parametrize("D", [100, 640])
+def test_graph_replayed_training_loop_on_the_tall_tile_and_cta_pair_kernels(D):
+    """The device-resident loop captured in CUDA graphs when the step's likelihood kernel is k_lik_tc_tall (D = 100) or the
+    cluster launch of the CTA-pair variant (D = 640: cudaLaunchKernelEx inside stream capture): graph replay equals the
+    eagerly enqueued loop bit for bit, and both follow the host-driven loop."""
+    from bijax_b200 import random as br
+    from bijax_b200 import utils as U
+    from functools import partial
+    from tests import cases as C
+
+    N = 6000
+    X, y = C.synth_logistic(N, D)
+    Xd, yd = torch.tensor(X, device="cuda"), torch.tensor(y, device="cuda")
+    model = bj.ADVI({"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D), scale_diag=np.ones(D))}, {}, lk.BernoulliLogits())
+    loss_fn = partial(model.loss_fn, outputs=yd, inputs={"X": Xd}, full_data_size=N, n_samples=16)
+    fresh = lambda: model.init(br.PRNGKey(0), initializer=lambda k, shape: 0.01 * br.normal(k, shape))
+    n = 2 * U.GRAPH_STEPS + 3
+    fused = bj.train(loss_fn, fresh(), optim.adam(0.01), n_epochs=n, seed=br.PRNGKey(3))
+    eng = next(iter(model._engines.values()))
+    assert eng.kernel_choice(16, N) == "tcgen05_bf16_split"
+    host = bj.train(loss_fn, fresh(), optim.adam(0.01), n_epochs=n, seed=br.PRNGKey(3), fused=False)
+    assert torch.allclose(fused["losses"], host["losses"], rtol=2e-5, atol=1e-5)
+    for k in ("loc", "scale_diag"):
+        assert torch.allclose(fused["params"]["posterior"][k], host["params"]["posterior"][k], rtol=1e-4, atol=1e-5)
+    old = U.GRAPH_STEPS
+    try:
+        U.GRAPH_STEPS = 10 ** 9
+        eager = bj.train(loss_fn, fresh(), optim.adam(0.01), n_epochs=n, seed=br.PRNGKey(3))
+    finally:
+        U.GRAPH_STEPS = old
+    assert torch.equal(eager["losses"], fused["losses"])
+    assert torch.equal(eager["params"]["posterior"]["loc"], fused["params"]["posterior"]["loc"])
+
+
 @pytest.mark.parametrize("vi", ["mean_field", "full_rank", "low_rank"])
 def test_posterior_log_prob_kernel_against_the_oracle(vi):
     """Posterior.log_prob (core.py:57-71) as one fused kernel: inverse bijector chains + log-det-Jacobians + diagonal /
