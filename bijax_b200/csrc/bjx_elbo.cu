@@ -420,12 +420,13 @@ __global__ void __launch_bounds__(256) k_lik_coin(const float* __restrict__ y, i
 }
 
 // ---- tail ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ Gpart, int PG, const float* __restrict__ statpart,
-                                                         int PS, int64_t SDw, int64_t S, float* __restrict__ G,
-                                                         float* __restrict__ stat) {
-  // block = 32 consecutive outputs (coalesced) x 8 warps striding over the partial slots; the eight per-warp sums are
+template <int W>  // warps per block: 8, or 32 when there are few outputs and many slots (c2: 384 outputs x 592 slots)
+__global__ void __launch_bounds__(W * 32) k_reduce_partials_w(const float* __restrict__ Gpart, int PG, const float* __restrict__ statpart,
+                                                              int PS, int64_t SDw, int64_t S, float* __restrict__ G,
+                                                              float* __restrict__ stat) {
+  // block = 32 consecutive outputs (coalesced) x W warps striding over the partial slots; the per-warp sums are
   // combined in a fixed order through shared memory, so the result does not depend on timing
-  __shared__ float red[8][33];
+  __shared__ float red[W][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   const float* src = nullptr;
@@ -437,23 +438,35 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
   } else if (i < SDw + S) {
     src = statpart + (i - SDw); P = PS; stride = S; dst = stat + (i - SDw);
   }
-  float t0 = 0.0f, t1 = 0.0f;
+  // four independent chains per warp: the loop is a chain of L2 latencies (148 slots at c3, 592 at c2), not of bytes
+  float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
   if (src != nullptr) {
     int p = w;
-    for (; p + 8 < P; p += 16) {
+    for (; p + 3 * W < P; p += 4 * W) {
       t0 += src[(size_t)p * stride];
-      t1 += src[(size_t)(p + 8) * stride];
+      t1 += src[(size_t)(p + W) * stride];
+      t2 += src[(size_t)(p + 2 * W) * stride];
+      t3 += src[(size_t)(p + 3 * W) * stride];
     }
-    if (p < P) t0 += src[(size_t)p * stride];
+    for (; p < P; p += W) t0 += src[(size_t)p * stride];
   }
-  red[w][lane] = t0 + t1;
+  red[w][lane] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (w == 0 && dst != nullptr) {
     float t = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    for (int k = 0; k < W; ++k) t += red[k][lane];
     *dst = t;
   }
+}
+// picks the block width: W = 32 when the grid would not even fill half of the SMs and the slots are many
+static void launch_reduce_partials(const float* Gpart, int PG, const float* statpart, int PS, int64_t SDw, int64_t S, float* G, float* stat,
+                                   cudaStream_t st) {
+  const unsigned blocks = (unsigned)((SDw + S + 31) / 32);
+  if (blocks < 64 && (PG > 64 || PS > 64))
+    k_reduce_partials_w<32><<<blocks, 1024, 0, st>>>(Gpart, PG, statpart, PS, SDw, S, G, stat);
+  else
+    k_reduce_partials_w<8><<<blocks, 256, 0, st>>>(Gpart, PG, statpart, PS, SDw, S, G, stat);
 }
 
 // Few partial slots and many outputs (the two-pass GEMM path: 9 K splits x S x Dw, 0.5 M outputs at c4): one thread per output
@@ -804,9 +817,8 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
     if (p.kernel == KERNEL_TC_BF16 && a.S > 32 && a.N > 0) {
       for (int64_t s0 = 0; s0 < a.S; s0 += 32) {  // partials are laid out [slice][CTA][S_slice, Dw]
         const int64_t Ss = a.S - s0 < 32 ? a.S - s0 : 32;
-        k_reduce_partials<<<(unsigned)((Ss * Dw + Ss + 31) / 32), 256, 0, st>>>(
-            (const float*)(ws + p.o_Gpart) + (size_t)p.PG * s0 * Dw, p.PG, (const float*)(ws + p.o_statpart) + (size_t)p.PS * s0, p.PS,
-            Ss * Dw, Ss, G + s0 * Dw, stat + s0);
+        launch_reduce_partials((const float*)(ws + p.o_Gpart) + (size_t)p.PG * s0 * Dw, p.PG,
+                               (const float*)(ws + p.o_statpart) + (size_t)p.PS * s0, p.PS, Ss * Dw, Ss, G + s0 * Dw, stat + s0, st);
         BJX_LAUNCH_CHECK("k_reduce_partials");
       }
     } else {
@@ -814,11 +826,9 @@ static int run_step(const BjxElboArgs& a, const Plan& p, cudaStream_t st, const 
       if (p.PG <= 16 && SDw >= 65536) {
         k_reduce_partials_few<<<(unsigned)((SDw + 255) / 256), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG, SDw, G);
         // the stat partials alone: outputs [SDw, SDw + S) of the general kernel, i.e. an empty G range
-        k_reduce_partials<<<(unsigned)((a.S + 31) / 32), 256, 0, st>>>(nullptr, 0, (const float*)(ws + p.o_statpart), p.PS, 0, a.S, G, stat);
+        launch_reduce_partials(nullptr, 0, (const float*)(ws + p.o_statpart), p.PS, 0, a.S, G, stat, st);
       } else {
-        k_reduce_partials<<<(unsigned)((SDw + a.S + 31) / 32), 256, 0, st>>>((const float*)(ws + p.o_Gpart), p.PG,
-                                                                              (const float*)(ws + p.o_statpart), p.PS, SDw,
-                                                                              a.S, G, stat);
+        launch_reduce_partials((const float*)(ws + p.o_Gpart), p.PG, (const float*)(ws + p.o_statpart), p.PS, SDw, a.S, G, stat, st);
       }
       BJX_LAUNCH_CHECK("k_reduce_partials");
     }
