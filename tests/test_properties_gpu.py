@@ -41,6 +41,27 @@ def test_random_small_problems_match_the_oracle(N, D, S, gauss, layout, softplus
     _run_case(model, ref, loc, raw, kwargs, y, X, 3 * N, seed % 1000, S, layout)
 
 
+@settings(max_examples=25, **_SETTINGS)
+@given(N=st.integers(1, 2500), D=st.integers(16, 1024), S=st.integers(1, 32), gauss=st.booleans(), prepared=st.booleans(),
+       seed=st.integers(0, 2**31 - 1))
+def test_random_widths_on_the_fused_tensor_core_kernels_match_the_oracle(N, D, S, gauss, prepared, seed):
+    """Any width in [16, 1024] with S <= 32 runs ONE pass over X on the tensor cores: 128-row tiles of one or two blocks (D <= 64,
+    D <= 128), 64-row tiles in a ring or with a spare slot (D <= 512), a cluster of two CTAs per tile (D <= 1024) -- ragged N,
+    widths that are not a multiple of anything, prepared planes or the in-step split, both likelihood families."""
+    prior = {"weights": tfd.MultivariateNormalDiag(loc=np.zeros(D, np.float32), scale_diag=np.ones(D, np.float32))}
+    if gauss:
+        X, y = C.synth_linear(N, D)
+        model, ref = C.build_pair(prior, {}, lk.GaussianLinear(), precision="bf16x2", prepare_dataset=prepared)
+        kwargs = {"log_noise_scale": np.float32(math.log(0.5))}
+    else:
+        X, y = C.synth_logistic(N, D)
+        model, ref = C.build_pair(prior, {}, lk.BernoulliLogits(), precision="bf16x2", prepare_dataset=prepared)
+        kwargs = {}
+    loc = 0.05 * tf.normal(tf.prng_key(seed), (D,), 1)
+    raw = np.full(D, math.log(0.1), np.float32)
+    _run_case(model, ref, loc, raw, kwargs, y, X, 4 * N, seed % 1000, S, 0, expect_kernel="tcgen05_bf16_split")
+
+
 @settings(max_examples=20, **_SETTINGS)
 @given(N=st.integers(1, 3000), D=st.sampled_from([3, 5, 15, 40, 128]), S=st.integers(1, 32), G=st.integers(2, 8), data=st.data())
 def test_row_shards_with_arbitrary_cuts_sum_to_the_unsharded_step(N, D, S, G, data):
