@@ -1582,6 +1582,7 @@ bool tc_eligible(const BjxElboArgs& a) {
   // row-index variant has no such fill, so a step without prepared planes splits X into the workspace first.
   if (a.Dw < 16 || a.Dw > 1024) return false;
   if (a.Dw > 512 && (a.row_index != nullptr || tc_pair_forced() < 0)) return false;  // the pair kernel has no gather variant (BJX_TC_PAIR=-1: off)
+  if (a.Dw > 512 && tc_max_clusters() <= 0) return false;  // no cluster of two CTAs can be resident here: the two-pass GEMM takes the shape
   if (a.row_index != nullptr && a.x_planes == nullptr) return false;  // no planes to gather from, and no in-step split of a full dataset
   return true;
 }
