@@ -19,6 +19,13 @@
 //               scoreboards between prefetch stages, which serialises them; depth comes from the number of warps.
 //   warp  16    MMA issuer (converged warp, elect.sync), owns the TMEM allocation
 //   warps 17-24 epilogue: tcgen05.ld logits -> link function -> bf16 split of g -> shared B operand of GEMM2
+//
+// Kernels in this file (launch_lik_tc picks one per shape; all read X exactly once):
+//   k_lik_tc<NBLK, IDX>                  raw fp32 X, converted to the split-bf16 image in registers (described above)
+//   k_lik_tc_tma<NBLK, EW, IDX, PAIR, NG> prepared planes, TMA-fed, 64-row tiles: 128 < D <= 512 (ring of tiles at D <= 256, spare
+//                                        slot above); IDX = rows gathered through an index with cp.async; PAIR = a cluster of two
+//                                        CTAs per tile, half of the columns each, for 512 < D <= 1024; NG = 2 epilogue groups
+//   k_lik_tc_tall<NBLK>                  prepared planes, TMA-fed, 128-row tiles without the partner swap: D <= 64 / D <= 128
 #include <cuda.h>
 
 #include <cstdlib>
